@@ -211,6 +211,11 @@ int rp_batch_sync(rp_batch* batch);
 int rp_batch_fetch_dense(rp_batch* batch, float* out, size_t out_floats);
 int rp_batch_fetch_sparse(rp_batch* batch, rp_rec* recs, size_t n_recs,
                           float* ups, size_t n_floats, rp_sparse_counts* counts);
+/* Same records, but left in DEVICE memory the caller owns (e.g. torch CUDA
+ * tensors handed to one ncclAllGather): no host copy, asynchronous on the
+ * context stream.  counts_dev receives n_pairs rp_sparse_counts. */
+int rp_batch_sparse_device(rp_batch* batch, void* recs_dev, size_t n_recs,
+                           void* ups_dev, size_t n_floats, void* counts_dev);
 /* log of the (unscaled) partition function per problem: 3 doubles per pair
  * (s1, s2, s1&s2); parity / debugging aid. */
 int rp_batch_fetch_logz(rp_batch* batch, double* logz, size_t n);

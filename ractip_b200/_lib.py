@@ -91,7 +91,7 @@ EXPORTS = [
     "rp_dense_plan", "rp_sparse_plan", "rp_create", "rp_destroy", "rp_last_error",
     "rp_strerror", "rp_set_stream", "rp_host_alloc", "rp_host_free", "rp_run_dense",
     "rp_run_sparse", "rp_batch_create", "rp_batch_run", "rp_batch_sync",
-    "rp_batch_fetch_dense", "rp_batch_fetch_sparse", "rp_batch_fetch_logz",
+    "rp_batch_fetch_dense", "rp_batch_fetch_sparse", "rp_batch_sparse_device", "rp_batch_fetch_logz",
     "rp_batch_destroy", "rp_last_timing", "rp_measure_peaks", "rp_zscore_shuffles",
     "rp_alg_flops_mcc", "rp_version",
 ]
@@ -132,6 +132,7 @@ def load() -> C.CDLL:
         "rp_batch_sync": (i, [vp]),
         "rp_batch_fetch_dense": (i, [vp, vp, sz]),
         "rp_batch_fetch_sparse": (i, [vp, vp, sz, vp, sz, vp]),
+        "rp_batch_sparse_device": (i, [vp, vp, sz, vp, sz, vp]),
         "rp_batch_fetch_logz": (i, [vp, vp, sz]),
         "rp_batch_destroy": (i, [vp]),
         "rp_last_timing": (i, [vp, P(RpTiming)]),

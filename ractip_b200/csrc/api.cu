@@ -1,0 +1,637 @@
+// api.cu -- the C ABI of include/ractip_prob.h over the CUDA kernels.
+//
+// Host-side mirror of what RactIP::solve does before it builds the IP
+// (reference src/ractip.cpp:546-548): for every pair, two single-strand
+// problems (rnafold: pair probabilities + unpaired windows) and one two-strand
+// problem (rnaduplex), batched over all pairs of a call -- the --zscore shuffle
+// loop (src/ractip.cpp:1638-1657) hands its whole batch over at once.
+//
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "dev_model.h"
+#include "kernels.h"
+#include "ractip_prob.h"
+#include "seq_encode.h"
+
+using rp::Problem;
+
+struct rp_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int ctas_per_sm = 0;
+  rp::DevModel* d_model = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  double* ws = nullptr;       // workspace slots (grow-only)
+  size_t ws_bytes = 0;
+  rp_timing timing = {};
+  bool timing_pending = false;
+  bool timed_copies = false;
+  std::string err;
+};
+
+struct rp_batch {
+  rp_ctx* ctx = nullptr;
+  int n_pairs = 0;
+  rp_opts opts = {};
+  std::vector<Problem> probs;
+  std::vector<int> order;
+  std::vector<rp_dense_layout> layout;
+  size_t total_floats = 0;
+  int maxn = 0;
+  int n_mcc = 0, n_duplex = 0;
+  size_t slot_doubles = 0;
+  double alg_flops = 0;
+  // device
+  uint8_t* d_seq = nullptr;
+  Problem* d_probs = nullptr;
+  int* d_order = nullptr;
+  int* d_counter = nullptr;
+  float* d_dense = nullptr;
+  double* d_logz = nullptr;
+  // sparse
+  std::vector<rp_sparse_layout> slayout;
+  size_t total_recs = 0, total_upf = 0;
+  rp::SparsePair* d_spairs = nullptr;
+  rp_rec* d_recs = nullptr;
+  float* d_ups = nullptr;
+  rp_sparse_counts* d_counts = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(rp_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(ctx, RP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+size_t bp_len(int L) { return (size_t)(L + 1) * (size_t)(L + 2) / 2; }
+
+int check_pairs(const rp_pair* pairs, int n_pairs, const rp_opts* opts) {
+  if (!pairs || !opts || n_pairs < 0) return RP_ERR_ARG;
+  for (int p = 0; p < n_pairs; p++)
+    if (!pairs[p].s1 || !pairs[p].s2 || pairs[p].n1 < 1 || pairs[p].n2 < 1) return RP_ERR_ARG;
+  return RP_OK;
+}
+
+int ensure_workspace(rp_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return RP_OK;
+  if (ctx->ws) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(ctx->ws));
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+  }
+  CU(cudaMalloc(&ctx->ws, bytes));
+  ctx->ws_bytes = bytes;
+  return RP_OK;
+}
+
+// number of CTAs (= workspace slots) for a batch
+int grid_for(const rp_ctx* ctx, int nprob, size_t slot_bytes) {
+  int g = ctx->sm_count * std::max(1, ctx->ctas_per_sm);
+  g = std::min(g, std::max(1, nprob));
+  // keep the workspace within a budget (long sequences: fewer, fatter slots)
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    size_t budget = (free_b + ctx->ws_bytes) / 10 * 7;
+    while (g > 1 && (size_t)g * slot_bytes > budget) g--;
+  }
+  return g;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rp_version(void) { return "ractip_b200 0.1 (sm_100a)"; }
+
+const char* rp_strerror(int code) {
+  switch (code) {
+    case RP_OK: return "ok";
+    case RP_ERR_ARG: return "bad argument";
+    case RP_ERR_NO_DEVICE: return "no usable CUDA device (the probability stage has no CPU fallback)";
+    case RP_ERR_CUDA: return "CUDA error";
+    case RP_ERR_IO: return "cannot read file";
+    case RP_ERR_FORMAT: return "malformed parameter data";
+    case RP_ERR_NO_DEFAULTS: return "requested energy tables are not embedded; load a parameter file";
+    case RP_ERR_SEQ: return "bad sequence";
+    case RP_ERR_TOO_LONG: return "sequence too long";
+    case RP_ERR_CAPACITY: return "output buffer too small";
+    case RP_ERR_UNSUPPORTED: return "unsupported model setting";
+    default: return "unknown error";
+  }
+}
+
+const char* rp_last_error(const rp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+void rp_opts_default(rp_opts* o) {
+  if (!o) return;
+  // defaults of src/cmdline.c:151-186 as mapped at src/ractip.cpp:1474-1498
+  o->max_w = 15; o->min_w = 5; o->th_ss = 0.5f; o->th_hy = 0.1f; o->th_ac = 0.003f; o->use_pf_duplex = 0;
+}
+
+int rp_dense_plan(const rp_pair* pairs, int n_pairs, const rp_opts* opts, rp_dense_layout* layout,
+                  size_t* total_floats) {
+  int rc = check_pairs(pairs, n_pairs, opts);
+  if (rc) return rc;
+  const size_t w = opts->max_w > 0 ? (size_t)opts->max_w : 0;
+  size_t off = 0;
+  for (int p = 0; p < n_pairs; p++) {
+    rp_dense_layout l;
+    l.n_bp1 = bp_len(pairs[p].n1); l.n_bp2 = bp_len(pairs[p].n2);
+    l.n_up1 = (size_t)pairs[p].n1 * w; l.n_up2 = (size_t)pairs[p].n2 * w;
+    l.n_hp = (size_t)(pairs[p].n1 + 1) * (size_t)(pairs[p].n2 + 1);
+    l.bp1 = off; off += l.n_bp1;
+    l.bp2 = off; off += l.n_bp2;
+    l.up1 = off; off += l.n_up1;
+    l.up2 = off; off += l.n_up2;
+    l.hp = off; off += l.n_hp;
+    if (layout) layout[p] = l;
+  }
+  if (total_floats) *total_floats = off;
+  return RP_OK;
+}
+
+int rp_sparse_plan(const rp_pair* pairs, int n_pairs, const rp_opts* opts, rp_sparse_layout* layout, size_t* total_recs,
+                   size_t* total_floats) {
+  int rc = check_pairs(pairs, n_pairs, opts);
+  if (rc) return rc;
+  const size_t w = opts->max_w > 0 ? (size_t)opts->max_w : 0;
+  // Each base pairs with total probability <= 1, so fewer than 1/th partners
+  // exceed th: at most n/(2 th) pairs inside one RNA, min(n1,n2)/th across.
+  auto cap_in = [&](int n) -> size_t {
+    size_t all = (size_t)n * (size_t)(n - 1) / 2;
+    if (!(opts->th_ss > 0.f)) return all;
+    return std::min(all, (size_t)std::floor(n / (2.0 * opts->th_ss)) + 1);
+  };
+  size_t roff = 0, foff = 0;
+  for (int p = 0; p < n_pairs; p++) {
+    rp_sparse_layout l;
+    l.cap_x = cap_in(pairs[p].n1);
+    l.cap_y = cap_in(pairs[p].n2);
+    size_t all = (size_t)pairs[p].n1 * (size_t)pairs[p].n2;
+    l.cap_z = !(opts->th_hy > 0.f) ? all
+                                   : std::min(all, (size_t)std::min(pairs[p].n1, pairs[p].n2) *
+                                                       ((size_t)std::floor(1.0 / opts->th_hy) + 1));
+    l.x = roff; roff += l.cap_x;
+    l.y = roff; roff += l.cap_y;
+    l.z = roff; roff += l.cap_z;
+    l.n_up1 = (size_t)pairs[p].n1 * w; l.n_up2 = (size_t)pairs[p].n2 * w;
+    l.up1 = foff; foff += l.n_up1;
+    l.up2 = foff; foff += l.n_up2;
+    if (layout) layout[p] = l;
+  }
+  if (total_recs) *total_recs = roff;
+  if (total_floats) *total_floats = foff;
+  return RP_OK;
+}
+
+double rp_alg_flops_mcc(int n) {
+  // F_mcc(n) = 6 I(n) + 2 S_in(n) + 2 S_out(n), TURN=3, MAXLOOP=30
+  if (n < 5) return 0.;
+  double I = 0, Sin = 0, Sout = 0;
+  for (int d = 4; d <= n - 1; d++) {
+    const int m = std::min(30, d - 6);
+    if (m >= 0) I += (double)(n - d) * (m + 1) * (m + 2) / 2.0;
+    Sin += (double)(n - d) * ((d - 2) + d + d);
+  }
+  for (int l = 5; l <= n; l++)
+    for (int k = 2; k <= l - 4; k++) Sout += std::max(0, n - l - 1) + (k - 2);
+  return 6. * I + 2. * Sin + 2. * Sout;
+}
+
+// ------------------------------------------------------------------ context
+int rp_create(rp_ctx** out, const rp_model* m, int device) {
+  rp_ctx* ctx = nullptr;
+  if (!out || !m) return fail(nullptr, RP_ERR_ARG, "rp_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return fail(nullptr, RP_ERR_NO_DEVICE,
+                std::string("rp_create: no CUDA device (") + (e == cudaSuccess ? "count 0" : cudaGetErrorString(e)) +
+                    "); the probability stage has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, RP_ERR_ARG, "rp_create: bad device index");
+  std::vector<rp::DevModel> host(1);
+  int rc = rp::build_dev_model(*m, host.data());
+  if (rc) return fail(nullptr, rc, "rp_create: unsupported model (temperature must be 37, dangles 2)");
+  ctx = new rp_ctx;
+  ctx->device = device;
+  auto bail = [&](int code, const std::string& msg) {
+    rp_destroy(ctx);
+    return fail(nullptr, code, msg);
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  ctx->stream = ctx->own_stream;
+  for (auto& ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&ctx->d_model, sizeof(rp::DevModel))) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMemcpy(ctx->d_model, host.data(), sizeof(rp::DevModel), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(RP_MCC_THREADS);
+  if (ctx->ctas_per_sm < 1)
+    return bail(RP_ERR_CUDA, "rp_create: kernel image not loadable on this device (built for sm_100a)");
+  *out = ctx;
+  return RP_OK;
+}
+
+int rp_destroy(rp_ctx* ctx) {
+  if (!ctx) return RP_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->d_model) cudaFree(ctx->d_model);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return RP_OK;
+}
+
+int rp_set_stream(rp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RP_ERR_ARG;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return RP_OK;
+}
+
+void* rp_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void rp_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// -------------------------------------------------------------------- batch
+int rp_batch_destroy(rp_batch* b) {
+  if (!b) return RP_OK;
+  if (b->ctx) {
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+  }
+  cudaFree(b->d_seq); cudaFree(b->d_probs); cudaFree(b->d_order); cudaFree(b->d_counter);
+  cudaFree(b->d_dense); cudaFree(b->d_logz);
+  cudaFree(b->d_spairs); cudaFree(b->d_recs); cudaFree(b->d_ups); cudaFree(b->d_counts);
+  delete b;
+  return RP_OK;
+}
+
+int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opts* opts, rp_batch** out) {
+  if (!ctx || !out) return fail(ctx, RP_ERR_ARG, "rp_batch_create: null argument");
+  *out = nullptr;
+  int rc = check_pairs(pairs, n_pairs, opts);
+  if (rc) return fail(ctx, rc, "rp_batch_create: bad pairs/opts");
+  CU(cudaSetDevice(ctx->device));
+  rp_batch* b = new rp_batch;
+  b->ctx = ctx;
+  b->n_pairs = n_pairs;
+  b->opts = *opts;
+  b->layout.resize(n_pairs);
+  rp_dense_plan(pairs, n_pairs, opts, b->layout.data(), &b->total_floats);
+  b->slayout.resize(n_pairs);
+  rp_sparse_plan(pairs, n_pairs, opts, b->slayout.data(), &b->total_recs, &b->total_upf);
+
+  // encoded sequences: per pair  0 s1 0 s2 0 s1s2 0
+  std::vector<uint8_t> seq;
+  size_t bytes = 0;
+  for (int p = 0; p < n_pairs; p++) bytes += 2 * ((size_t)pairs[p].n1 + pairs[p].n2) + 4;
+  seq.reserve(bytes + 16);
+  const int w = opts->max_w > 0 ? opts->max_w : 0;
+  size_t ws_need = 0;
+  for (int p = 0; p < n_pairs; p++) {
+    const rp_pair& pr = pairs[p];
+    const rp_dense_layout& L = b->layout[p];
+    seq.push_back(0);
+    const int off1 = (int)seq.size();
+    for (int i = 0; i < pr.n1; i++) seq.push_back(rp::encode_base(pr.s1[i]));
+    seq.push_back(0);
+    const int off2 = (int)seq.size();
+    for (int i = 0; i < pr.n2; i++) seq.push_back(rp::encode_base(pr.s2[i]));
+    seq.push_back(0);
+    const int off12 = (int)seq.size();
+    for (int i = 0; i < pr.n1; i++) seq.push_back(rp::encode_base(pr.s1[i]));
+    for (int i = 0; i < pr.n2; i++) seq.push_back(rp::encode_base(pr.s2[i]));
+    seq.push_back(0);
+    Problem q;
+    std::memset(&q, 0, sizeof q);
+    q.pair = p; q.max_w = w; q.n1 = pr.n1; q.n2 = pr.n2; q.th_hy = opts->th_hy;
+    q.out_bp = q.out_up = q.out_hp = -1;
+    // rnafold(fa1, ...), rnafold(fa2, ...)  src/ractip.cpp:546-547
+    Problem a = q;
+    a.kind = rp::KIND_LINEAR; a.which = 0; a.seq_off = off1; a.n = pr.n1; a.cp = 0;
+    a.out_bp = (long long)L.bp1; a.out_up = w > 0 ? (long long)L.up1 : -1;
+    b->probs.push_back(a);
+    a.which = 1; a.seq_off = off2; a.n = pr.n2;
+    a.out_bp = (long long)L.bp2; a.out_up = w > 0 ? (long long)L.up2 : -1;
+    b->probs.push_back(a);
+    // rnaduplex(fa1, fa2, hp_)  src/ractip.cpp:548
+    Problem c = q;
+    c.which = 2; c.seq_off = off12; c.out_hp = (long long)L.hp;
+    if (opts->use_pf_duplex) {
+      c.kind = rp::KIND_DUPLEX; c.n = pr.n1 + pr.n2; c.cp = pr.n1 + 1;
+      b->n_duplex++;
+      ws_need = std::max(ws_need, 2 * (size_t)(pr.n1 + 2) * (size_t)(pr.n2 + 2));
+    } else {
+      c.kind = rp::KIND_COFOLD; c.n = pr.n1 + pr.n2; c.cp = pr.n1 + 1;
+      b->maxn = std::max(b->maxn, c.n);
+      b->alg_flops += rp_alg_flops_mcc(c.n);
+    }
+    b->probs.push_back(c);
+    b->maxn = std::max(b->maxn, std::max(pr.n1, pr.n2));
+    b->alg_flops += rp_alg_flops_mcc(pr.n1) + rp_alg_flops_mcc(pr.n2);
+  }
+  b->n_mcc = (int)b->probs.size() - b->n_duplex;
+  b->slot_doubles = std::max(rp::slot_doubles(b->maxn), ws_need);
+  // queue order: most expensive first (LPT), ties by index for determinism
+  b->order.resize(b->probs.size());
+  std::iota(b->order.begin(), b->order.end(), 0);
+  std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) {
+    auto cost = [&](const Problem& q) { return q.kind == rp::KIND_DUPLEX ? 0.0 : (double)q.n * q.n * (q.n + 1500.0); };
+    return cost(b->probs[x]) > cost(b->probs[y]);
+  });
+
+  auto bail = [&](cudaError_t e, const char* what) {
+    rp_batch_destroy(b);
+    return fail(ctx, RP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  cudaError_t e;
+  const size_t np = b->probs.size();
+  if ((e = cudaMalloc(&b->d_seq, seq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc seq");
+  if ((e = cudaMalloc(&b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
+  if ((e = cudaMalloc(&b->d_order, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
+  if ((e = cudaMalloc(&b->d_counter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
+  if ((e = cudaMalloc(&b->d_dense, std::max<size_t>(1, b->total_floats) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense");
+  if ((e = cudaMalloc(&b->d_logz, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logz");
+  cudaStream_t st = ctx->stream;
+  if ((e = cudaMemcpyAsync(b->d_seq, seq.data(), seq.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D seq");
+  if (np) {
+    if ((e = cudaMemcpyAsync(b->d_probs, b->probs.data(), np * sizeof(Problem), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D probs");
+    if ((e = cudaMemcpyAsync(b->d_order, b->order.data(), np * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D order");
+  }
+  if ((e = cudaMemsetAsync(b->d_logz, 0, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double), st)) != cudaSuccess) return bail(e, "memset logz");
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "sync");  // host vectors go out of scope
+  *out = b;
+  return RP_OK;
+}
+
+int rp_batch_run(rp_batch* b) {
+  if (!b) return RP_ERR_ARG;
+  rp_ctx* ctx = b->ctx;
+  CU(cudaSetDevice(ctx->device));
+  const int nprob = (int)b->probs.size();
+  ctx->timing = rp_timing{};
+  ctx->timing.alg_flops = b->alg_flops;
+  if (nprob == 0) { ctx->timing_pending = false; return RP_OK; }
+  const size_t slot_bytes = b->slot_doubles * sizeof(double);
+  const int grid = grid_for(ctx, nprob, slot_bytes);
+  int rc = ensure_workspace(ctx, (size_t)grid * slot_bytes);
+  if (rc) return rc;
+  rp::BatchDev d;
+  d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order; d.nprob = nprob;
+  d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = grid;
+  d.dense = b->d_dense; d.logz = b->d_logz;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(b->d_counter, 0, sizeof(int), st));
+  CU(cudaEventRecord(ctx->ev[0], st));
+  int launches = 0;
+  if (b->n_mcc > 0) {
+    CU(rp::launch_mcc(d, grid, RP_MCC_THREADS, st));
+    launches++;
+  }
+  if (b->n_duplex > 0) {
+    CU(rp::launch_duplex(d, std::min(grid, nprob), st));
+    launches++;
+  }
+  CU(cudaEventRecord(ctx->ev[1], st));
+  ctx->timing.kernel_launches = launches;
+  ctx->timing_pending = true;
+  ctx->timed_copies = false;
+  return RP_OK;
+}
+
+int rp_batch_sync(rp_batch* b) {
+  if (!b) return RP_ERR_ARG;
+  rp_ctx* ctx = b->ctx;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RP_OK;
+}
+
+int rp_batch_fetch_dense(rp_batch* b, float* out, size_t out_floats) {
+  if (!b || !out) return RP_ERR_ARG;
+  rp_ctx* ctx = b->ctx;
+  if (out_floats < b->total_floats) return fail(ctx, RP_ERR_CAPACITY, "rp_batch_fetch_dense: buffer too small");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (b->total_floats)
+    CU(cudaMemcpyAsync(out, b->d_dense, b->total_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->timed_copies = true;
+  return RP_OK;
+}
+
+}  // extern "C" (reopened below)
+
+namespace {
+int sparse_prepare(rp_batch* b) {
+  rp_ctx* ctx = b->ctx;
+  const int np = b->n_pairs;
+  if (b->d_spairs || np == 0) return RP_OK;
+  std::vector<rp::SparsePair> sp(np);
+  for (int p = 0; p < np; p++) {
+    const rp_dense_layout& L = b->layout[p];
+    const rp_sparse_layout& S = b->slayout[p];
+    rp::SparsePair& q = sp[p];
+    q.n1 = b->probs[3 * p].n; q.n2 = b->probs[3 * p + 1].n;
+    q.bp1 = (long long)L.bp1; q.bp2 = (long long)L.bp2; q.hp = (long long)L.hp;
+    q.x = (long long)S.x; q.y = (long long)S.y; q.z = (long long)S.z;
+    q.cap_x = (int)S.cap_x; q.cap_y = (int)S.cap_y; q.cap_z = (int)S.cap_z;
+    q.up1_src = (long long)L.up1; q.up2_src = (long long)L.up2;
+    q.up1_dst = (long long)S.up1; q.up2_dst = (long long)S.up2;
+    q.n_up1 = (int)S.n_up1; q.n_up2 = (int)S.n_up2;
+  }
+  CU(cudaMalloc(&b->d_spairs, np * sizeof(rp::SparsePair)));
+  CU(cudaMemcpy(b->d_spairs, sp.data(), np * sizeof(rp::SparsePair), cudaMemcpyHostToDevice));
+  return RP_OK;
+}
+
+int sparse_launch(rp_batch* b, rp_rec* d_recs, float* d_ups, rp_sparse_counts* d_counts) {
+  rp_ctx* ctx = b->ctx;
+  rp::SparseDev s;
+  s.pairs = b->d_spairs; s.dense = b->d_dense; s.recs = d_recs; s.ups = d_ups; s.counts = d_counts;
+  s.th_ss = b->opts.th_ss; s.th_hy = b->opts.th_hy;
+  CU(cudaMemsetAsync(d_counts, 0, b->n_pairs * sizeof(rp_sparse_counts), ctx->stream));
+  CU(rp::launch_sparse(s, b->n_pairs, ctx->stream));
+  ctx->timing.kernel_launches += 2;
+  return RP_OK;
+}
+}  // namespace
+
+extern "C" int rp_batch_sparse_device(rp_batch* b, void* recs_dev, size_t n_recs, void* ups_dev, size_t n_floats,
+                                      void* counts_dev) {
+  if (!b || !recs_dev || !counts_dev || (!ups_dev && b->total_upf)) return RP_ERR_ARG;
+  rp_ctx* ctx = b->ctx;
+  if (n_recs < b->total_recs || n_floats < b->total_upf)
+    return fail(ctx, RP_ERR_CAPACITY, "rp_batch_sparse_device: buffer too small");
+  CU(cudaSetDevice(ctx->device));
+  if (b->n_pairs == 0) return RP_OK;
+  int rc = sparse_prepare(b);
+  if (rc) return rc;
+  return sparse_launch(b, static_cast<rp_rec*>(recs_dev), static_cast<float*>(ups_dev),
+                       static_cast<rp_sparse_counts*>(counts_dev));
+}
+
+extern "C" int rp_batch_fetch_sparse(rp_batch* b, rp_rec* recs, size_t n_recs, float* ups, size_t n_floats,
+                                     rp_sparse_counts* counts) {
+  if (!b || !recs || !counts || (!ups && b->total_upf)) return RP_ERR_ARG;
+  rp_ctx* ctx = b->ctx;
+  if (n_recs < b->total_recs || n_floats < b->total_upf)
+    return fail(ctx, RP_ERR_CAPACITY, "rp_batch_fetch_sparse: buffer too small");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int np = b->n_pairs;
+  if (np == 0) return RP_OK;
+  int rc = sparse_prepare(b);
+  if (rc) return rc;
+  if (!b->d_recs) {
+    CU(cudaMalloc(&b->d_recs, std::max<size_t>(1, b->total_recs) * sizeof(rp_rec)));
+    CU(cudaMalloc(&b->d_ups, std::max<size_t>(1, b->total_upf) * sizeof(float)));
+    CU(cudaMalloc(&b->d_counts, np * sizeof(rp_sparse_counts)));
+  }
+  rc = sparse_launch(b, b->d_recs, b->d_ups, b->d_counts);
+  if (rc) return rc;
+  CU(cudaEventRecord(ctx->ev[2], st));
+  if (b->total_recs) CU(cudaMemcpyAsync(recs, b->d_recs, b->total_recs * sizeof(rp_rec), cudaMemcpyDeviceToHost, st));
+  if (b->total_upf) CU(cudaMemcpyAsync(ups, b->d_ups, b->total_upf * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(counts, b->d_counts, np * sizeof(rp_sparse_counts), cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(ctx->ev[3], st));
+  CU(cudaStreamSynchronize(st));
+  ctx->timed_copies = true;
+  for (int p = 0; p < np; p++)
+    if (counts[p].overflow) return fail(ctx, RP_ERR_CAPACITY, "rp_batch_fetch_sparse: record capacity exceeded");
+  return RP_OK;
+}
+
+extern "C" {
+
+int rp_batch_fetch_logz(rp_batch* b, double* logz, size_t n) {
+  if (!b || !logz) return RP_ERR_ARG;
+  rp_ctx* ctx = b->ctx;
+  if (n < (size_t)b->n_pairs * 3) return fail(ctx, RP_ERR_CAPACITY, "rp_batch_fetch_logz: buffer too small");
+  CU(cudaSetDevice(ctx->device));
+  if (b->n_pairs)
+    CU(cudaMemcpyAsync(logz, b->d_logz, (size_t)b->n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RP_OK;
+}
+
+int rp_last_timing(const rp_ctx* cctx, rp_timing* t) {
+  if (!cctx || !t) return RP_ERR_ARG;
+  rp_ctx* ctx = const_cast<rp_ctx*>(cctx);
+  if (ctx->timing_pending) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->timing.ms_total = ms;
+    if (ctx->timed_copies) {
+      CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+      ctx->timing.ms_d2h = ms;
+    }
+    ctx->timing_pending = false;
+  }
+  *t = ctx->timing;
+  return RP_OK;
+}
+
+// ------------------------------------------------------- one-shot host calls
+int rp_run_dense(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opts* opts, float* out, size_t out_floats) {
+  if (!ctx || !out) return fail(ctx, RP_ERR_ARG, "rp_run_dense: null argument");
+  rp_batch* b = nullptr;
+  int rc = rp_batch_create(ctx, pairs, n_pairs, opts, &b);
+  if (rc) return rc;
+  if (out_floats < b->total_floats) {
+    rp_batch_destroy(b);
+    return fail(ctx, RP_ERR_CAPACITY, "rp_run_dense: buffer too small");
+  }
+  rc = rp_batch_run(b);
+  if (!rc) rc = rp_batch_fetch_dense(b, out, out_floats);
+  rp_timing t;
+  if (!rc) rp_last_timing(ctx, &t);
+  rp_batch_destroy(b);
+  return rc;
+}
+
+int rp_run_sparse(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opts* opts, rp_rec* recs, size_t n_recs,
+                  float* ups, size_t n_floats, rp_sparse_counts* counts) {
+  if (!ctx || !recs || !counts) return fail(ctx, RP_ERR_ARG, "rp_run_sparse: null argument");
+  rp_batch* b = nullptr;
+  int rc = rp_batch_create(ctx, pairs, n_pairs, opts, &b);
+  if (rc) return rc;
+  rc = rp_batch_run(b);
+  if (!rc) rc = rp_batch_fetch_sparse(b, recs, n_recs, ups, n_floats, counts);
+  rp_timing t;
+  if (!rc) rp_last_timing(ctx, &t);
+  rp_batch_destroy(b);
+  return rc;
+}
+
+// ------------------------------------------------------------------- peaks
+int rp_measure_peaks(rp_ctx* ctx, double* fp64_tflops, double* smem_gbs) {
+  if (!ctx) return RP_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const int grid = ctx->sm_count * 8, threads = 256;
+  double* d_out = nullptr;
+  CU(cudaMalloc(&d_out, (size_t)grid * threads * sizeof(double)));
+  cudaStream_t st = ctx->stream;
+  float best_f = 1e30f, best_s = 1e30f;
+  const int it_f = 1 << 15, it_s = 1 << 12;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(cudaEventRecord(ctx->ev[4], st));
+    CU(rp::launch_peak_fp64(d_out, grid, it_f, st));
+    CU(cudaEventRecord(ctx->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    if (rep > 0) best_f = std::min(best_f, ms);
+    CU(cudaEventRecord(ctx->ev[4], st));
+    CU(rp::launch_peak_smem(d_out, grid, it_s, st));
+    CU(cudaEventRecord(ctx->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    if (rep > 0) best_s = std::min(best_s, ms);
+  }
+  CU(cudaFree(d_out));
+  if (fp64_tflops) *fp64_tflops = 2.0 * 8 * (double)it_f * grid * threads / (best_f * 1e-3) / 1e12;
+  if (smem_gbs) *smem_gbs = 8.0 * 16 * (double)it_s * grid * threads / (best_s * 1e-3) / 1e9;
+  return RP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// kernels.cu -- sm_100a kernels of the probability stage.
+//
+// mcc_persistent: one CTA per problem *slot*.  Each CTA pulls problems (one
+// RNA, or one two-strand concatenation) from a global queue ordered by
+// decreasing cost, runs the whole inside/outside/unpaired-window pipeline of
+// mcc_driver.h on it inside its private HBM workspace slot, writes the fp32
+// results in the reference's layouts, and pulls the next one.  The grid is
+// sized to the number of CTAs that are simultaneously resident
+// (SMs x occupancy), so the whole shuffle batch is ONE launch.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "mcc_driver.h"
+
+namespace rp {
+
+namespace {
+
+struct CtaExec {
+  __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+  template <class F>
+  __device__ __forceinline__ void phase(F f) {
+    f(threadIdx.x);
+    __syncthreads();
+  }
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(RP_MCC_THREADS, RP_MCC_MIN_CTAS) mcc_persistent(BatchDev b) {
+  extern __shared__ double part[];  // 3 * blockDim.x
+  __shared__ int s_next;
+  CtaExec ex;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(b.counter, 1);
+    __syncthreads();
+    const int q = s_next;
+    __syncthreads();
+    if (q >= b.nprob) break;
+    const Problem p = b.probs[b.order[q]];
+    if (p.kind == KIND_DUPLEX) continue;  // handled by duplex_kernel
+    Ctx c;
+    bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)blockIdx.x * b.slot_stride);
+    solve_mcc(ex, c, p, b.dense, b.logz, part);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pf_duplex (--duplex): log-space forward/backward over pure duplexes.
+// Restates reference src/pf_duplex.c:128-164 (fw), :166-206 (bk), :97-103 (pr)
+// with LogAdd of :34-40.  One CTA per problem; cells on the wavefront
+// w = i + (n2 - j) are independent (every predecessor (k,l) has k<i, l>j).
+// The backward table is computed in the equivalent pull form
+//   bk(k,l) = logsum( close(k,l), bk(i,j) - E(k,l;i,j)  for i>k, j<l ).
+// ---------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double log_add(double x, double y) {
+  if (x == -INFINITY) return y;
+  if (y == -INFINITY) return x;
+  return x > y ? log1p(exp(y - x)) + x : log1p(exp(x - y)) + y;
+}
+
+__device__ __forceinline__ int i_ext_loop(const DevModel& M, int type, int s5, int s3) {
+  int e = 0;
+  if (s5 >= 0 && s3 >= 0) e += M.i_mmExt[type][s5][s3];
+  else if (s5 >= 0) e += M.i_dangle5[type][s5];
+  else if (s3 >= 0) e += M.i_dangle3[type][s3];
+  if (type > 2) e += M.i_TermAU;
+  return e;
+}
+
+__device__ __forceinline__ int i_int_loop(const DevModel& M, int n1, int n2, int type, int type2, int si1, int sj1,
+                                          int sp1, int sq1) {
+  const int nl = n1 > n2 ? n1 : n2, ns = n1 > n2 ? n2 : n1;
+  if (nl == 0) return M.i_stack[type][type2];
+  if (ns == 0) {
+    int e = M.i_bulge[nl];
+    if (nl == 1) e += M.i_stack[type][type2];
+    else {
+      if (type > 2) e += M.i_TermAU;
+      if (type2 > 2) e += M.i_TermAU;
+    }
+    return e;
+  }
+  if (ns == 1) {
+    if (nl == 1) return M.i_int11[type][type2][si1][sj1];
+    if (nl == 2) return n1 == 1 ? M.i_int21[type][type2][si1][sq1][sj1] : M.i_int21[type2][type][sq1][si1][sp1];
+    int e = M.i_internal[nl + 1];
+    e += min(M.i_MAX_NINIO, (nl - ns) * M.i_ninio);
+    return e + M.i_mm1n[type][si1][sj1] + M.i_mm1n[type2][sq1][sp1];
+  }
+  if (ns == 2) {
+    if (nl == 2) return M.i_int22[type][type2][si1][sp1][sq1][sj1];
+    if (nl == 3) return M.i_internal[5] + M.i_ninio + M.i_mm23[type][si1][sj1] + M.i_mm23[type2][sq1][sp1];
+  }
+  int e = M.i_internal[nl + ns];
+  e += min(M.i_MAX_NINIO, (nl - ns) * M.i_ninio);
+  return e + M.i_mmI[type][si1][sj1] + M.i_mmI[type2][sq1][sp1];
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) duplex_kernel(BatchDev b) {
+  __shared__ double red[256];
+  const DevModel& M = *b.model;
+  for (int q = blockIdx.x; q < b.nprob; q += gridDim.x) {
+    const Problem p = b.probs[q];
+    if (p.kind != KIND_DUPLEX) continue;
+    const int n1 = p.n1, n2 = p.n2;
+    const uint8_t* A = b.seq + p.seq_off - 1;       // A[1..n1]
+    const uint8_t* B = A + n1;                      // B[1..n2] (stored right after s1)
+    double* ws = b.ws + (size_t)(blockIdx.x % b.nslots) * b.slot_stride;
+    const int ld = n2 + 2;
+    double* fw = ws;
+    double* bk = ws + (size_t)(n1 + 2) * ld;
+    const double kT = M.kT;
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int x = tid; x < (n1 + 2) * ld; x += T) { fw[x] = -INFINITY; bk[x] = -INFINITY; }
+    __syncthreads();
+    // forward: wavefront w = i + (n2 - j), i in 1..n1, j in 1..n2
+    double esum = -INFINITY;
+    for (int w = 1; w <= n1 + n2 - 1; w++) {
+      for (int i = 1 + tid; i <= n1; i += T) {
+        const int j = n2 - (w - i);
+        if (j < 1 || j > n2) continue;
+        const int type = pair_type(A[i] & 7, B[j] & 7);
+        if (!type) continue;
+        int E = M.i_DuplexInit + i_ext_loop(M, type, i > 1 ? (A[i - 1] & 7) : -1, j < n2 ? (B[j + 1] & 7) : -1);
+        double f = -E * 10. / kT;
+        for (int k = i - 1; k > 0 && k > i - MAXLOOP - 2; k--)
+          for (int l = j + 1; l <= n2; l++) {
+            if (i - k + l - j - 2 > MAXLOOP) break;
+            const int type2 = pair_type(A[k] & 7, B[l] & 7);
+            if (!type2) continue;
+            E = i_int_loop(M, i - k - 1, l - j - 1, type2, rtype(type), A[k + 1] & 7, B[l - 1] & 7, A[i - 1] & 7,
+                           B[j + 1] & 7);
+            f = log_add(f, fw[k * ld + l] - E * 10. / kT);
+          }
+        fw[i * ld + j] = f;
+        E = i_ext_loop(M, rtype(type), j > 1 ? (B[j - 1] & 7) : -1, i < n1 ? (A[i + 1] & 7) : -1);
+        esum = log_add(esum, f - E * 10. / kT);
+      }
+      __syncthreads();
+    }
+    // reduce the per-thread partial log-sums (fixed order: deterministic)
+    red[tid] = esum;
+    __syncthreads();
+    if (tid == 0) {
+      double s = -INFINITY;
+      for (int t = 0; t < T; t++) s = log_add(s, red[t]);
+      red[0] = s;
+    }
+    __syncthreads();
+    const double Esum = red[0];
+    __syncthreads();
+    // backward, pull form: wavefront from the far corner (i=n1, j=1) inwards
+    for (int w = n1 + n2 - 1; w >= 1; w--) {
+      for (int k = 1 + tid; k <= n1; k += T) {
+        const int l = n2 - (w - k);
+        if (l < 1 || l > n2) continue;
+        const int type2 = pair_type(A[k] & 7, B[l] & 7);
+        if (!type2) continue;
+        int E = i_ext_loop(M, rtype(type2), l > 1 ? (B[l - 1] & 7) : -1, k < n1 ? (A[k + 1] & 7) : -1);
+        double v = -E * 10. / kT;
+        for (int i = k + 1; i <= n1 && i < k + MAXLOOP + 2; i++)
+          for (int j = l - 1; j >= 1; j--) {
+            if (i - k + l - j - 2 > MAXLOOP) break;
+            const int type = pair_type(A[i] & 7, B[j] & 7);
+            if (!type) continue;
+            E = i_int_loop(M, i - k - 1, l - j - 1, type2, rtype(type), A[k + 1] & 7, B[l - 1] & 7, A[i - 1] & 7,
+                           B[j + 1] & 7);
+            v = log_add(v, bk[i * ld + j] - E * 10. / kT);
+          }
+        bk[k * ld + l] = v;
+      }
+      __syncthreads();
+    }
+    if (p.out_hp >= 0) {
+      float* hp = b.dense + p.out_hp;
+      for (int x = tid; x < (n1 + 1) * (n2 + 1); x += T) {
+        const int i = x / (n2 + 1), j = x % (n2 + 1);
+        hp[x] = (i >= 1 && j >= 1) ? (float)exp(fw[i * ld + j] + bk[i * ld + j] - Esum) : 0.f;
+      }
+    }
+    if (b.logz && tid == 0) b.logz[(size_t)p.pair * 3 + 2] = Esum;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// thresholded records in the reference's variable-creation order
+// (src/ractip.cpp:557-567 for x/y: j ascending, i descending; :598-609 for z:
+// i ascending, j ascending).  One warp per list: ballot + popcount keeps order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(96) sparse_kernel(SparseDev s) {
+  const int pair = blockIdx.x;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const SparsePair sp = s.pairs[pair];
+  int count = 0, overflow = 0;
+  if (warp < 2) {
+    const int L = warp == 0 ? sp.n1 : sp.n2;
+    const float* bp = s.dense + (warp == 0 ? sp.bp1 : sp.bp2);
+    rp_rec* out = s.recs + (warp == 0 ? sp.x : sp.y);
+    const int cap = warp == 0 ? sp.cap_x : sp.cap_y;
+    // scan order: j = 1..L-1 (0-based), i = j-1..0  -> linear index within column j
+    for (int j = 1; j < L; j++) {
+      for (int i0 = j - 1; i0 >= 0; i0 -= 32) {
+        const int i = i0 - lane;
+        float p = 0.f;
+        bool hit = false;
+        if (i >= 0) {
+          const int I = i + 1, J = j + 1;
+          p = bp[(size_t)I * (2 * L + 1 - I) / 2 + J];
+          hit = p > s.th_ss;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int pos = count + __popc(m & ((1u << lane) - 1));
+          if (pos < cap) { out[pos].i = i; out[pos].j = j; out[pos].p = p; }
+        }
+        count += __popc(m);
+      }
+    }
+    if (count > cap) overflow = 1;
+  } else {
+    const float* hp = s.dense + sp.hp;
+    rp_rec* out = s.recs + sp.z;
+    const int total = sp.n1 * sp.n2;
+    for (int x0 = 0; x0 < total; x0 += 32) {
+      const int x = x0 + lane;
+      float p = 0.f;
+      bool hit = false;
+      int i = 0, j = 0;
+      if (x < total) {
+        i = x / sp.n2; j = x % sp.n2;
+        p = hp[(size_t)(i + 1) * (sp.n2 + 1) + (j + 1)];
+        hit = p > s.th_hy;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = count + __popc(m & ((1u << lane) - 1));
+        if (pos < sp.cap_z) { out[pos].i = i; out[pos].j = j; out[pos].p = p; }
+      }
+      count += __popc(m);
+    }
+    if (count > sp.cap_z) overflow = 1;
+  }
+  if (lane == 0) {
+    int* cnt = reinterpret_cast<int*>(&s.counts[pair]);
+    cnt[warp] = count;
+    if (overflow) atomicOr(&cnt[3], 1);
+  }
+}
+
+// gather the up sections of the dense buffer into the compact float buffer
+__global__ void gather_up_kernel(SparseDev s) {
+  const SparsePair sp = s.pairs[blockIdx.x];
+  for (int x = threadIdx.x; x < sp.n_up1; x += blockDim.x) s.ups[sp.up1_dst + x] = s.dense[sp.up1_src + x];
+  for (int x = threadIdx.x; x < sp.n_up2; x += blockDim.x) s.ups[sp.up2_dst + x] = s.dense[sp.up2_src + x];
+}
+
+// ---------------------------------------------------------------------------
+// roofline denominators measured live: fp64 FMA pipe and shared-memory reads
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peak_fp64_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void __launch_bounds__(256) peak_smem_kernel(double* out, int iters) {
+  __shared__ double buf[4096];
+  for (int x = threadIdx.x; x < 4096; x += blockDim.x) buf[x] = x;
+  __syncthreads();
+  double acc = 0;
+  int idx = threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) acc += buf[(idx + u * 256) & 4095];
+    idx = (idx + 1) & 4095;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// host-callable launchers
+// ---------------------------------------------------------------------------
+int mcc_max_ctas_per_sm(int threads) {
+  int n = 0;
+  size_t smem = 3 * sizeof(double) * threads;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mcc_persistent, threads, smem) != cudaSuccess) return 0;
+  return n;
+}
+
+cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, cudaStream_t st) {
+  size_t smem = 3 * sizeof(double) * threads;
+  mcc_persistent<<<grid, threads, smem, st>>>(b);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st) {
+  duplex_kernel<<<grid, 256, 0, st>>>(b);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sparse(const SparseDev& s, int n_pairs, cudaStream_t st) {
+  sparse_kernel<<<n_pairs, 96, 0, st>>>(s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  gather_up_kernel<<<n_pairs, 256, 0, st>>>(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peak_fp64(double* out, int grid, int iters, cudaStream_t st) {
+  peak_fp64_kernel<<<grid, 256, 0, st>>>(out, iters);
+  return cudaGetLastError();
+}
+cudaError_t launch_peak_smem(double* out, int grid, int iters, cudaStream_t st) {
+  peak_smem_kernel<<<grid, 256, 0, st>>>(out, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace rp

@@ -1,0 +1,60 @@
+// kernels.h -- launch interface between the C-ABI host layer and kernels.cu
+#ifndef RP_KERNELS_H
+#define RP_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mcc_core.h"
+#include "ractip_prob.h"
+
+#ifndef RP_MCC_THREADS
+#define RP_MCC_THREADS 256
+#endif
+#ifndef RP_MCC_MIN_CTAS
+#define RP_MCC_MIN_CTAS 2
+#endif
+
+namespace rp {
+
+struct BatchDev {
+  const DevModel* model;
+  const uint8_t* seq;      // encoded sequences, one zero byte of padding around each
+  const Problem* probs;
+  const int* order;        // problem indices by decreasing cost
+  int nprob;
+  int* counter;            // work-queue head
+  double* ws;              // nslots workspace slots
+  size_t slot_stride;      // doubles per slot
+  int nslots;
+  float* dense;            // dense fp32 outputs (reference layouts)
+  double* logz;            // 3 per pair, may be null
+};
+
+struct SparsePair {
+  int n1, n2;
+  long long bp1, bp2, hp;              // float offsets into the dense buffer
+  long long x, y, z;                   // record offsets
+  int cap_x, cap_y, cap_z;
+  long long up1_src, up2_src, up1_dst, up2_dst;
+  int n_up1, n_up2;
+};
+
+struct SparseDev {
+  const SparsePair* pairs;
+  const float* dense;
+  rp_rec* recs;
+  float* ups;
+  rp_sparse_counts* counts;
+  float th_ss, th_hy;
+};
+
+int mcc_max_ctas_per_sm(int threads);
+cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, cudaStream_t st);
+cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st);
+cudaError_t launch_sparse(const SparseDev& s, int n_pairs, cudaStream_t st);
+cudaError_t launch_peak_fp64(double* out, int grid, int iters, cudaStream_t st);
+cudaError_t launch_peak_smem(double* out, int grid, int iters, cudaStream_t st);
+
+}  // namespace rp
+#endif

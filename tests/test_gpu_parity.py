@@ -1,0 +1,243 @@
+"""Parity of the CUDA probability stage (through the C ABI) with the CPU oracle.
+
+Bars (BASELINE.json north_star): every probability within 1e-6 absolute of the fp64
+reference path; identical thresholded variable sets.  The outputs are fp32 casts of fp64
+values (src/ractip.cpp:367,375,453), so agreement is checked at float resolution:
+|diff| <= 2e-7 on values in [0,1] (one fp32 ulp at 1.0 is 1.2e-7), far inside the 1e-6 bar.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import rand_seq
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-7          # fp32 ulp-level; the north_star bar is 1e-6
+BAR = 1e-6
+
+
+def _oracle_pair(oracle, s1, s2, opts):
+    bp1, up1 = oracle.rnafold(s1, opts.max_w)
+    bp2, up2 = oracle.rnafold(s2, opts.max_w)
+    hp = oracle.rnaduplex(s1, s2, opts.th_hy, bool(opts.use_pf_duplex))
+    return bp1, up1, bp2, up2, hp
+
+
+def _threshold_sets(bp1, up1, bp2, up2, hp, n1, n2, opts):
+    """Variable lists in the reference's creation order (src/ractip.cpp:557-567,578-588,598-609,621-627)."""
+    def xs(bp, L):
+        out = []
+        off = [i * (2 * L + 1 - i) // 2 for i in range(L + 1)]
+        for j in range(1, L):
+            for i in range(j - 1, -1, -1):
+                if bp[off[i + 1] + j + 1] > np.float32(opts.th_ss):
+                    out.append((i, j))
+        return out
+    z = [(i, j) for i in range(n1) for j in range(n2) if hp[i + 1][j + 1] > np.float32(opts.th_hy)]
+    def vs(up):
+        return [(i, i + j) for i in range(up.shape[0]) for j in range(opts.min_w - 1, up.shape[1])
+                if up[i][j] > np.float32(opts.th_ac)]
+    return xs(bp1, n1), xs(bp2, n2), z, vs(up1), vs(up2)
+
+
+def _near_threshold(a, th, eps=3e-7):
+    return np.abs(a.astype(np.float64) - float(np.float32(th))) < eps
+
+
+def _compare(res, ora, s1, s2, opts, tag=""):
+    bp1, up1, bp2, up2, hp = ora
+    for name, got, want in [("bp1", res.bp1, bp1), ("bp2", res.bp2, bp2), ("up1", res.up1, up1), ("up2", res.up2, up2)]:
+        d = np.abs(got.astype(np.float64) - want.astype(np.float64)).max() if got.size else 0.0
+        assert d <= TOL, (tag, name, d)
+    # hp is thresholded: entries within float noise of th_hy may legitimately differ in presence
+    mism = (res.hp != 0) != (hp != 0)
+    if mism.any():
+        dense = np.where(res.hp != 0, res.hp, hp)
+        assert _near_threshold(dense[mism], opts.th_hy).all(), (tag, "hp support")
+    both = (res.hp != 0) & (hp != 0)
+    if both.any():
+        assert np.abs(res.hp[both].astype(np.float64) - hp[both]).max() <= TOL, (tag, "hp")
+
+
+def test_bundled_pairs_one_ragged_batch(stage, oracle, bundled):
+    """All 8 bundled pairs in one call: dense parity and identical variable sets."""
+    from ractip_b200 import default_opts
+    opts = default_opts()
+    pairs = [(bundled["sequences"][a], bundled["sequences"][b]) for a, b in bundled["pairs"]]
+    res = stage.run_dense(pairs, opts)
+    assert stage.last_timing().kernel_launches >= 1
+    for (a, b), (s1, s2), r in zip(bundled["pairs"], pairs, res):
+        ora = _oracle_pair(oracle, s1, s2, opts)
+        _compare(r, ora, s1, s2, opts, f"{a}x{b}")
+        got = _threshold_sets(r.bp1, r.up1, r.bp2, r.up2, r.hp, len(s1), len(s2), opts)
+        want = _threshold_sets(*ora, len(s1), len(s2), opts)
+        for g, w, nm, arr, th in zip(got, want, "xyzvw", (r.bp1, r.bp2, r.hp, r.up1, r.up2),
+                                     (opts.th_ss, opts.th_ss, opts.th_hy, opts.th_ac, opts.th_ac)):
+            if g != w:  # only values sitting on the threshold within float noise may flip
+                assert _near_threshold(np.asarray(arr).ravel(), th).any(), (a, b, nm)
+            else:
+                assert g == w
+        assert np.array_equal(r.offset1, np.array([i * (2 * len(s1) + 1 - i) // 2 for i in range(len(s1) + 1)]))
+
+
+def test_readme_dis_known_answer_on_gpu(stage, bundled):
+    """README.md:91-97: the thresholded GPU matrices contain exactly the answer's helices."""
+    s = bundled["sequences"]["DIS"]
+    r = stage.solve_probabilities(s, s)
+    ans = bundled["readme_dis"]["s1"]
+    stack, want = [], set()
+    for k, ch in enumerate(ans):
+        if ch == "(":
+            stack.append(k)
+        elif ch == ")":
+            want.add((stack.pop(), k))
+    L = len(s)
+    got = {(i, j) for j in range(1, L) for i in range(j) if r.bp1[r.offset1[i + 1] + j + 1] > 0.5}
+    assert got == want
+    kiss = [k for k, ch in enumerate(ans) if ch == "["]
+    for a, b in zip(kiss, reversed(kiss)):
+        assert r.hp[a + 1][b + 1] > 0.9
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (2, 5), (4, 4), (5, 5), (7, 3), (9, 12), (33, 64), (130, 31)])
+def test_edge_and_ragged_lengths(stage, oracle, n1, n2):
+    from ractip_b200 import default_opts
+    rng = np.random.default_rng(1000 * n1 + n2)
+    opts = default_opts()
+    pairs = [(rand_seq(rng, n1), rand_seq(rng, n2)) for _ in range(3)]
+    for (s1, s2), r in zip(pairs, stage.run_dense(pairs, opts)):
+        _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"{n1}x{n2}")
+
+
+def test_longer_than_one_cta_chunk(stage, oracle):
+    """n > CTA width: the per-diagonal cell loop runs in several chunks (two-strand n = 430)."""
+    from ractip_b200 import default_opts
+    rng = np.random.default_rng(77)
+    s1, s2 = rand_seq(rng, 300), rand_seq(rng, 130)
+    opts = default_opts()
+    r = stage.run_dense([(s1, s2)], opts)[0]
+    _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, "300x130")
+
+
+def test_options_window_thresholds(stage, oracle, bundled):
+    from ractip_b200 import default_opts
+    s1, s2 = bundled["sequences"]["Tar"], bundled["sequences"]["Tarstar"]
+    for kw in [dict(max_w=1), dict(max_w=30, min_w=3), dict(th_hy=0.0), dict(th_hy=0.5, th_ss=0.2)]:
+        opts = default_opts(**kw)
+        r = stage.run_dense([(s1, s2)], opts)[0]
+        assert r.up1.shape == (len(s1), opts.max_w)
+        _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, str(kw))
+
+
+def test_special_hairpins_and_letters(stage, oracle):
+    from ractip_b200 import default_opts
+    opts = default_opts()
+    pairs = [("GGGGGACCCC", "CCAACGGG"), ("ggggaccuuaugc", "GGGTGACTCC"), ("ACAGUACUGAGCAGUACU", "NNACGUNNACGU")]
+    for (s1, s2), r in zip(pairs, stage.run_dense(pairs, opts)):
+        _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, s1)
+
+
+def test_pf_duplex_branch(stage, oracle, bundled):
+    """--duplex (src/ractip.cpp:390-399): dense hp from the log-space duplex forward/backward."""
+    from ractip_b200 import default_opts
+    opts = default_opts(use_pf_duplex=1)
+    pairs = [(bundled["sequences"]["DIS"], bundled["sequences"]["DIS"]),
+             (bundled["sequences"]["MicA"], bundled["sequences"]["ompA"]), ("GGGAAACC", "GGUUUCCC"), ("A", "U")]
+    for (s1, s2), r in zip(pairs, stage.run_dense(pairs, opts)):
+        want = oracle.rnaduplex(s1, s2, opts.th_hy, True)
+        assert np.abs(r.hp.astype(np.float64) - want).max() <= TOL
+        bp1, up1 = oracle.rnafold(s1, opts.max_w)
+        assert np.abs(r.bp1 - bp1).max() <= TOL and np.abs(r.up1 - up1).max() <= TOL
+
+
+def test_log_partition_functions(stage, oracle, bundled):
+    from ractip_b200 import default_opts
+    s1, s2 = bundled["sequences"]["CopA"], bundled["sequences"]["CopT"]
+    b = stage.batch([(s1, s2)], default_opts())
+    b.run()
+    lz = b.fetch_logz()[0]
+    b.close()
+    want = [oracle.fold(s1)[2], oracle.fold(s2)[2], oracle.fold(s1 + s2, len(s1) + 1)[2]]
+    assert np.abs(lz - np.array(want)).max() < 1e-9
+
+
+def test_sparse_records_in_reference_order(stage, oracle, bundled):
+    """rp_run_sparse == thresholding the dense matrices in the reference's loop order."""
+    from ractip_b200 import default_opts
+    opts = default_opts()
+    pairs = [(bundled["sequences"][a], bundled["sequences"][b]) for a, b in bundled["pairs"]]
+    dense = stage.run_dense(pairs, opts)
+    sparse = stage.run_sparse(pairs, opts)
+    for (s1, s2), d, sp in zip(pairs, dense, sparse):
+        x, y, z, _, _ = _threshold_sets(d.bp1, d.up1, d.bp2, d.up2, d.hp, len(s1), len(s2), opts)
+        assert [(int(r["i"]), int(r["j"])) for r in sp.x] == x
+        assert [(int(r["i"]), int(r["j"])) for r in sp.y] == y
+        assert [(int(r["i"]), int(r["j"])) for r in sp.z] == z
+        for r in sp.x:
+            assert r["p"] == d.bp1[d.offset1[r["i"] + 1] + r["j"] + 1]
+        for r in sp.z:
+            assert r["p"] == d.hp[r["i"] + 1][r["j"] + 1]
+        assert np.array_equal(sp.up1, d.up1) and np.array_equal(sp.up2, d.up2)
+
+
+def test_shuffle_batch_matches_oracle_and_is_deterministic(stage, oracle, bundled):
+    """A slice of the --zscore batch (MicA x ompA, seed 1) against the oracle; bitwise repeatable."""
+    from ractip_b200 import default_opts, zscore_shuffles
+    s1, s2 = bundled["sequences"]["MicA"], bundled["sequences"]["ompA"]
+    r1, r2 = zscore_shuffles(s1, s2, 12, 1)
+    pairs = list(zip(r1, r2))
+    opts = default_opts()
+    b = stage.batch(pairs, opts)
+    b.run()
+    flat1 = b.fetch_dense().copy()
+    b.run()
+    flat2 = b.fetch_dense().copy()
+    assert np.array_equal(flat1, flat2)
+    for (a, c), r in zip(pairs, b.split_dense(flat1)):
+        _compare(r, _oracle_pair(oracle, a, c, opts), a, c, opts, "shuffle")
+    b.close()
+
+
+def test_full_batch_size_independent_properties(stage, bundled):
+    """BASELINE config 4 at full size (1000 shuffles): properties that need no oracle.
+    sum_j p(i,j) + P(i unpaired) = 1 for every base of every shuffled sequence; windows monotone;
+    hp entries either 0 or above the threshold; dinucleotide-shuffled inputs keep their length."""
+    from ractip_b200 import default_opts, zscore_shuffles
+    s1, s2 = bundled["sequences"]["MicA"], bundled["sequences"]["ompA"]
+    r1, r2 = zscore_shuffles(s1, s2, 1000, 1)
+    opts = default_opts()
+    b = stage.batch(list(zip(r1, r2)), opts)
+    b.run()
+    flat = b.fetch_dense()
+    res = b.split_dense(flat)
+    b.close()
+    assert np.isfinite(flat).all()
+    worst = 0.0
+    for r in res:
+        for bp, off, up in ((r.bp1, r.offset1, r.up1), (r.bp2, r.offset2, r.up2)):
+            L = up.shape[0]
+            full = np.zeros((L + 1, L + 1), dtype=np.float64)
+            for i in range(1, L):
+                full[i, i + 1:L + 1] = bp[off[i] + i + 1: off[i] + L + 1]
+            tot = (full + full.T)[1:, 1:].sum(axis=1) + up[:, 0]
+            worst = max(worst, np.abs(tot - 1).max())
+            assert (np.diff(up.astype(np.float64), axis=1) <= 1e-6).all()
+        nz = r.hp[r.hp != 0]
+        assert (nz > np.float32(opts.th_hy)).all()
+    assert worst < 5e-6  # ~L fp32 roundings per row
+
+
+def test_error_paths(stage, lib):
+    from ractip_b200 import default_opts, RpError
+    from ractip_b200._lib import RpPair
+    opts = default_opts()
+    pairs = (RpPair * 1)()
+    pairs[0].s1, pairs[0].n1, pairs[0].s2, pairs[0].n2 = b"ACGUACGU", 8, b"ACGU", 4
+    small = np.zeros(4, dtype=np.float32)
+    assert lib.rp_run_dense(stage.ctx, pairs, 1, C.byref(opts), small.ctypes.data, small.size) == 9  # RP_ERR_CAPACITY
+    assert lib.rp_run_dense(stage.ctx, None, 1, C.byref(opts), small.ctypes.data, small.size) == 1
+    assert stage.run_dense([], opts) == []
+    with pytest.raises(RpError):
+        stage.run_dense([("", "ACGU")], opts)
