@@ -343,7 +343,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "config": {"workload": desc, "pairs_per_step": total_pairs, "sharding": f"shuffles r::{world}" if world > 1 else "none",
                        "collective": "one all_gather of sparse records" if world > 1 else "none",
                        "l2": "per-step working set (workspace slots, GBs) exceeds the 126 MB L2; no flush needed",
-                       "threads_per_cta": 256},
+                       "threads_per_cta": 512},
             "clocks": clocks,
             "e2e": {"value": e2e_d, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": out_bytes * world, "api": "rp_run_dense (reference layouts, pinned host buffer)"},

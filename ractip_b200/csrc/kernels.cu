@@ -28,9 +28,11 @@ struct CtaExec {
 }  // namespace
 
 __global__ void __launch_bounds__(RP_MCC_THREADS, RP_MCC_MIN_CTAS) mcc_persistent(BatchDev b) {
-  extern __shared__ double part[];  // 3 * blockDim.x
+  extern __shared__ double smem_raw[];
   __shared__ int s_next;
   CtaExec ex;
+  Shared sh;
+  carve_shared(sh, smem_raw, blockDim.x);
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(b.counter, 1);
     __syncthreads();
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(RP_MCC_THREADS, RP_MCC_MIN_CTAS) mcc_persisten
     if (p.kind == KIND_DUPLEX) continue;  // handled by duplex_kernel
     Ctx c;
     bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)blockIdx.x * b.slot_stride);
-    solve_mcc(ex, c, p, b.dense, b.logz, part);
+    solve_mcc(ex, c, p, b.dense, b.logz, sh);
   }
 }
 
@@ -292,13 +294,14 @@ __global__ void __launch_bounds__(256) peak_smem_kernel(double* out, int iters) 
 // ---------------------------------------------------------------------------
 int mcc_max_ctas_per_sm(int threads) {
   int n = 0;
-  size_t smem = 3 * sizeof(double) * threads;
+  size_t smem = shared_bytes(threads);
+  cudaFuncSetAttribute(mcc_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mcc_persistent, threads, smem) != cudaSuccess) return 0;
   return n;
 }
 
 cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, cudaStream_t st) {
-  size_t smem = 3 * sizeof(double) * threads;
+  size_t smem = shared_bytes(threads);
   mcc_persistent<<<grid, threads, smem, st>>>(b);
   return cudaGetLastError();
 }

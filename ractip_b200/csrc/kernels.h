@@ -9,10 +9,10 @@
 #include "ractip_prob.h"
 
 #ifndef RP_MCC_THREADS
-#define RP_MCC_THREADS 256
+#define RP_MCC_THREADS 512
 #endif
 #ifndef RP_MCC_MIN_CTAS
-#define RP_MCC_MIN_CTAS 2
+#define RP_MCC_MIN_CTAS 1
 #endif
 
 namespace rp {

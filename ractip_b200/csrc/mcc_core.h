@@ -60,6 +60,7 @@ enum {
   T_Q = 0, T_QQ, T_QM, T_QM1, T_QM2, T_QB, T_QBI, T_QB1N, T_QBAU,
   T_OUT, T_OUTI, T_OUT1N, T_OUTAU, T_MC, T_PR, T_PRML, T_PMLB, T_PL,
   T_DG, T_RR, T_LL, T_XX,
+  T_LIST,   // not doubles: per-diagonal lists of pairable cells (uint16), see listp()/posp()
   T_COUNT
 };
 enum {
@@ -91,23 +92,53 @@ RP_HD double* vecp(const Ctx& c, int v) { return c.ws + (size_t)T_COUNT * c.te +
 
 #define TB(c, t, d, i) (tabp(c, t)[(size_t)(d) * (c).ld + (i)])
 
+// Per-diagonal compaction of the cells that can pair (static per sequence):
+//   LIST[d*ld + r] = i of the r-th pairable cell (i,i+d);  POS[d*ld + i] = #pairable cells (i',i'+d), i' < i.
+// Interior-loop work is dealt out over these lists, so no thread idles on a cell that cannot pair.
+RP_HD uint16_t* listp(const Ctx& c) { return reinterpret_cast<uint16_t*>(tabp(c, T_LIST)); }
+RP_HD uint16_t* posp(const Ctx& c) { return reinterpret_cast<uint16_t*>(tabp(c, T_LIST)) + c.te * 2; }
+
+// CTA-shared scratch (CUDA shared memory; a heap block in the host emulation)
+constexpr int RP_SMEM_SEQ = 4096;  // sequences up to this length are staged in shared memory
+struct Shared {
+  int T;
+  double* part;     // [3][T] partial sums of the current phase
+  double* tap_g;    // [TAP_CLASSES][MAX_TAPS] loop weights (x scale)
+  int* tap_off;     // [TAP_CLASSES][MAX_TAPS] po - dd*ld for the current problem
+  uint8_t* tap_po;  // [TAP_CLASSES][MAX_TAPS]
+  uint8_t* tap_u2;  // [TAP_CLASSES][MAX_TAPS]
+  double* red;      // [128] small reductions (nick sums)
+  uint8_t* S;       // [RP_SMEM_SEQ + 8] staged sequence
+};
+RP_HD size_t shared_bytes(int T) {
+  return sizeof(double) * (3 * (size_t)T + TAP_CLASSES * MAX_TAPS + 128) + sizeof(int) * TAP_CLASSES * MAX_TAPS +
+         2 * TAP_CLASSES * MAX_TAPS + RP_SMEM_SEQ + 16;
+}
+RP_HD void carve_shared(Shared& sh, void* base, int T) {
+  sh.T = T;
+  double* p = static_cast<double*>(base);
+  sh.part = p; p += 3 * (size_t)T;
+  sh.tap_g = p; p += TAP_CLASSES * MAX_TAPS;
+  sh.red = p; p += 128;
+  int* q = reinterpret_cast<int*>(p);
+  sh.tap_off = q; q += TAP_CLASSES * MAX_TAPS;
+  uint8_t* b = reinterpret_cast<uint8_t*>(q);
+  sh.tap_po = b; b += TAP_CLASSES * MAX_TAPS;
+  sh.tap_u2 = b; b += TAP_CLASSES * MAX_TAPS;
+  sh.S = b;
+}
+
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
 RP_HD int base(const Ctx& c, int i) { return c.S[i] & 7; }
 
 RP_HD int pair_type(int a, int b) {
-  // CG=1 GC=2 GU=3 UG=4 AU=5 UA=6 ; a,b in 0..4 (N,A,C,G,U)
-  const int code = a * 5 + b;
-  switch (code) {
-    case 2 * 5 + 3: return 1;
-    case 3 * 5 + 2: return 2;
-    case 3 * 5 + 4: return 3;
-    case 4 * 5 + 3: return 4;
-    case 1 * 5 + 4: return 5;
-    case 4 * 5 + 1: return 6;
-    default: return 0;
-  }
+  // CG=1 GC=2 GU=3 UG=4 AU=5 UA=6 ; a,b in 0..4 (N,A,C,G,U).  One nibble per (a-1,b-1).
+  const uint64_t LUT = (5ull << 12) | (1ull << 24) | (2ull << 36) | (3ull << 44) | (6ull << 48) | (4ull << 56);
+  const int idx = ((a - 1) & 3) * 4 + ((b - 1) & 3);
+  const int t = (int)((LUT >> (4 * idx)) & 15);
+  return (a && b) ? t : 0;
 }
 RP_HD int rtype(int t) { return t == 0 ? 0 : (t == 7 ? 7 : ((t - 1) ^ 1) + 1); }
 
@@ -194,26 +225,58 @@ RP_HD Split make_split(int C, int T) {
 }
 
 // ---------------------------------------------------------------------------
-// prologue: per-problem vectors and the d<=TURN diagonals
+// prologue: shared tap tables, per-problem vectors, pair lists, d<=TURN diagonals
 // ---------------------------------------------------------------------------
-RP_HD void prologue(Ctx& c, int tid, int T) {
+// copy S[0..n+1] into shared memory (the caller then points c.S at sh.S)
+RP_HD void stage_sequence(const Ctx& c, const Shared& sh, int tid) {
+  for (int x = tid; x <= c.n + 1; x += sh.T) sh.S[x] = c.S[x];
+}
+
+RP_HD void prologue(Ctx& c, const Shared& sh, int tid) {
   const DevModel& M = *c.M;
-  const int n = c.n;
+  const int n = c.n, T = sh.T;
+  // interior-loop taps into shared memory; the table offset depends on this problem's ld
+  for (int x = tid; x < TAP_CLASSES * MAX_TAPS; x += T) {
+    const int cl = x / MAX_TAPS, t = x % MAX_TAPS;
+    if (t < M.ntaps[cl]) {
+      const Tap tp = M.taps[cl][t];
+      sh.tap_g[x] = tp.g;
+      sh.tap_off[x] = (int)tp.po - (int)tp.dd * c.ld;
+      sh.tap_po[x] = (uint8_t)tp.po;
+      sh.tap_u2[x] = (uint8_t)tp.u2;
+    }
+  }
   // scale[k] = pf_scale^-k, mlb[k] = (expMLbase/pf_scale)^k: built by repeated
   // multiplication by one thread so that every consumer sees the same values
   if (tid == 0) {
     double s = 1.0, b = 1.0;
+    double* sc = vecp(c, V_SCALE);
+    double* ml = vecp(c, V_MLB);
     for (int k = 0; k <= n + 2; k++) {
-      vecp(c, V_SCALE)[k] = s;
-      vecp(c, V_MLB)[k] = b;
+      sc[k] = s;
+      ml[k] = b;
       s *= M.scale1;
       b *= M.mlb1;
     }
   }
+  // pair lists: one thread per diagonal
+  uint16_t* LIST = listp(c);
+  uint16_t* POS = posp(c);
+  for (int d = tid; d < n; d += T) {
+    uint16_t* L = LIST + (size_t)d * c.ld;
+    uint16_t* P = POS + (size_t)d * c.ld;
+    int cnt = 0;
+    for (int i = 1; i <= n - d; i++) {
+      P[i] = (uint16_t)cnt;
+      if (d > TURN && pair_type(base(c, i), base(c, i + d))) L[cnt++] = (uint16_t)i;
+    }
+    P[n - d + 1 <= n ? n - d + 1 : n] = (uint16_t)cnt;  // d = 0: i = n+1 does not exist and is never asked for
+    if (d == 0) P[n] = 0;
+  }
 }
-RP_HD void prologue2(Ctx& c, int tid, int T) {
+RP_HD void prologue2(Ctx& c, const Shared& sh, int tid) {
   const DevModel& M = *c.M;
-  const int n = c.n;
+  const int n = c.n, T = sh.T;
   for (int u = tid; u <= n; u += T) {
     double q;
     if (u <= 30) q = M.exphairpin[u];
@@ -265,39 +328,122 @@ RP_HD void prologue2(Ctx& c, int tid, int T) {
 }
 
 // ---------------------------------------------------------------------------
-// inside pass, diagonal d >= TURN+1; cells i0 .. i0+C-1 handled as a chunk
-// part: [3][T] doubles (interior, QM2, q-split)
+// shared pieces of the inside and outside phases
 // ---------------------------------------------------------------------------
-RP_HD void inside_A(const Ctx& c, int d, int i0, int C, int tid, int T, double* part) {
+// sum over the taps of one class that slice `s` of `S` owns; Bc points at the
+// table entry of the closing cell, sign=+1 inside (inner pairs lie dd diagonals
+// below), -1 outside (enclosing pairs lie dd diagonals above).
+template <int SIGN, bool GUARD>
+RP_HD double tap_sum(const double* Bc, const double* g, const int* off, const uint8_t* po, const uint8_t* u2, int nt,
+                     int s, int S, int maxpo, int maxu2) {
+  double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+  int t = s;
+  for (; t + 3 * S < nt; t += 4 * S) {
+    double v0 = Bc[SIGN * off[t]], v1 = Bc[SIGN * off[t + S]], v2 = Bc[SIGN * off[t + 2 * S]], v3 = Bc[SIGN * off[t + 3 * S]];
+    if (GUARD) {
+      v0 = (po[t] <= maxpo && u2[t] <= maxu2) ? v0 : 0.;
+      v1 = (po[t + S] <= maxpo && u2[t + S] <= maxu2) ? v1 : 0.;
+      v2 = (po[t + 2 * S] <= maxpo && u2[t + 2 * S] <= maxu2) ? v2 : 0.;
+      v3 = (po[t + 3 * S] <= maxpo && u2[t + 3 * S] <= maxu2) ? v3 : 0.;
+    }
+    a0 += g[t] * v0; a1 += g[t + S] * v1; a2 += g[t + 2 * S] * v2; a3 += g[t + 3 * S] * v3;
+  }
+  for (; t < nt; t += S) {
+    double v = Bc[SIGN * off[t]];
+    if (GUARD) v = (po[t] <= maxpo && u2[t] <= maxu2) ? v : 0.;
+    a0 += g[t] * v;
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// the nine loop shapes that do not factorise, closing pair `type` with
+// neighbours (si1,sj1), inner pair of reversed type t2r with neighbours (sp1,sq1)
+RP_HD double special_loop(const DevModel& M, int s, int type, int t2r, int si1, int sj1, int sp1, int sq1) {
+  switch (s) {
+    case 0: return M.expstack[type][t2r] * M.scale_small[2];
+    case 1:
+    case 2: return M.expbulge[1] * M.expstack[type][t2r] * M.scale_small[3];
+    case 3: return M.int11[type][t2r][si1][sj1] * M.scale_small[4];
+    case 4: return M.int21[type][t2r][si1][sq1][sj1] * M.scale_small[5];   // u1=1,u2=2
+    case 5: return M.int21[t2r][type][sq1][si1][sp1] * M.scale_small[5];   // u1=2,u2=1
+    case 6: return M.int22[type][t2r][si1][sp1][sq1][sj1] * M.scale_small[6];
+    default: return M.expinternal[5] * M.expninio[1] * M.mm23[type][si1][sj1] * M.mm23[t2r][sq1][sp1] * M.scale_small[7];
+  }
+}
+
+// sum_x A[x*sa] * B[x*sb] for x = s, s+S, ... < cnt, skipping x == skip
+RP_HD double strided_dot(const double* A, long sa, const double* B, long sb, int cnt, int s, int S, int skip) {
+  double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+  int x = s;
+  for (; x + 3 * S < cnt; x += 4 * S) {
+    double p0 = A[(long)x * sa] * B[(long)x * sb];
+    double p1 = A[(long)(x + S) * sa] * B[(long)(x + S) * sb];
+    double p2 = A[(long)(x + 2 * S) * sa] * B[(long)(x + 2 * S) * sb];
+    double p3 = A[(long)(x + 3 * S) * sa] * B[(long)(x + 3 * S) * sb];
+    a0 += (x == skip) ? 0. : p0;
+    a1 += (x + S == skip) ? 0. : p1;
+    a2 += (x + 2 * S == skip) ? 0. : p2;
+    a3 += (x + 3 * S == skip) ? 0. : p3;
+  }
+  for (; x < cnt; x += S) {
+    double p = A[(long)x * sa] * B[(long)x * sb];
+    a0 += (x == skip) ? 0. : p;
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// work split of the interior-loop items of a chunk: cnt pairable cells x SI slices
+struct ISplit {
+  int lo, cnt, cntp, SI;
+};
+RP_HD ISplit make_isplit(const Ctx& c, int d, int i0, int C, int T) {
+  const uint16_t* P = posp(c) + (size_t)d * c.ld;
+  ISplit s;
+  s.lo = P[i0];
+  s.cnt = (int)P[i0 + C] - s.lo;
+  int cp = (s.cnt + 31) & ~31;
+  if (cp > T) cp = T;
+  if (cp < 32) cp = 32;
+  s.cntp = cp;
+  s.SI = T / cp;
+  if (s.SI < 1) s.SI = 1;
+  return s;
+}
+
+// ---------------------------------------------------------------------------
+// inside pass, diagonal d >= TURN+1; cells i0 .. i0+C-1 handled as a chunk
+// sh.part: [3][T] doubles (interior, QM2, q-split)
+// ---------------------------------------------------------------------------
+RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   const DevModel& M = *c.M;
-  const Split sp = make_split(C, T);
-  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
-  if (slice >= sp.S || cell >= C) return;
-  const int i = i0 + cell, j = i + d, S = sp.S;
-  double accI = 0., accM = 0., accQ = 0.;
-  const int type = pair_type(base(c, i), base(c, j));
-  // --- interior loops -------------------------------------------------------
-  if (type) {
-    // strand guards: inner 5' end must stay on i's strand, inner 3' end on j's
-    const int maxpo = (c.cp > 0 && i < c.cp) ? c.cp - 1 - i : 1000;
-    const int maxu2 = (c.cp > 0 && j >= c.cp) ? j - 1 - c.cp : 1000;
-    const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
-    if (ddmax >= 2) {
+  const int T = sh.T;
+  const long ld = c.ld;
+  // --- (1) interior loops: items = (pairable cell, slice) ---------------------
+  const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
+  if (ddmax >= 2) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = tid % is.cntp, sl = tid / is.cntp;
+    if (sl < is.SI && r < is.cnt) {
+      const int i = listp(c)[(size_t)d * ld + is.lo + r], j = i + d;
+      const int type = pair_type(base(c, i), base(c, j));
+      // strand guards: inner 5' end must stay on i's strand, inner 3' end on j's
+      const int maxpo = (c.cp > 0 && i < c.cp) ? c.cp - 1 - i : 1000;
+      const int maxu2 = (c.cp > 0 && j >= c.cp) ? j - 1 - c.cp : 1000;
+      const bool guard = maxpo < MAXLOOP + 1 || maxu2 < MAXLOOP;
       const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
       const int tabs[TAP_CLASSES] = {T_QBI, T_QB1N, T_QBAU};
       const double fac[TAP_CLASSES] = {M.mmI[type][si1][sj1], M.mm1n[type][si1][sj1], type > 2 ? M.expTermAU : 1.0};
+      double accI = 0.;
       for (int cl = 0; cl < TAP_CLASSES; cl++) {
         const int nt = M.tap_prefix[cl][ddmax];
-        const double* B = tabp(c, tabs[cl]);
-        double acc = 0.;
-        for (int t = slice; t < nt; t += S) {
-          const Tap tp = M.taps[cl][t];
-          if (tp.po <= maxpo && tp.u2 <= maxu2) acc += tp.g * B[(size_t)(d - tp.dd) * c.ld + i + tp.po];
-        }
-        accI += fac[cl] * acc;
+        const double* Bc = tabp(c, tabs[cl]) + (size_t)d * ld + i;
+        const int o = cl * MAX_TAPS;
+        const double a = guard ? tap_sum<1, true>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2)
+                               : tap_sum<1, false>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2);
+        accI += fac[cl] * a;
       }
       // table-driven small loops
-      for (int s = slice; s < RP_N_SPECIAL; s += S) {
+      for (int s = sl; s < RP_N_SPECIAL; s += is.SI) {
         int u1, u2;
         special_uv(s, u1, u2);
         const int dd = u1 + u2 + 2;
@@ -305,47 +451,53 @@ RP_HD void inside_A(const Ctx& c, int d, int i0, int C, int tid, int T, double* 
         const int k = i + 1 + u1, l = j - 1 - u2;
         const int t2 = pair_type(base(c, k), base(c, l));
         if (!t2) continue;
-        accI += TB(c, T_QB, d - dd, k) *
-                int_loop(M, u1, u2, type, rtype(t2), si1, sj1, base(c, k - 1), base(c, l + 1)) * M.scale_small[dd];
+        accI += TB(c, T_QB, d - dd, k) * special_loop(M, s, type, rtype(t2), si1, sj1, base(c, k - 1), base(c, l + 1));
       }
+      sh.part[tid] = accI;
     }
   }
-  // --- QM2(i,j) = sum_k qm(i,k-1) qm1(k,j), k-1|k on one strand ---------------
-  {
-    const double* A = tabp(c, T_QM);
-    const double* B = tabp(c, T_QM1);
-    for (int a = TURN + 1 + slice; a <= d - 2 - TURN; a += S) {
-      const int k = i + 1 + a;
-      if (!ss(c, k - 1, k)) continue;
-      accM += A[(size_t)a * c.ld + i] * B[(size_t)(d - 1 - a) * c.ld + k];
+  // --- (2) split sums: items = (cell, slice) ---------------------------------
+  const Split sp = make_split(C, T);
+  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
+  if (slice < sp.S && cell < C) {
+    const int i = i0 + cell;
+    // QM2(i,j) = sum_a qm[a][i] * qm1[d-1-a][i+1+a], a = TURN+1 .. d-2-TURN; the split k=i+1+a may not be the nick
+    const int cntM = d - 2 * TURN - 2;   // number of terms
+    double accM = 0., accQ = 0.;
+    if (cntM > 0) {
+      const int skip = c.cp > 0 ? c.cp - 1 - i - (TURN + 1) : -1;  // a = cp-1-i  <=> k = cp
+      accM = strided_dot(tabp(c, T_QM) + (size_t)(TURN + 1) * ld + i, ld,
+                         tabp(c, T_QM1) + (size_t)(d - 2 - TURN) * ld + i + TURN + 2, 1 - ld, cntM, slice, sp.S, skip);
     }
+    // sum_a q[a][i] * qq[d-1-a][i+1+a], a = 0 .. d-2-TURN
+    const int cntQ = d - 1 - TURN;
+    if (cntQ > 0)
+      accQ = strided_dot(tabp(c, T_Q) + i, ld, tabp(c, T_QQ) + (size_t)(d - 1) * ld + i + 1, 1 - ld, cntQ, slice, sp.S, -1);
+    sh.part[T + tid] = accM;
+    sh.part[2 * T + tid] = accQ;
   }
-  // --- sum_k q(i,k-1) qq(k,j) ------------------------------------------------
-  {
-    const double* A = tabp(c, T_Q);
-    const double* B = tabp(c, T_QQ);
-    for (int a = slice; a <= d - 2 - TURN; a += S) accQ += A[(size_t)a * c.ld + i] * B[(size_t)(d - 1 - a) * c.ld + i + 1 + a];
-  }
-  part[0 * T + tid] = accI;
-  part[1 * T + tid] = accM;
-  part[2 * T + tid] = accQ;
 }
 
-RP_HD void inside_B(Ctx& c, int d, int i0, int C, int tid, int T, const double* part) {
+RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   const DevModel& M = *c.M;
+  const int T = sh.T;
   const Split sp = make_split(C, T);
   if (tid >= sp.Cp || tid >= C) return;
   const int i = i0 + tid, j = i + d, n = c.n;
   double sI = 0., sM = 0., sQ = 0.;
   for (int s = 0; s < sp.S; s++) {
-    sI += part[0 * T + s * sp.Cp + tid];
-    sM += part[1 * T + s * sp.Cp + tid];
-    sQ += part[2 * T + s * sp.Cp + tid];
+    sM += sh.part[T + s * sp.Cp + tid];
+    sQ += sh.part[2 * T + s * sp.Cp + tid];
   }
   const int type = pair_type(base(c, i), base(c, j));
   const double* scale = vecp(c, V_SCALE);
   double qb = 0.;
   if (type) {
+    if (d - (TURN + 1) >= 2) {
+      const ISplit is = make_isplit(c, d, i0, C, T);
+      const int r = (int)posp(c)[(size_t)d * c.ld + i] - is.lo;
+      for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+    }
     if (ss(c, i, j)) qb += hairpin(c, i, j, type);
     qb += sI;
     if (ss(c, i, i + 1) && ss(c, j - 1, j))
@@ -391,24 +543,20 @@ RP_HD void inside_B(Ctx& c, int d, int i0, int C, int tid, int T, const double* 
   TB(c, T_Q, d, i) = scale[d + 1] + qq + sQ;
 }
 
-// the recurrence for U needs its previous diagonal initialised
-RP_HD void inside_begin(Ctx& c, int tid, int T) {
-  // U on diagonal TURN is 0 (qm1 vanishes there); vectors were zeroed by prologue2
-  (void)c; (void)tid; (void)T;
-}
-
 RP_HD void inside_end(Ctx& c) { c.invZ = 1.0 / TB(c, T_Q, c.n - 1, 1); }
 
 // ---------------------------------------------------------------------------
 // outside pass, diagonal d from n-1 down to TURN+1.
 // out(k,l) = Z_outside(k,l)/Z  (ViennaRNA's probs[] before the final *qb).
 // ---------------------------------------------------------------------------
-// two-strand only, once per diagonal before outside_A: the closing pairs that
+// two-strand only, twice per diagonal before outside_A: the closing pairs that
 // straddle the nick feed the stems sitting directly in the nicked loop.
 //   Qr(r)    = sum_{p<cp} out(p,r) ExtClose(p,r) scale[2] q(p+1,cp-1)        complete after diag r-cp+1
 //   Qrout(l) = sum_{r>l} Qr(r) q(l+1,r-1)
 //   Ql(p)    = sum_{r>=cp} out(p,r) ExtClose(p,r) scale[2] q(cp,r-1)         complete after diag cp-p
 //   Qlout(k) = sum_{p<k} Ql(p) q(p+1,k-1)
+// Step d finalises Qr(d+cp), Qrout(d+cp-1), Ql(cp-1-d), Qlout(cp-d).  Each sum
+// is split over 32 threads (fixed partition => deterministic), partials in sh.red.
 RP_HD double nick_close(const Ctx& c, int p, int r) {
   const int tp = pair_type(base(c, p), base(c, r));
   if (!tp || r - p <= TURN) return 0.;
@@ -417,123 +565,141 @@ RP_HD double nick_close(const Ctx& c, int p, int r) {
   return o * vecp(c, V_SCALE)[2] *
          ext_stem(*c.M, rtype(tp), ss(c, r - 1, r) ? base(c, r - 1) : -1, ss(c, p, p + 1) ? base(c, p + 1) : -1);
 }
-RP_HD void outside_nick1(Ctx& c, int d, int tid, int T) {
+RP_HD void outside_nick1(Ctx& c, const Shared& sh, int d, int tid) {
   if (c.cp <= 0) return;
   const int n = c.n, cp = c.cp;
-  // diag d+1 is final.  r = d + cp: its last contributing pair (cp-1, r) has diag d+1.
-  const int r = d + cp;
-  if (tid == 0 && r >= cp && r <= n) {
+  for (int w = tid; w < 128; w += sh.T) {
+    const int lane = w & 31, job = w >> 5;
     double s = 0.;
-    for (int p = 1; p < cp; p++) {
-      double w = nick_close(c, p, r);
-      if (w != 0.) s += w * (p + 1 <= cp - 1 ? TB(c, T_Q, cp - 2 - p, p + 1) : 1.0);
+    if (job == 0) {          // Qr(r), r = d+cp: closing pairs (p,r), all of diag >= d+1
+      const int r = d + cp;
+      if (r >= cp && r <= n)
+        for (int p = 1 + lane; p < cp; p += 32) {
+          const double v = nick_close(c, p, r);
+          if (v != 0.) s += v * (p + 1 <= cp - 1 ? TB(c, T_Q, cp - 2 - p, p + 1) : 1.0);
+        }
+    } else if (job == 1) {   // Ql(p), p = cp-1-d
+      const int p = cp - 1 - d;
+      if (p >= 1 && p < cp)
+        for (int rr = cp + lane; rr <= n; rr += 32) {
+          const double v = nick_close(c, p, rr);
+          if (v != 0.) s += v * (cp <= rr - 1 ? TB(c, T_Q, rr - 1 - cp, cp) : 1.0);
+        }
+    } else if (job == 2) {   // part of Qrout(l), l = d+cp-1, that uses Qr(r), r >= l+2 (earlier steps)
+      const int l = d + cp - 1;
+      if (l >= cp && l < n)
+        for (int r = l + 2 + lane; r <= n; r += 32) s += vecp(c, V_QR)[r] * TB(c, T_Q, r - 2 - l, l + 1);
+    } else {                 // part of Qlout(k), k = cp-d, that uses Ql(p), p <= k-2 (earlier steps)
+      const int k = cp - d;
+      if (k >= 2 && k < cp)
+        for (int p = 1 + lane; p <= k - 2; p += 32) s += vecp(c, V_QL)[p] * TB(c, T_Q, k - 2 - p, p + 1);
     }
-    vecp(c, V_QR)[r] = s;
-  }
-  // p = cp-1-d: its last contributing pair (p, cp) has diag d+1.
-  const int p = cp - 1 - d;
-  if (tid == (T > 32 ? 32 : 0) && p >= 1 && p < cp) {
-    double s = 0.;
-    for (int rr = cp; rr <= n; rr++) {
-      double w = nick_close(c, p, rr);
-      if (w != 0.) s += w * (cp <= rr - 1 ? TB(c, T_Q, rr - 1 - cp, cp) : 1.0);
-    }
-    vecp(c, V_QL)[p] = s;
+    sh.red[w] = s;
   }
 }
-RP_HD void outside_nick2(Ctx& c, int d, int tid, int T) {
+RP_HD void outside_nick2(Ctx& c, const Shared& sh, int d, int tid) {
   if (c.cp <= 0) return;
   const int n = c.n, cp = c.cp;
-  const int l = d + cp - 1;  // needs Qr(r), r>=l+1=d+cp: all done
-  if (tid == 0 && l >= cp && l < n) {
-    double s = 0.;
-    for (int r = l + 1; r <= n; r++) s += vecp(c, V_QR)[r] * (l + 1 <= r - 1 ? TB(c, T_Q, r - 2 - l, l + 1) : 1.0);
-    vecp(c, V_QROUT)[l] = s;
-  }
-  const int k = cp - d;  // needs Ql(p), p<=k-1=cp-1-d: all done
-  if (tid == (T > 32 ? 32 : 0) && k >= 2 && k < cp) {
-    double s = 0.;
-    for (int p = 1; p < k; p++) s += vecp(c, V_QL)[p] * (p + 1 <= k - 1 ? TB(c, T_Q, k - 2 - p, p + 1) : 1.0);
-    vecp(c, V_QLOUT)[k] = s;
+  if (tid == 0) {
+    double qr = 0., rest = 0.;
+    for (int t = 0; t < 32; t++) { qr += sh.red[t]; rest += sh.red[64 + t]; }
+    const int r = d + cp, l = d + cp - 1;
+    if (r >= cp && r <= n) vecp(c, V_QR)[r] = qr;
+    // Qrout(l) = Qr(l+1)*q(l+1,l) + rest, q of the empty segment is 1
+    if (l >= cp && l < n) vecp(c, V_QROUT)[l] = qr + rest;
+  } else if (tid == 32 || (sh.T <= 32 && tid == 1)) {
+    double ql = 0., rest = 0.;
+    for (int t = 0; t < 32; t++) { ql += sh.red[32 + t]; rest += sh.red[96 + t]; }
+    const int p = cp - 1 - d, k = cp - d;
+    if (p >= 1 && p < cp) vecp(c, V_QL)[p] = ql;
+    if (k >= 2 && k < cp) vecp(c, V_QLOUT)[k] = ql + rest;
   }
 }
 
-// part: [3][T] doubles (interior, PR, ML-left)
-RP_HD void outside_A(const Ctx& c, int d, int i0, int C, int tid, int T, double* part) {
+// sh.part: [3][T] doubles (interior, PR, ML-left)
+RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   const DevModel& M = *c.M;
+  const int T = sh.T, n = c.n;
+  const long ld = c.ld;
+  // --- (1) interior loops seen from the inner pair (k,l): items = (pairable cell, slice)
+  const int ddmax = n - 1 - d < MAXLOOP + 2 ? n - 1 - d : MAXLOOP + 2;
+  if (ddmax >= 2) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = tid % is.cntp, sl = tid / is.cntp;
+    if (sl < is.SI && r < is.cnt) {
+      const int k = listp(c)[(size_t)d * ld + is.lo + r], l = k + d;
+      double accI = 0.;
+      // enclosing pair (i,j) = (k-po, l+1+u2)
+      int maxpo = k - 1, maxu2 = n - l - 1;
+      if (c.cp > 0) {
+        if (k >= c.cp && k - c.cp < maxpo) maxpo = k - c.cp;        // i must stay on k's strand
+        if (l < c.cp && c.cp - 2 - l < maxu2) maxu2 = c.cp - 2 - l;  // j must stay on l's strand
+      }
+      if (maxpo >= 1 && maxu2 >= 0 && TB(c, T_QB, d, k) != 0.) {
+        const int type = pair_type(base(c, k), base(c, l));
+        const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
+        const bool guard = maxpo < MAXLOOP + 1 || maxu2 < MAXLOOP;
+        const int tabs[TAP_CLASSES] = {T_OUTI, T_OUT1N, T_OUTAU};
+        const double fac[TAP_CLASSES] = {M.mmI[t2][sq1][sp1], M.mm1n[t2][sq1][sp1], type > 2 ? M.expTermAU : 1.0};
+        for (int cl = 0; cl < TAP_CLASSES; cl++) {
+          const int nt = M.tap_prefix[cl][ddmax];
+          const double* Bc = tabp(c, tabs[cl]) + (size_t)d * ld + k;
+          const int o = cl * MAX_TAPS;
+          const double a = guard ? tap_sum<-1, true>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2)
+                                 : tap_sum<-1, false>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2);
+          accI += fac[cl] * a;
+        }
+        for (int s = sl; s < RP_N_SPECIAL; s += is.SI) {
+          int u1, u2;
+          special_uv(s, u1, u2);
+          const int dd = u1 + u2 + 2;
+          if (dd > ddmax || u1 + 1 > maxpo || u2 > maxu2) continue;
+          const int i = k - 1 - u1, j = l + 1 + u2;
+          const int t1 = pair_type(base(c, i), base(c, j));
+          if (!t1) continue;
+          const double o = TB(c, T_OUT, d + dd, i);
+          if (o == 0.) continue;
+          accI += o * special_loop(M, s, t1, t2, base(c, i + 1), base(c, j - 1), sp1, sq1);
+        }
+      }
+      sh.part[tid] = accI;
+    }
+  }
+  // --- (2) multiloop sums: items = (cell, slice) --------------------------------
   const Split sp = make_split(C, T);
   const int cell = tid % sp.Cp, slice = tid / sp.Cp;
-  if (slice >= sp.S || cell >= C) return;
-  const int k = i0 + cell, l = k + d, n = c.n, S = sp.S;
-  double accI = 0., accP = 0., accL = 0.;
-  const int type = pair_type(base(c, k), base(c, l));
-  const bool live = type && TB(c, T_QB, d, k) != 0.;
-  if (live) {
-    // enclosing pair (i,j) = (k-po, l+1+u2)
-    int maxpo = k - 1, maxu2 = n - l - 1;
-    if (c.cp > 0) {
-      if (k >= c.cp && k - c.cp < maxpo) maxpo = k - c.cp;        // i must stay on k's strand
-      if (l < c.cp && c.cp - 2 - l < maxu2) maxu2 = c.cp - 2 - l;  // j must stay on l's strand
+  if (slice < sp.S && cell < C) {
+    const int k = i0 + cell, l = k + d;
+    double accP = 0., accL = 0.;
+    // PR(k,l) = sum_b Mc[d+2+b][k] * qm[b][l+1], b = TURN+1 .. n-l-2   [k is the closing 5' end]
+    if (l + 2 <= n && ss(c, l, l + 1)) {
+      const int cnt = n - l - 2 - TURN;
+      if (cnt > 0)
+        accP = strided_dot(tabp(c, T_MC) + (size_t)(d + 3 + TURN) * ld + k, ld,
+                           tabp(c, T_QM) + (size_t)(TURN + 1) * ld + l + 1, ld, cnt, slice, sp.S, -1);
     }
-    const int ddmax = n - 1 - d < MAXLOOP + 2 ? n - 1 - d : MAXLOOP + 2;
-    if (ddmax >= 2 && maxpo >= 1 && maxu2 >= 0) {
-      const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = l < n ? base(c, l + 1) : 0;
-      const int tabs[TAP_CLASSES] = {T_OUTI, T_OUT1N, T_OUTAU};
-      const double fac[TAP_CLASSES] = {M.mmI[t2][sq1][sp1], M.mm1n[t2][sq1][sp1], type > 2 ? M.expTermAU : 1.0};
-      for (int cl = 0; cl < TAP_CLASSES; cl++) {
-        const int nt = M.tap_prefix[cl][ddmax];
-        const double* B = tabp(c, tabs[cl]);
-        double acc = 0.;
-        for (int t = slice; t < nt; t += S) {
-          const Tap tp = M.taps[cl][t];
-          if (tp.po <= maxpo && tp.u2 <= maxu2) acc += tp.g * B[(size_t)(d + tp.dd) * c.ld + k - tp.po];
-        }
-        accI += fac[cl] * acc;
-      }
-      for (int s = slice; s < RP_N_SPECIAL; s += S) {
-        int u1, u2;
-        special_uv(s, u1, u2);
-        const int dd = u1 + u2 + 2;
-        if (dd > ddmax || u1 + 1 > maxpo || u2 > maxu2) continue;
-        const int i = k - 1 - u1, j = l + 1 + u2;
-        const int t1 = pair_type(base(c, i), base(c, j));
-        if (!t1) continue;
-        const double o = TB(c, T_OUT, d + dd, i);
-        if (o == 0.) continue;
-        accI += o * int_loop(M, u1, u2, t1, t2, base(c, i + 1), base(c, j - 1), sp1, sq1) * M.scale_small[dd];
-      }
+    // ML-left(k,l) = sum_cc PRML[d+2+cc][k-2-cc] * qm[cc][k-1-cc], cc = TURN+1 .. k-3
+    if (l < n && k > 2 && ss(c, k - 1, k) && ss(c, l, l + 1) && posp(c)[(size_t)d * ld + k + 1] != posp(c)[(size_t)d * ld + k]) {
+      const int cnt = k - 3 - TURN;
+      if (cnt > 0 && TB(c, T_QB, d, k) != 0.)
+        accL = strided_dot(tabp(c, T_PRML) + (size_t)(d + 3 + TURN) * ld + k - 3 - TURN, ld - 1,
+                           tabp(c, T_QM) + (size_t)(TURN + 1) * ld + k - 2 - TURN, ld - 1, cnt, slice, sp.S, -1);
     }
+    sh.part[T + tid] = accP;
+    sh.part[2 * T + tid] = accL;
   }
-  // PR(k,l) = sum_{j>=l+2} Mc(k,j) qm(l+1,j-1)   [k plays the closing 5' end]
-  if (l + 2 <= n && ss(c, l, l + 1)) {
-    const double* A = tabp(c, T_MC);
-    const double* B = tabp(c, T_QM);
-    const int bmax = n - l - 2;
-    for (int b = TURN + 1 + slice; b <= bmax; b += S) accP += A[(size_t)(d + 2 + b) * c.ld + k] * B[(size_t)b * c.ld + l + 1];
-  }
-  // ML-left(k,l) = sum_{i<=k-2} PRML(i,l) qm(i+1,k-1)
-  if (live && l < n && k > 2 && ss(c, k - 1, k) && ss(c, l, l + 1)) {
-    const double* A = tabp(c, T_PRML);
-    const double* B = tabp(c, T_QM);
-    const int cmax = k - 3;  // i = k-2-cc >= 1
-    for (int cc = TURN + 1 + slice; cc <= cmax; cc += S)
-      accL += A[(size_t)(d + 2 + cc) * c.ld + k - 2 - cc] * B[(size_t)cc * c.ld + k - 1 - cc];
-  }
-  part[0 * T + tid] = accI;
-  part[1 * T + tid] = accP;
-  part[2 * T + tid] = accL;
 }
 
-RP_HD void outside_B(Ctx& c, int d, int i0, int C, int tid, int T, const double* part) {
+RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   const DevModel& M = *c.M;
+  const int T = sh.T;
   const Split sp = make_split(C, T);
   if (tid >= sp.Cp || tid >= C) return;
   const int k = i0 + tid, l = k + d, n = c.n;
   double sI = 0., sP = 0., sL = 0.;
   for (int s = 0; s < sp.S; s++) {
-    sI += part[0 * T + s * sp.Cp + tid];
-    sP += part[1 * T + s * sp.Cp + tid];
-    sL += part[2 * T + s * sp.Cp + tid];
+    sP += sh.part[T + s * sp.Cp + tid];
+    sL += sh.part[2 * T + s * sp.Cp + tid];
   }
   const double* scale = vecp(c, V_SCALE);
   const bool mlr = l < n && ss(c, l, l + 1);  // something may follow l inside a multiloop
@@ -551,6 +717,11 @@ RP_HD void outside_B(Ctx& c, int d, int i0, int C, int tid, int T, const double*
   const int type = pair_type(base(c, k), base(c, l));
   double out = 0.;
   if (type && TB(c, T_QB, d, k) != 0.) {
+    if ((n - 1 - d) >= 2) {
+      const ISplit is = make_isplit(c, d, i0, C, T);
+      const int r = (int)posp(c)[(size_t)d * c.ld + k] - is.lo;
+      for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+    }
     const double q5 = k > 1 ? TB(c, T_Q, k - 2, 1) : 1.0;
     const double q3 = l < n ? TB(c, T_Q, n - l - 1, l + 1) : 1.0;
     out = q5 * q3 * c.invZ *

@@ -9,14 +9,18 @@
 
 namespace rp {
 
-// part: scratch of 3*T doubles shared by the CTA.  dense: base of the dense
+// sh: CTA-shared scratch (see Shared).  dense: base of the dense
 // float output.  logz: 3 doubles per pair (s1, s2, s1&s2) or nullptr.
 template <class Exec>
-RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* logz, double* part) {
-  const int T = ex.nthreads();
+RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* logz, const Shared& sh) {
+  const int T = sh.T;
   const int n = c.n;
-  ex.phase([&](int tid) { prologue(c, tid, T); });
-  ex.phase([&](int tid) { prologue2(c, tid, T); });
+  if (n + 2 <= RP_SMEM_SEQ) {
+    ex.phase([&](int tid) { stage_sequence(c, sh, tid); });
+    c.S = sh.S;
+  }
+  ex.phase([&](int tid) { prologue(c, sh, tid); });
+  ex.phase([&](int tid) { prologue2(c, sh, tid); });
 
   // ---- inside: anti-diagonal wavefront, shortest spans first
   for (int d = TURN + 1; d <= n - 1; d++) {
@@ -24,8 +28,8 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
     const int chunk = make_split(cells, T).Cp;
     for (int i0 = 1; i0 <= cells; i0 += chunk) {
       const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
-      ex.phase([&](int tid) { inside_A(c, d, i0, C, tid, T, part); });
-      ex.phase([&](int tid) { inside_B(c, d, i0, C, tid, T, part); });
+      ex.phase([&](int tid) { inside_A(c, sh, d, i0, C, tid); });
+      ex.phase([&](int tid) { inside_B(c, sh, d, i0, C, tid); });
     }
   }
   inside_end(c);
@@ -38,15 +42,15 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
   // ---- outside: longest spans first
   for (int d = n - 1; d >= TURN + 1; d--) {
     if (c.cp > 0) {
-      ex.phase([&](int tid) { outside_nick1(c, d, tid, T); });
-      ex.phase([&](int tid) { outside_nick2(c, d, tid, T); });
+      ex.phase([&](int tid) { outside_nick1(c, sh, d, tid); });
+      ex.phase([&](int tid) { outside_nick2(c, sh, d, tid); });
     }
     const int cells = n - d;
     const int chunk = make_split(cells, T).Cp;
     for (int i0 = 1; i0 <= cells; i0 += chunk) {
       const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
-      ex.phase([&](int tid) { outside_A(c, d, i0, C, tid, T, part); });
-      ex.phase([&](int tid) { outside_B(c, d, i0, C, tid, T, part); });
+      ex.phase([&](int tid) { outside_A(c, sh, d, i0, C, tid); });
+      ex.phase([&](int tid) { outside_B(c, sh, d, i0, C, tid); });
     }
   }
 

@@ -39,12 +39,14 @@ extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, i
   p.out_up = (kind == rp::KIND_LINEAR && up && max_w > 0) ? (long long)nbp : -1;
   p.out_hp = (kind == rp::KIND_COFOLD && hp) ? (long long)(nbp + nup) : -1;
   std::vector<double> ws(rp::slot_doubles(n), 1e300);  // poison: stale data must never be read
-  std::vector<double> part(3 * (size_t)T, 0.0);
+  std::vector<double> smem(rp::shared_bytes(T) / sizeof(double) + 2, 0.0);
+  rp::Shared sh;
+  rp::carve_shared(sh, smem.data(), T);
   double lz[3] = {0, 0, 0};
   rp::Ctx c;
   rp::bind_ctx(c, &M, S.data(), p, ws.data());
   SerialExec ex{T};
-  rp::solve_mcc(ex, c, p, dense.data(), lz, part.data());
+  rp::solve_mcc(ex, c, p, dense.data(), lz, sh);
   if (p.out_bp >= 0) std::memcpy(bp, dense.data(), nbp * sizeof(float));
   if (p.out_up >= 0) std::memcpy(up, dense.data() + nbp, nup * sizeof(float));
   if (p.out_hp >= 0) std::memcpy(hp, dense.data() + nbp + nup, nhp * sizeof(float));
