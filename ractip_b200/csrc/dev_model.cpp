@@ -10,7 +10,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <vector>
 
 namespace rp {
 namespace {
@@ -138,46 +137,33 @@ int build_dev_model(const rp_model& m, DevModel* out) {
   for (int i = 0; i < D.n_tri; i++) D.exptri[i] = bf(m.Triloop37[i]);
   for (int i = 0; i < D.n_hex; i++) D.exphex[i] = bf(m.Hexaloop37[i]);
 
-  // Factorised interior loops.  For (u1,u2) outside the table-driven small
-  // cases the loop weight splits into  f(closing pair) * f(inner pair) * g(u1,u2):
-  //   generic   (us>=2, not 2x2/2x3): expinternal[u]*expninio[|u1-u2|], pair factors expmismatchI
-  //   1xn       (us==1, ul>=3)      : expinternal[u]*expninio[ul-1],   pair factors expmismatch1nI
-  //   bulge     (us==0, ul>=2)      : expbulge[ul],                    pair factors expTermAU^[type>2]
-  // stack, 1-bulge, 1x1, 1x2, 2x2 and 2x3 loops are evaluated directly.
-  std::vector<Tap> lists[TAP_CLASSES];
+  // Factorised interior loops (see dev_model.h for the classes).
   for (int u1 = 0; u1 <= MAXLOOP; u1++)
-    for (int u2 = 0; u1 + u2 <= MAXLOOP; u2++) {
+    for (int u2 = 0; u2 < GROW_LD; u2++) {
+      D.grow[u1][u2] = 0.;
+      D.gfull[u1][u2] = 0.;
+      D.gcls[u1][u2] = CLS_NONE;
+      if (u1 + u2 > MAXLOOP) continue;
       const int ul = std::max(u1, u2), us = std::min(u1, u2);
-      int cls = -1;
+      int cls = CLS_SPECIAL;
       double g = 0;
       if (us == 0) {
-        if (ul >= 2) { cls = TAP_BULGE; g = D.expbulge[ul]; }
+        if (ul >= 2) { cls = CLS_BULGE; g = D.expbulge[ul]; }
       } else if (us == 1) {
-        if (ul >= 3) { cls = TAP_1N; g = D.expinternal[ul + us] * D.expninio[ul - us]; }
+        if (ul >= 3) { cls = CLS_1N; g = D.expinternal[ul + us] * D.expninio[ul - us]; }
       } else if (!(us == 2 && (ul == 2 || ul == 3))) {
-        cls = TAP_GENERIC;
+        cls = CLS_GENERIC;
         g = D.expinternal[ul + us] * D.expninio[ul - us];
       }
-      if (cls < 0) continue;
-      Tap t;
-      t.dd = static_cast<int16_t>(u1 + u2 + 2);
-      t.po = static_cast<int16_t>(u1 + 1);
-      t.u2 = u2;
-      t.g = g * D.scale_small[u1 + u2 + 2];
-      lists[cls].push_back(t);
+      g *= D.scale_small[u1 + u2 + 2];
+      D.gcls[u1][u2] = static_cast<uint8_t>(cls);
+      if (cls == CLS_SPECIAL) continue;
+      D.gfull[u1][u2] = g;
+      const int row_cls = u1 == 0 ? CLS_BULGE : (u1 == 1 ? CLS_1N : CLS_GENERIC);
+      if (cls == row_cls) D.grow[u1][u2] = g;
+      else if (u2 == 0) D.ghead_b[u1] = g;  // rows >= 2: bulge (u1,0)
+      else D.ghead_1[u1] = g;               // rows >= 3: 1xn (u1,1)
     }
-  for (int c = 0; c < TAP_CLASSES; c++) {
-    std::stable_sort(lists[c].begin(), lists[c].end(), [](const Tap& a, const Tap& b) { return a.dd < b.dd; });
-    if (lists[c].size() > static_cast<size_t>(MAX_TAPS)) return RP_ERR_UNSUPPORTED;
-    D.ntaps[c] = static_cast<int>(lists[c].size());
-    std::copy(lists[c].begin(), lists[c].end(), D.taps[c]);
-    for (int x = 0; x < MAXLOOP + 4; x++) {
-      int cnt = 0;
-      for (const Tap& t : lists[c])
-        if (t.dd <= x) cnt++;
-      D.tap_prefix[c][x] = cnt;
-    }
-  }
   return RP_OK;
 }
 

@@ -16,18 +16,19 @@ namespace rp {
 constexpr int TURN = RP_TURN;
 constexpr int MAXLOOP = RP_MAXLOOP;
 
-// One term of the factorised interior-loop sum: inner pair sits `dd` diagonals
-// below the closing pair and `po` positions to the right of it
-// (dd = u1+u2+2, po = u1+1); g = loop weight that depends on (u1,u2) only,
-// already multiplied by scale[u1+u2+2].
-struct Tap {
-  int16_t dd, po;
-  int32_t u2;
-  double g;
-};
-
-enum { TAP_GENERIC = 0, TAP_1N = 1, TAP_BULGE = 2, TAP_CLASSES = 3 };
-constexpr int MAX_TAPS = 384;
+// Factorised interior loops.  Outside the table-driven small cases the weight
+// of the loop (u1 unpaired on the 5' side, u2 on the 3' side) splits into
+//     f(closing pair) * f(inner pair) * g(u1,u2)
+// with three classes of pair factors:
+//   GENERIC (us>=2, not 2x2/2x3): g = expinternal[u]*expninio[|u1-u2|], f = expmismatchI
+//   ONE_N   (us==1, ul>=3)      : g = expinternal[u]*expninio[ul-1],   f = expmismatch1nI
+//   BULGE   (us==0, ul>=2)      : g = expbulge[ul],                    f = expTermAU^[type>2]
+// so the sum over inner pairs becomes, per class, a weighted sum over a table
+// that already carries the inner pair's factor.  All g below include
+// scale[u1+u2+2].  Stack, 1-bulge, 1x1, 1x2, 2x2 and 2x3 loops do not factorise
+// (class SPECIAL) and are evaluated directly.
+enum { CLS_GENERIC = 0, CLS_1N = 1, CLS_BULGE = 2, CLS_SPECIAL = 3, CLS_NONE = 255 };
+constexpr int GROW_LD = 32;
 
 struct DevModel {
   double pf_scale, scale1, mlb1;  // scale1 = 1/pf_scale, mlb1 = expMLbase*scale1
@@ -46,10 +47,16 @@ struct DevModel {
   int tetra_code[200], tri_code[40], hex_code[200];
   double exptetra[200], exptri[40], exphex[200];
   int special_hp;
-  // factorised interior loops, per class, sorted by dd ascending
-  int ntaps[TAP_CLASSES];
-  int tap_prefix[TAP_CLASSES][MAXLOOP + 4];  // #taps with dd <= x
-  Tap taps[TAP_CLASSES][MAX_TAPS];
+  // Row view of the factorised loops: row u1 is scanned along u2.
+  //   row 0 runs over the BULGE table, row 1 over the ONE_N table, rows >=2 over GENERIC;
+  //   grow[u1][u2] is the run weight (0 where (u1,u2) is SPECIAL or handled as a head);
+  //   rows >= 2 have two heads in other tables: u2=0 (BULGE, ghead_b[u1]) and
+  //   u2=1 (ONE_N, ghead_1[u1], rows >= 3).
+  double grow[MAXLOOP + 1][GROW_LD];
+  double ghead_b[GROW_LD], ghead_1[GROW_LD];
+  // Full (u1,u2) view for the unpaired-window gap sums.
+  double gfull[MAXLOOP + 1][GROW_LD];
+  uint8_t gcls[MAXLOOP + 1][GROW_LD];
   // integer view for pf_duplex (scale_parameters semantics at 37 C)
   int i_dangle5[8][5], i_dangle3[8][5], i_mmExt[8][5][5];
   int i_stack[8][8], i_bulge[31], i_internal[31], i_mmI[8][5][5], i_mm1n[8][5][5], i_mm23[8][5][5];

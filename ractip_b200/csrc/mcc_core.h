@@ -103,29 +103,24 @@ constexpr int RP_SMEM_SEQ = 4096;  // sequences up to this length are staged in 
 struct Shared {
   int T;
   double* part;     // [3][T] partial sums of the current phase
-  double* tap_g;    // [TAP_CLASSES][MAX_TAPS] loop weights (x scale)
-  int* tap_off;     // [TAP_CLASSES][MAX_TAPS] po - dd*ld for the current problem
-  uint8_t* tap_po;  // [TAP_CLASSES][MAX_TAPS]
-  uint8_t* tap_u2;  // [TAP_CLASSES][MAX_TAPS]
+  double* grow;     // [MAXLOOP+1][GROW_LD] run weights of the factorised interior loops (DevModel::grow)
+  double* ghead_b;  // [GROW_LD]
+  double* ghead_1;  // [GROW_LD]
   double* red;      // [128] small reductions (nick sums)
   uint8_t* S;       // [RP_SMEM_SEQ + 8] staged sequence
 };
 RP_HD size_t shared_bytes(int T) {
-  return sizeof(double) * (3 * (size_t)T + TAP_CLASSES * MAX_TAPS + 128) + sizeof(int) * TAP_CLASSES * MAX_TAPS +
-         2 * TAP_CLASSES * MAX_TAPS + RP_SMEM_SEQ + 16;
+  return sizeof(double) * (3 * (size_t)T + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
 }
 RP_HD void carve_shared(Shared& sh, void* base, int T) {
   sh.T = T;
   double* p = static_cast<double*>(base);
   sh.part = p; p += 3 * (size_t)T;
-  sh.tap_g = p; p += TAP_CLASSES * MAX_TAPS;
+  sh.grow = p; p += (MAXLOOP + 1) * GROW_LD;
+  sh.ghead_b = p; p += GROW_LD;
+  sh.ghead_1 = p; p += GROW_LD;
   sh.red = p; p += 128;
-  int* q = reinterpret_cast<int*>(p);
-  sh.tap_off = q; q += TAP_CLASSES * MAX_TAPS;
-  uint8_t* b = reinterpret_cast<uint8_t*>(q);
-  sh.tap_po = b; b += TAP_CLASSES * MAX_TAPS;
-  sh.tap_u2 = b; b += TAP_CLASSES * MAX_TAPS;
-  sh.S = b;
+  sh.S = reinterpret_cast<uint8_t*>(p);
 }
 
 // ---------------------------------------------------------------------------
@@ -235,16 +230,11 @@ RP_HD void stage_sequence(const Ctx& c, const Shared& sh, int tid) {
 RP_HD void prologue(Ctx& c, const Shared& sh, int tid) {
   const DevModel& M = *c.M;
   const int n = c.n, T = sh.T;
-  // interior-loop taps into shared memory; the table offset depends on this problem's ld
-  for (int x = tid; x < TAP_CLASSES * MAX_TAPS; x += T) {
-    const int cl = x / MAX_TAPS, t = x % MAX_TAPS;
-    if (t < M.ntaps[cl]) {
-      const Tap tp = M.taps[cl][t];
-      sh.tap_g[x] = tp.g;
-      sh.tap_off[x] = (int)tp.po - (int)tp.dd * c.ld;
-      sh.tap_po[x] = (uint8_t)tp.po;
-      sh.tap_u2[x] = (uint8_t)tp.u2;
-    }
+  // interior-loop run weights into shared memory
+  for (int x = tid; x < (MAXLOOP + 1) * GROW_LD; x += T) sh.grow[x] = M.grow[x / GROW_LD][x % GROW_LD];
+  for (int x = tid; x < GROW_LD; x += T) {
+    sh.ghead_b[x] = M.ghead_b[x];
+    sh.ghead_1[x] = M.ghead_1[x];
   }
   // scale[k] = pf_scale^-k, mlb[k] = (expMLbase/pf_scale)^k: built by repeated
   // multiplication by one thread so that every consumer sees the same values
@@ -330,30 +320,61 @@ RP_HD void prologue2(Ctx& c, const Shared& sh, int tid) {
 // ---------------------------------------------------------------------------
 // shared pieces of the inside and outside phases
 // ---------------------------------------------------------------------------
-// sum over the taps of one class that slice `s` of `S` owns; Bc points at the
-// table entry of the closing cell, sign=+1 inside (inner pairs lie dd diagonals
-// below), -1 outside (enclosing pairs lie dd diagonals above).
-template <int SIGN, bool GUARD>
-RP_HD double tap_sum(const double* Bc, const double* g, const int* off, const uint8_t* po, const uint8_t* u2, int nt,
-                     int s, int S, int maxpo, int maxu2) {
+// weighted sum along one row of the factorised interior loops:
+//   sum_{u2=lo..hi} g[u2] * p[u2*step]
+RP_HD double row_sum(const double* g, const double* p, int step, int lo, int hi) {
   double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-  int t = s;
-  for (; t + 3 * S < nt; t += 4 * S) {
-    double v0 = Bc[SIGN * off[t]], v1 = Bc[SIGN * off[t + S]], v2 = Bc[SIGN * off[t + 2 * S]], v3 = Bc[SIGN * off[t + 3 * S]];
-    if (GUARD) {
-      v0 = (po[t] <= maxpo && u2[t] <= maxu2) ? v0 : 0.;
-      v1 = (po[t + S] <= maxpo && u2[t + S] <= maxu2) ? v1 : 0.;
-      v2 = (po[t + 2 * S] <= maxpo && u2[t + 2 * S] <= maxu2) ? v2 : 0.;
-      v3 = (po[t + 3 * S] <= maxpo && u2[t + 3 * S] <= maxu2) ? v3 : 0.;
-    }
-    a0 += g[t] * v0; a1 += g[t + S] * v1; a2 += g[t + 2 * S] * v2; a3 += g[t + 3 * S] * v3;
+  const double* q = p + (long)lo * step;
+  g += lo;
+  int cnt = hi - lo + 1;
+  for (; cnt >= 4; cnt -= 4) {
+    a0 += g[0] * q[0];
+    a1 += g[1] * q[step];
+    a2 += g[2] * q[2 * step];
+    a3 += g[3] * q[3 * step];
+    g += 4;
+    q += 4 * step;
   }
-  for (; t < nt; t += S) {
-    double v = Bc[SIGN * off[t]];
-    if (GUARD) v = (po[t] <= maxpo && u2[t] <= maxu2) ? v : 0.;
-    a0 += g[t] * v;
+  for (; cnt > 0; cnt--) {
+    a0 += g[0] * q[0];
+    g++;
+    q += step;
   }
   return (a0 + a1) + (a2 + a3);
+}
+
+// The factorised part of the interior-loop sum of one cell, restricted to the
+// row pairs (q, 30-q), q = sl, sl+SI, ... (each pair holds 32 terms, so slices
+// are balanced).  SIGN=+1: inside, inner pair (i+1+u1, j-1-u2) lies u1+u2+2
+// diagonals below the cell; SIGN=-1: outside, enclosing pair (k-1-u1, l+1+u2)
+// lies above.  cell0 = d*ld + i.  Bounds: u1 <= u1max, u2 <= u2cap,
+// u1+u2+2 <= ddmax; every element touched is a valid cell, so no guards.
+template <int SIGN>
+RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, const double* TA, int cell0, int ld,
+                         int u1max, int u2cap, int ddmax, int sl, int SI, double& sI, double& s1, double& sA) {
+  const int step = -SIGN * ld;
+  for (int q = sl; q <= MAXLOOP / 2; q += SI) {
+    for (int h = 0; h < 2; h++) {
+      const int u1 = h == 0 ? q : MAXLOOP - q;
+      if (h == 1 && u1 == q) break;
+      if (u1 > u1max) continue;
+      int u2hi = MAXLOOP - u1;
+      if (u2cap < u2hi) u2hi = u2cap;
+      if (ddmax - 2 - u1 < u2hi) u2hi = ddmax - 2 - u1;
+      if (u2hi < 0) continue;
+      const int o0 = cell0 - SIGN * ((u1 + 2) * ld - (1 + u1));  // element (u1, u2=0)
+      const double* g = sh.grow + u1 * GROW_LD;
+      if (u1 == 0) {
+        if (u2hi >= 2) sA += row_sum(g, TA + o0, step, 2, u2hi);
+      } else if (u1 == 1) {
+        if (u2hi >= 3) s1 += row_sum(g, T1 + o0, step, 3, u2hi);
+      } else {
+        sA += sh.ghead_b[u1] * TA[o0];
+        if (u2hi >= 1) s1 += sh.ghead_1[u1] * T1[o0 + step];
+        if (u2hi >= 2) sI += row_sum(g, TI + o0, step, 2, u2hi);
+      }
+    }
+  }
 }
 
 // the nine loop shapes that do not factorise, closing pair `type` with
@@ -371,25 +392,34 @@ RP_HD double special_loop(const DevModel& M, int s, int type, int t2r, int si1, 
   }
 }
 
-// sum_x A[x*sa] * B[x*sb] for x = s, s+S, ... < cnt, skipping x == skip
-RP_HD double strided_dot(const double* A, long sa, const double* B, long sb, int cnt, int s, int S, int skip) {
+// sum of A[x*sa] * B[x*sb] over x in [x0,x1) with x = s (mod S)
+RP_HD double dot_range(const double* A, int sa, const double* B, int sb, int x0, int x1, int s, int S) {
+  int x = x0 + ((s - x0) % S + S) % S;
+  if (x >= x1) return 0.;
+  int cnt = (x1 - 1 - x) / S + 1;
+  const double* a = A + (long)x * sa;
+  const double* b = B + (long)x * sb;
+  const int da = S * sa, db = S * sb;
   double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-  int x = s;
-  for (; x + 3 * S < cnt; x += 4 * S) {
-    double p0 = A[(long)x * sa] * B[(long)x * sb];
-    double p1 = A[(long)(x + S) * sa] * B[(long)(x + S) * sb];
-    double p2 = A[(long)(x + 2 * S) * sa] * B[(long)(x + 2 * S) * sb];
-    double p3 = A[(long)(x + 3 * S) * sa] * B[(long)(x + 3 * S) * sb];
-    a0 += (x == skip) ? 0. : p0;
-    a1 += (x + S == skip) ? 0. : p1;
-    a2 += (x + 2 * S == skip) ? 0. : p2;
-    a3 += (x + 3 * S == skip) ? 0. : p3;
+  for (; cnt >= 4; cnt -= 4) {
+    a0 += a[0] * b[0];
+    a1 += a[da] * b[db];
+    a2 += a[2 * da] * b[2 * db];
+    a3 += a[3 * da] * b[3 * db];
+    a += 4 * da;
+    b += 4 * db;
   }
-  for (; x < cnt; x += S) {
-    double p = A[(long)x * sa] * B[(long)x * sb];
-    a0 += (x == skip) ? 0. : p;
+  for (; cnt > 0; cnt--) {
+    a0 += a[0] * b[0];
+    a += da;
+    b += db;
   }
   return (a0 + a1) + (a2 + a3);
+}
+// same over x in [0,cnt) skipping x == skip (the split that would fall on the nick)
+RP_HD double strided_dot(const double* A, int sa, const double* B, int sb, int cnt, int s, int S, int skip) {
+  if (skip < 0 || skip >= cnt) return dot_range(A, sa, B, sb, 0, cnt, s, S);
+  return dot_range(A, sa, B, sb, 0, skip, s, S) + dot_range(A, sa, B, sb, skip + 1, cnt, s, S);
 }
 
 // work split of the interior-loop items of a chunk: cnt pairable cells x SI slices
@@ -405,8 +435,8 @@ RP_HD ISplit make_isplit(const Ctx& c, int d, int i0, int C, int T) {
   if (cp > T) cp = T;
   if (cp < 32) cp = 32;
   s.cntp = cp;
-  s.SI = T / cp;
-  if (s.SI < 1) s.SI = 1;
+  int si = T / cp;  // slices per cell: a power of two <= 16 (there are 16 row pairs)
+  s.SI = si >= 16 ? 16 : si >= 8 ? 8 : si >= 4 ? 4 : si >= 2 ? 2 : 1;
   return s;
 }
 
@@ -429,19 +459,13 @@ RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int ti
       // strand guards: inner 5' end must stay on i's strand, inner 3' end on j's
       const int maxpo = (c.cp > 0 && i < c.cp) ? c.cp - 1 - i : 1000;
       const int maxu2 = (c.cp > 0 && j >= c.cp) ? j - 1 - c.cp : 1000;
-      const bool guard = maxpo < MAXLOOP + 1 || maxu2 < MAXLOOP;
       const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
-      const int tabs[TAP_CLASSES] = {T_QBI, T_QB1N, T_QBAU};
-      const double fac[TAP_CLASSES] = {M.mmI[type][si1][sj1], M.mm1n[type][si1][sj1], type > 2 ? M.expTermAU : 1.0};
-      double accI = 0.;
-      for (int cl = 0; cl < TAP_CLASSES; cl++) {
-        const int nt = M.tap_prefix[cl][ddmax];
-        const double* Bc = tabp(c, tabs[cl]) + (size_t)d * ld + i;
-        const int o = cl * MAX_TAPS;
-        const double a = guard ? tap_sum<1, true>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2)
-                               : tap_sum<1, false>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2);
-        accI += fac[cl] * a;
-      }
+      int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
+      if (maxpo - 1 < u1max) u1max = maxpo - 1;
+      double sI = 0., s1 = 0., sA = 0.;
+      interior_rows<1>(sh, tabp(c, T_QBI), tabp(c, T_QB1N), tabp(c, T_QBAU), d * (int)ld + i, (int)ld, u1max, maxu2,
+                       ddmax, sl, is.SI, sI, s1, sA);
+      double accI = M.mmI[type][si1][sj1] * sI + M.mm1n[type][si1][sj1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
       // table-driven small loops
       for (int s = sl; s < RP_N_SPECIAL; s += is.SI) {
         int u1, u2;
@@ -638,17 +662,12 @@ RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int t
       if (maxpo >= 1 && maxu2 >= 0 && TB(c, T_QB, d, k) != 0.) {
         const int type = pair_type(base(c, k), base(c, l));
         const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
-        const bool guard = maxpo < MAXLOOP + 1 || maxu2 < MAXLOOP;
-        const int tabs[TAP_CLASSES] = {T_OUTI, T_OUT1N, T_OUTAU};
-        const double fac[TAP_CLASSES] = {M.mmI[t2][sq1][sp1], M.mm1n[t2][sq1][sp1], type > 2 ? M.expTermAU : 1.0};
-        for (int cl = 0; cl < TAP_CLASSES; cl++) {
-          const int nt = M.tap_prefix[cl][ddmax];
-          const double* Bc = tabp(c, tabs[cl]) + (size_t)d * ld + k;
-          const int o = cl * MAX_TAPS;
-          const double a = guard ? tap_sum<-1, true>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2)
-                                 : tap_sum<-1, false>(Bc, sh.tap_g + o, sh.tap_off + o, sh.tap_po + o, sh.tap_u2 + o, nt, sl, is.SI, maxpo, maxu2);
-          accI += fac[cl] * a;
-        }
+        int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
+        if (maxpo - 1 < u1max) u1max = maxpo - 1;
+        double sI = 0., s1 = 0., sA = 0.;
+        interior_rows<-1>(sh, tabp(c, T_OUTI), tabp(c, T_OUT1N), tabp(c, T_OUTAU), d * (int)ld + k, (int)ld, u1max,
+                          maxu2, ddmax, sl, is.SI, sI, s1, sA);
+        accI = M.mmI[t2][sq1][sp1] * sI + M.mm1n[t2][sq1][sp1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
         for (int s = sl; s < RP_N_SPECIAL; s += is.SI) {
           int u1, u2;
           special_uv(s, u1, u2);
@@ -775,12 +794,25 @@ RP_HD void unstru_hairpin(Ctx& c, int tid, int T) {
     TB(c, T_DG, d, i) = v;
   }
 }
-// U2 (side=0): DG(p,k) += sum over interior loops closed by (p,o) with inner pair (k,l)
-// U3 (side=1): DG(l,o) += same loops, 3' gap
+// U2 (side=0): DG(p,k) += weight of all interior loops closed by some (p,o) with inner pair (k,l): 5' gap (p,k)
+// U3 (side=1): DG(l,o) += the same loops seen from their 3' gap (l,o)
+// One item per gap.  For the factorised classes the sum over the free pair end is a dot
+// product of two table rows that already carry the pair factors:
+//   side 0:  sum_l  outX(p, l+1+u2) * qbX(k, l)          (both advance one diagonal per l)
+//   side 1:  sum_p  outX(p, o)      * qbX(p+1+u1, l)     (both step one diagonal down, one cell right)
+RP_HD int special_index(int u1, int u2) {
+  // inverse of special_uv: (0,0)->0 (1,0)->1 (0,1)->2 (1,1)->3 (1,2)->4 (2,1)->5 (2,2)->6 (2,3)->7 (3,2)->8
+  if (u1 == 0) return u2 == 0 ? 0 : 2;
+  if (u1 == 1) return u2 == 0 ? 1 : (u2 == 1 ? 3 : 4);
+  if (u1 == 2) return u2 == 1 ? 5 : (u2 == 2 ? 6 : 7);
+  return 8;
+}
 RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
   const DevModel& M = *c.M;
-  const int n = c.n;
+  const int n = c.n, ld = c.ld;
   const int items = n * (MAXLOOP + 1);
+  const int tabO[3] = {T_OUTI, T_OUT1N, T_OUTAU};
+  const int tabQ[3] = {T_QBI, T_QB1N, T_QBAU};
   for (int x = tid; x < items; x += T) {
     const int ug = x / n;      // size of the gap this item owns
     const int a = x % n + 1;   // gap is the open interval (a, a+ug+1)
@@ -788,40 +820,49 @@ RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
     if (b > n || ug < 1) continue;  // an empty gap cannot contain a window
     double acc = 0.;
     if (side == 0) {
-      // p=a, k=b, u1=ug; run over l and u2 (o=l+1+u2)
       const int p = a, k = b, u1 = ug;
-      const int sp1 = base(c, k - 1), si1 = base(c, p + 1);
-      for (int l = k + TURN + 1; l < n; l++) {
-        const int t2 = pair_type(base(c, k), base(c, l));
-        const double qb = t2 ? TB(c, T_QB, l - k, k) : 0.;
-        if (qb == 0.) continue;
-        const int sq1 = base(c, l + 1);
-        for (int u2 = 0; u1 + u2 <= MAXLOOP && l + 1 + u2 <= n; u2++) {
-          const int o = l + 1 + u2;
-          const int t1 = pair_type(base(c, p), base(c, o));
-          if (!t1) continue;
-          const double ou = TB(c, T_OUT, o - p, p);
-          if (ou == 0.) continue;
-          acc += ou * qb * int_loop(M, u1, u2, t1, rtype(t2), si1, base(c, o - 1), sp1, sq1) * M.scale_small[u1 + u2 + 2];
+      for (int u2 = 0; u1 + u2 <= MAXLOOP; u2++) {
+        const int lmin = k + TURN + 1, lmax = n - 1 - u2;
+        if (lmax < lmin) break;
+        const int cls = M.gcls[u1][u2];
+        if (cls != CLS_SPECIAL) {
+          acc += M.gfull[u1][u2] * dot_range(tabp(c, tabO[cls]) + (size_t)(lmin + 1 + u2 - p) * ld + p, ld,
+                                             tabp(c, tabQ[cls]) + (size_t)(lmin - k) * ld + k, ld, 0, lmax - lmin + 1, 0, 1);
+        } else {
+          const int sidx = special_index(u1, u2);
+          const int sp1 = base(c, k - 1), si1 = base(c, p + 1);
+          for (int l = lmin; l <= lmax; l++) {
+            const double qb = TB(c, T_QB, l - k, k);
+            if (qb == 0.) continue;
+            const int o = l + 1 + u2;
+            const double ou = TB(c, T_OUT, o - p, p);
+            if (ou == 0.) continue;
+            acc += ou * qb * special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
+                                          si1, base(c, o - 1), sp1, base(c, l + 1));
+          }
         }
       }
     } else {
-      // l=a, o=b, u2=ug; run over p and u1 (k=p+1+u1)
       const int l = a, o = b, u2 = ug;
-      const int sq1 = base(c, l + 1), sj1 = base(c, o - 1);
-      for (int p = 1; p + 1 + TURN + 1 <= l; p++) {
-        const int t1 = pair_type(base(c, p), base(c, o));
-        const double ou = t1 ? TB(c, T_OUT, o - p, p) : 0.;
-        if (ou == 0.) continue;
-        const int si1 = base(c, p + 1);
-        for (int u1 = 0; u1 + u2 <= MAXLOOP; u1++) {
-          const int k = p + 1 + u1;
-          if (l - k <= TURN) break;
-          const int t2 = pair_type(base(c, k), base(c, l));
-          if (!t2) continue;
-          const double qb = TB(c, T_QB, l - k, k);
-          if (qb == 0.) continue;
-          acc += ou * qb * int_loop(M, u1, u2, t1, rtype(t2), si1, sj1, base(c, k - 1), sq1) * M.scale_small[u1 + u2 + 2];
+      for (int u1 = 0; u1 + u2 <= MAXLOOP; u1++) {
+        const int pmax = l - TURN - 2 - u1;  // k = p+1+u1 <= l-TURN-1
+        if (pmax < 1) break;
+        const int cls = M.gcls[u1][u2];
+        if (cls != CLS_SPECIAL) {
+          acc += M.gfull[u1][u2] * dot_range(tabp(c, tabO[cls]) + (size_t)(o - 1) * ld + 1, 1 - ld,
+                                             tabp(c, tabQ[cls]) + (size_t)(l - 2 - u1) * ld + 2 + u1, 1 - ld, 0, pmax, 0, 1);
+        } else {
+          const int sidx = special_index(u1, u2);
+          const int sq1 = base(c, l + 1), sj1 = base(c, o - 1);
+          for (int p = 1; p <= pmax; p++) {
+            const double ou = TB(c, T_OUT, o - p, p);
+            if (ou == 0.) continue;
+            const int k = p + 1 + u1;
+            const double qb = TB(c, T_QB, l - k, k);
+            if (qb == 0.) continue;
+            acc += ou * qb * special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
+                                          base(c, p + 1), sj1, base(c, k - 1), sq1);
+          }
         }
       }
     }
