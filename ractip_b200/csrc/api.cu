@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -28,6 +29,7 @@ struct rp_ctx {
   int device = 0;
   int sm_count = 0;
   int ctas_per_sm = 0;
+  int threads = RP_MCC_THREADS;  // CTA width of the wavefront kernel (RP_MCC_THREADS env var narrows it: tuning aid)
   rp::DevModel* d_model = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
@@ -254,7 +256,11 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
   if ((e = cudaMalloc(&ctx->d_model, sizeof(rp::DevModel))) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMemcpy(ctx->d_model, host.data(), sizeof(rp::DevModel), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail(RP_ERR_CUDA, cudaGetErrorString(e));
-  ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(RP_MCC_THREADS);
+  if (const char* e = std::getenv("RP_MCC_THREADS")) {
+    int t = std::atoi(e) / 32 * 32;
+    if (t >= 64 && t <= RP_MCC_THREADS) ctx->threads = t;
+  }
+  ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads);
   if (ctx->ctas_per_sm < 1)
     return bail(RP_ERR_CUDA, "rp_create: kernel image not loadable on this device (built for sm_100a)");
   *out = ctx;
@@ -422,7 +428,7 @@ int rp_batch_run(rp_batch* b) {
   CU(cudaEventRecord(ctx->ev[0], st));
   int launches = 0;
   if (b->n_mcc > 0) {
-    CU(rp::launch_mcc(d, grid, RP_MCC_THREADS, st));
+    CU(rp::launch_mcc(d, grid, ctx->threads, st));
     launches++;
   }
   if (b->n_duplex > 0) {

@@ -12,7 +12,7 @@
 #define RP_MCC_THREADS 512
 #endif
 #ifndef RP_MCC_MIN_CTAS
-#define RP_MCC_MIN_CTAS 1
+#define RP_MCC_MIN_CTAS 2
 #endif
 
 namespace rp {
