@@ -16,6 +16,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "dev_model.h"
@@ -40,6 +41,10 @@ struct rp_ctx {
   bool timing_pending = false;
   bool timed_copies = false;
   std::string err;
+  // device buffers of destroyed batches, reused by the next batch (cudaMalloc/cudaFree cost
+  // milliseconds and cudaFree synchronises the device: fatal for the one-shot host calls)
+  std::vector<std::pair<void*, size_t>> pool_free;
+  std::vector<std::pair<void*, size_t>> pool_live;
 };
 
 struct rp_batch {
@@ -107,6 +112,41 @@ int ensure_workspace(rp_ctx* ctx, size_t bytes) {
   CU(cudaMalloc(&ctx->ws, bytes));
   ctx->ws_bytes = bytes;
   return RP_OK;
+}
+
+cudaError_t pool_alloc(rp_ctx* ctx, void** out, size_t bytes) {
+  bytes = std::max<size_t>(bytes, 256);
+  int best = -1;
+  for (size_t k = 0; k < ctx->pool_free.size(); k++)
+    if (ctx->pool_free[k].second >= bytes && (best < 0 || ctx->pool_free[k].second < ctx->pool_free[best].second)) best = (int)k;
+  if (best >= 0 && ctx->pool_free[best].second <= 4 * bytes + (1 << 20)) {
+    *out = ctx->pool_free[best].first;
+    ctx->pool_live.push_back(ctx->pool_free[best]);
+    ctx->pool_free.erase(ctx->pool_free.begin() + best);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {  // give cached buffers back to the driver and retry once
+    for (auto& f : ctx->pool_free) cudaFree(f.first);
+    ctx->pool_free.clear();
+    e = cudaMalloc(out, bytes);
+  }
+  if (e == cudaSuccess) ctx->pool_live.emplace_back(*out, bytes);
+  return e;
+}
+template <class T>
+cudaError_t pool_alloc(rp_ctx* ctx, T** out, size_t bytes) {
+  return pool_alloc(ctx, reinterpret_cast<void**>(out), bytes);
+}
+void pool_release(rp_ctx* ctx, void* p) {
+  if (!p) return;
+  for (size_t k = 0; k < ctx->pool_live.size(); k++)
+    if (ctx->pool_live[k].first == p) {
+      ctx->pool_free.push_back(ctx->pool_live[k]);
+      ctx->pool_live.erase(ctx->pool_live.begin() + k);
+      return;
+    }
+  cudaFree(p);
 }
 
 // number of CTAs (= workspace slots) for a batch
@@ -272,6 +312,8 @@ int rp_destroy(rp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->ws) cudaFree(ctx->ws);
+  for (auto& f : ctx->pool_free) cudaFree(f.first);
+  for (auto& f : ctx->pool_live) cudaFree(f.first);
   if (ctx->d_model) cudaFree(ctx->d_model);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -302,9 +344,12 @@ int rp_batch_destroy(rp_batch* b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
   }
-  cudaFree(b->d_seq); cudaFree(b->d_probs); cudaFree(b->d_order); cudaFree(b->d_counter);
-  cudaFree(b->d_dense); cudaFree(b->d_logz);
-  cudaFree(b->d_spairs); cudaFree(b->d_recs); cudaFree(b->d_ups); cudaFree(b->d_counts);
+  if (b->ctx) {
+    rp_ctx* ctx = b->ctx;
+    for (void* p : {(void*)b->d_seq, (void*)b->d_probs, (void*)b->d_order, (void*)b->d_counter, (void*)b->d_dense,
+                    (void*)b->d_logz, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
+      pool_release(ctx, p);
+  }
   delete b;
   return RP_OK;
 }
@@ -389,12 +434,12 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   };
   cudaError_t e;
   const size_t np = b->probs.size();
-  if ((e = cudaMalloc(&b->d_seq, seq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc seq");
-  if ((e = cudaMalloc(&b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
-  if ((e = cudaMalloc(&b->d_order, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
-  if ((e = cudaMalloc(&b->d_counter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
-  if ((e = cudaMalloc(&b->d_dense, std::max<size_t>(1, b->total_floats) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense");
-  if ((e = cudaMalloc(&b->d_logz, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logz");
+  if ((e = pool_alloc(ctx, &b->d_seq, seq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc seq");
+  if ((e = pool_alloc(ctx, &b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
+  if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
+  if ((e = pool_alloc(ctx, &b->d_counter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
+  if ((e = pool_alloc(ctx, &b->d_dense, std::max<size_t>(1, b->total_floats) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense");
+  if ((e = pool_alloc(ctx, &b->d_logz, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logz");
   cudaStream_t st = ctx->stream;
   if ((e = cudaMemcpyAsync(b->d_seq, seq.data(), seq.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D seq");
   if (np) {
@@ -483,7 +528,7 @@ int sparse_prepare(rp_batch* b) {
     q.up1_dst = (long long)S.up1; q.up2_dst = (long long)S.up2;
     q.n_up1 = (int)S.n_up1; q.n_up2 = (int)S.n_up2;
   }
-  CU(cudaMalloc(&b->d_spairs, np * sizeof(rp::SparsePair)));
+  CU(pool_alloc(ctx, &b->d_spairs, np * sizeof(rp::SparsePair)));
   CU(cudaMemcpy(b->d_spairs, sp.data(), np * sizeof(rp::SparsePair), cudaMemcpyHostToDevice));
   return RP_OK;
 }
@@ -527,9 +572,9 @@ extern "C" int rp_batch_fetch_sparse(rp_batch* b, rp_rec* recs, size_t n_recs, f
   int rc = sparse_prepare(b);
   if (rc) return rc;
   if (!b->d_recs) {
-    CU(cudaMalloc(&b->d_recs, std::max<size_t>(1, b->total_recs) * sizeof(rp_rec)));
-    CU(cudaMalloc(&b->d_ups, std::max<size_t>(1, b->total_upf) * sizeof(float)));
-    CU(cudaMalloc(&b->d_counts, np * sizeof(rp_sparse_counts)));
+    CU(pool_alloc(ctx, &b->d_recs, std::max<size_t>(1, b->total_recs) * sizeof(rp_rec)));
+    CU(pool_alloc(ctx, &b->d_ups, std::max<size_t>(1, b->total_upf) * sizeof(float)));
+    CU(pool_alloc(ctx, &b->d_counts, np * sizeof(rp_sparse_counts)));
   }
   rc = sparse_launch(b, b->d_recs, b->d_ups, b->d_counts);
   if (rc) return rc;

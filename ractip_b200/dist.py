@@ -1,0 +1,125 @@
+"""Multi-GPU plumbing of the --zscore shuffle batch (one process per GPU).
+
+The shuffles of the loop at reference src/ractip.cpp:1638-1657 are independent
+(only four float accumulators cross iterations, :1626-1627,1655-1656), so rank r
+of W takes shuffles r, r+W, r+2W, ... and runs the probability stage on them.
+What the host-side ILP needs afterwards -- the thresholded variable lists and
+the unpaired-window tables of every shuffle -- is exchanged with ONE all-gather
+of a fixed-capacity byte buffer per rank:
+
+    [ rp_rec records | up floats | rp_sparse_counts ]      (each part 256-B aligned)
+
+Capacities come from rp_sparse_plan (a bound, not a count), so every rank's
+buffer has the same size and no size exchange is needed.  torch.distributed does
+the transport (NCCL over NVLink on GPUs, gloo in the CPU tests); the kernels
+write straight into the buffer through rp_batch_sparse_device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import RpOpts, RpPair, RpSparseLayout
+from .stage import REC_DTYPE, PairRecords
+
+ALIGN = 256
+
+
+def shard_indices(n: int, rank: int, world: int) -> List[int]:
+    """Interleaved shard: balanced even if costs drift along the batch."""
+    return list(range(rank, n, world))
+
+
+def _plan(pairs: Sequence[Tuple[str, str]], opts: RpOpts):
+    lib = _lib.load()
+    n = len(pairs)
+    arr = (RpPair * max(n, 1))()
+    keep = []
+    for k, (a, b) in enumerate(pairs):
+        ba, bb = a.encode(), b.encode()
+        keep.append((ba, bb))
+        arr[k].s1, arr[k].n1, arr[k].s2, arr[k].n2 = ba, len(ba), bb, len(bb)
+    lay = (RpSparseLayout * max(n, 1))()
+    tr, tf = C.c_size_t(), C.c_size_t()
+    rc = lib.rp_sparse_plan(arr, n, C.byref(opts), lay, C.byref(tr), C.byref(tf))
+    if rc:
+        raise RuntimeError("rp_sparse_plan failed: %d" % rc)
+    return lay, tr.value, tf.value
+
+
+def _up(x: int) -> int:
+    return (x + ALIGN - 1) // ALIGN * ALIGN
+
+
+class ShardPlan:
+    """Who computes what, and the layout of the gathered buffer."""
+
+    def __init__(self, pairs: Sequence[Tuple[str, str]], opts: RpOpts, rank: int, world: int):
+        self.pairs, self.opts, self.rank, self.world = list(pairs), opts, rank, world
+        self.n = len(self.pairs)
+        self.shards = [shard_indices(self.n, r, world) for r in range(world)]
+        self.layouts, recs, ups, cnts = [], [], [], []
+        for r in range(world):
+            lay, tr, tf = _plan([self.pairs[i] for i in self.shards[r]], opts)
+            self.layouts.append(lay)
+            recs.append(tr * REC_DTYPE.itemsize)
+            ups.append(tf * 4)
+            cnts.append(len(self.shards[r]) * 16)
+        # identical section sizes on every rank: the maximum over ranks
+        self.rec_bytes, self.up_bytes, self.cnt_bytes = _up(max(recs)), _up(max(ups)), _up(max(cnts))
+        self.nbytes = self.rec_bytes + self.up_bytes + self.cnt_bytes
+
+    @property
+    def my_pairs(self) -> List[Tuple[str, str]]:
+        return [self.pairs[i] for i in self.shards[self.rank]]
+
+    def section_offsets(self) -> Tuple[int, int, int]:
+        return 0, self.rec_bytes, self.rec_bytes + self.up_bytes
+
+    def capacities(self) -> Tuple[int, int]:
+        """(records, floats) the local buffer can hold: what rp_batch_sparse_device is told."""
+        return self.rec_bytes // REC_DTYPE.itemsize, self.up_bytes // 4
+
+    def rec_view(self, buf: np.ndarray) -> np.ndarray:
+        """The record section of one rank's buffer as a structured array."""
+        o_rec = 0
+        usable = self.rec_bytes // REC_DTYPE.itemsize * REC_DTYPE.itemsize
+        return buf[o_rec:o_rec + usable].view(REC_DTYPE)
+
+    def gather(self, local, group=None):
+        """The single collective of the path.  `local` is a uint8 tensor of nbytes (CUDA or CPU)."""
+        import torch
+        import torch.distributed as dist
+        assert local.dtype == torch.uint8 and local.numel() == self.nbytes
+        out = torch.empty(self.world * self.nbytes, dtype=torch.uint8, device=local.device)
+        if self.world == 1:
+            out.copy_(local)
+            return out
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+
+    def unpack(self, gathered: np.ndarray) -> List[PairRecords]:
+        """Gathered bytes (host) -> per-shuffle records in the ORIGINAL batch order."""
+        gathered = np.ascontiguousarray(gathered).view(np.uint8).reshape(self.world, self.nbytes)
+        w = max(self.opts.max_w, 0)
+        out: List[PairRecords] = [None] * self.n  # type: ignore
+        o_rec, o_up, o_cnt = self.section_offsets()
+        for r in range(self.world):
+            buf = gathered[r]
+            recs = self.rec_view(buf)
+            ups = buf[o_up:o_up + self.up_bytes].view(np.float32)
+            cnts = buf[o_cnt:o_cnt + self.cnt_bytes].view(np.int32).reshape(-1, 4)
+            for k, gi in enumerate(self.shards[r]):
+                S = self.layouts[r][k]
+                s1, s2 = self.pairs[gi]
+                nx, ny, nz, ov = (int(v) for v in cnts[k])
+                if ov:
+                    raise RuntimeError(f"record capacity exceeded for shuffle {gi}")
+                out[gi] = PairRecords(
+                    x=recs[S.x:S.x + nx], y=recs[S.y:S.y + ny], z=recs[S.z:S.z + nz],
+                    up1=ups[S.up1:S.up1 + S.n_up1].reshape(len(s1), w),
+                    up2=ups[S.up2:S.up2 + S.n_up2].reshape(len(s2), w))
+        return out
