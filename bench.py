@@ -187,7 +187,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     opts = default_opts()
     stage = ProbabilityStage(model, device=local_rank)
     lib = stage.lib
-    stream = torch.cuda.current_stream(dev)
+    # One explicit (non-default) stream carries the kernels, the NCCL collective and the
+    # timing events.  (The legacy default stream has handle 0, which rp_set_stream reads as
+    # "use the context's own stream": events recorded there would not see the kernels.)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     lib.rp_set_stream(stage.ctx, C.c_void_p(stream.cuda_stream))
 
     def barrier():
@@ -249,6 +254,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         ms = float(tmax.item())
     ms_per_step = ms / args.steps
     value = total_pairs / (ms_per_step * 1e-3)
+    if world > 1:
+        # the timed path must have produced real data: every rank's section of the gathered
+        # buffer carries counts, and this rank's records equal a fresh rp_run_sparse of its shard
+        g = gathered.cpu().numpy().reshape(world, -1)
+        for r in range(world):
+            cnts = g[r][rec_b + up_b:rec_b + up_b + 16 * (len(all_pairs[r::world]) if args.scaling != "weak" else len(mine))]
+            assert cnts.view(np.int32).reshape(-1, 4)[:, :3].sum() > 0, f"rank {r} gathered nothing"
+        chk = stage.run_sparse(mine[:3], opts)
+        mine_recs = g[rank][:rec_b // 12 * 12].view(REC_DTYPE)
+        mine_cnt = g[rank][rec_b + up_b:rec_b + up_b + 16 * len(mine)].view(np.int32).reshape(-1, 4)
+        for k, c in enumerate(chk):
+            S = batch.slayout[k]
+            assert mine_recs[S.x:S.x + int(mine_cnt[k][0])].tolist() == c.x.tolist(), "gathered records differ"
+            assert mine_recs[S.z:S.z + int(mine_cnt[k][2])].tolist() == c.z.tolist(), "gathered records differ"
 
     # ---------------- end to end through the C ABI with host buffers
     n = len(mine)
