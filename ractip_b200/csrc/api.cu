@@ -153,6 +153,10 @@ void pool_release(rp_ctx* ctx, void* p) {
 int grid_for(const rp_ctx* ctx, int nprob, size_t slot_bytes) {
   int g = ctx->sm_count * std::max(1, ctx->ctas_per_sm);
   g = std::min(g, std::max(1, nprob));
+  if (const char* e = std::getenv("RP_GRID")) {  // tuning aid
+    int v = std::atoi(e);
+    if (v >= 1 && v < g) g = v;
+  }
   // keep the workspace within a budget (long sequences: fewer, fatter slots)
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -468,6 +472,15 @@ int rp_batch_run(rp_batch* b) {
   d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order; d.nprob = nprob;
   d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = grid;
   d.dense = b->d_dense; d.logz = b->d_logz;
+  d.prof = nullptr;
+  d.dbg = std::getenv("RP_DEBUG_SKIP") ? std::atoi(std::getenv("RP_DEBUG_SKIP")) : 0;
+  static long long* d_prof = nullptr;
+  const bool profile = std::getenv("RP_PROFILE") != nullptr;
+  if (profile) {
+    if (!d_prof) CU(cudaMalloc(&d_prof, 64 * sizeof(long long)));
+    CU(cudaMemsetAsync(d_prof, 0, 64 * sizeof(long long), ctx->stream));
+    d.prof = d_prof;
+  }
   cudaStream_t st = ctx->stream;
   CU(cudaMemsetAsync(b->d_counter, 0, sizeof(int), st));
   CU(cudaEventRecord(ctx->ev[0], st));
@@ -481,6 +494,16 @@ int rp_batch_run(rp_batch* b) {
     launches++;
   }
   CU(cudaEventRecord(ctx->ev[1], st));
+  if (profile) {
+    long long h[64];
+    CU(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    static const char* names[19] = {"stage", "prologue", "prologue2", "inside_A", "inside_B", "nick1", "nick2", "outside_A", "outside_B", "write_bp", "un_hairpin", "un_gaps0", "un_gaps1", "un_domrows", "un_domcols", "un_mltab", "un_windows", "write_hp", "logz"};
+    long long tot = 0;
+    for (int k = 0; k < 19; k++) tot += h[k];
+    for (int k = 0; k < 19; k++)
+      if (h[32 + k]) std::fprintf(stderr, "[rp_profile] %-11s %6.2f%%  calls %9lld  cycles/call %9.0f\n", names[k], 100.0 * h[k] / tot, h[32 + k], (double)h[k] / h[32 + k]);
+  }
   ctx->timing.kernel_launches = launches;
   ctx->timing_pending = true;
   ctx->timed_copies = false;

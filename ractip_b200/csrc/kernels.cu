@@ -17,11 +17,18 @@ namespace rp {
 namespace {
 
 struct CtaExec {
+  long long* prof;  // optional per-phase cycle counters (RP_PROFILE=1), else null
   __device__ __forceinline__ int nthreads() const { return blockDim.x; }
   template <class F>
-  __device__ __forceinline__ void phase(F f) {
+  __device__ __forceinline__ void phase(int id, F f) {
+    long long t0 = 0;
+    if (prof && threadIdx.x == 0) t0 = clock64();
     f(threadIdx.x);
     __syncthreads();
+    if (prof && threadIdx.x == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(prof + id), (unsigned long long)(clock64() - t0));
+      atomicAdd(reinterpret_cast<unsigned long long*>(prof + 32 + id), 1ull);
+    }
   }
 };
 
@@ -31,6 +38,7 @@ __global__ void __launch_bounds__(RP_MCC_THREADS, RP_MCC_MIN_CTAS) mcc_persisten
   extern __shared__ double smem_raw[];
   __shared__ int s_next;
   CtaExec ex;
+  ex.prof = b.prof;
   Shared sh;
   carve_shared(sh, smem_raw, blockDim.x);
   for (;;) {
@@ -43,6 +51,7 @@ __global__ void __launch_bounds__(RP_MCC_THREADS, RP_MCC_MIN_CTAS) mcc_persisten
     if (p.kind == KIND_DUPLEX) continue;  // handled by duplex_kernel
     Ctx c;
     bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)blockIdx.x * b.slot_stride);
+    c.dbg = b.dbg;
     solve_mcc(ex, c, p, b.dense, b.logz, sh);
   }
 }

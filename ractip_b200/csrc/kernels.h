@@ -9,10 +9,10 @@
 #include "ractip_prob.h"
 
 #ifndef RP_MCC_THREADS
-#define RP_MCC_THREADS 512
+#define RP_MCC_THREADS 1024
 #endif
 #ifndef RP_MCC_MIN_CTAS
-#define RP_MCC_MIN_CTAS 2
+#define RP_MCC_MIN_CTAS 1
 #endif
 
 namespace rp {
@@ -29,6 +29,8 @@ struct BatchDev {
   int nslots;
   float* dense;            // dense fp32 outputs (reference layouts)
   double* logz;            // 3 per pair, may be null
+  long long* prof;         // 64 counters (cycles, calls per phase id) or null
+  int dbg;                 // RP_DEBUG_SKIP bits (tuning aid; results are wrong when set)
 };
 
 struct SparsePair {

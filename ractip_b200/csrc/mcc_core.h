@@ -76,6 +76,7 @@ struct Ctx {
   double* ws;         // slot workspace: T_COUNT tables then V_COUNT vectors
   size_t te, ve;      // elements per table / per vector
   double invZ;        // set after the inside pass
+  int dbg;            // tuning aid (RP_DEBUG_SKIP): 1 skip interior rows, 2 skip split sums, 4 skip gap sums
 };
 
 RP_HD size_t table_elems(int n) { return (size_t)n * (size_t)(n + 1) + 8; }
@@ -86,6 +87,7 @@ RP_HD void bind_ctx(Ctx& c, const DevModel* M, const uint8_t* S, const Problem& 
   c.M = M; c.S = S; c.n = p.n; c.cp = p.cp; c.ld = p.n + 1; c.kind = p.kind; c.max_w = p.max_w;
   c.ws = ws; c.te = table_elems(p.n); c.ve = vector_elems(p.n);
   c.invZ = 0;
+  c.dbg = 0;
 }
 RP_HD double* tabp(const Ctx& c, int t) { return c.ws + (size_t)t * c.te; }
 RP_HD double* vecp(const Ctx& c, int v) { return c.ws + (size_t)T_COUNT * c.te + (size_t)v * c.ve; }
@@ -463,7 +465,7 @@ RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int ti
       int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
       if (maxpo - 1 < u1max) u1max = maxpo - 1;
       double sI = 0., s1 = 0., sA = 0.;
-      interior_rows<1>(sh, tabp(c, T_QBI), tabp(c, T_QB1N), tabp(c, T_QBAU), d * (int)ld + i, (int)ld, u1max, maxu2,
+      if (!(c.dbg & 1)) interior_rows<1>(sh, tabp(c, T_QBI), tabp(c, T_QB1N), tabp(c, T_QBAU), d * (int)ld + i, (int)ld, u1max, maxu2,
                        ddmax, sl, is.SI, sI, s1, sA);
       double accI = M.mmI[type][si1][sj1] * sI + M.mm1n[type][si1][sj1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
       // table-driven small loops
@@ -488,14 +490,14 @@ RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int ti
     // QM2(i,j) = sum_a qm[a][i] * qm1[d-1-a][i+1+a], a = TURN+1 .. d-2-TURN; the split k=i+1+a may not be the nick
     const int cntM = d - 2 * TURN - 2;   // number of terms
     double accM = 0., accQ = 0.;
-    if (cntM > 0) {
+    if (cntM > 0 && !(c.dbg & 2)) {
       const int skip = c.cp > 0 ? c.cp - 1 - i - (TURN + 1) : -1;  // a = cp-1-i  <=> k = cp
       accM = strided_dot(tabp(c, T_QM) + (size_t)(TURN + 1) * ld + i, ld,
                          tabp(c, T_QM1) + (size_t)(d - 2 - TURN) * ld + i + TURN + 2, 1 - ld, cntM, slice, sp.S, skip);
     }
     // sum_a q[a][i] * qq[d-1-a][i+1+a], a = 0 .. d-2-TURN
     const int cntQ = d - 1 - TURN;
-    if (cntQ > 0)
+    if (cntQ > 0 && !(c.dbg & 2))
       accQ = strided_dot(tabp(c, T_Q) + i, ld, tabp(c, T_QQ) + (size_t)(d - 1) * ld + i + 1, 1 - ld, cntQ, slice, sp.S, -1);
     sh.part[T + tid] = accM;
     sh.part[2 * T + tid] = accQ;
@@ -665,7 +667,7 @@ RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int t
         int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
         if (maxpo - 1 < u1max) u1max = maxpo - 1;
         double sI = 0., s1 = 0., sA = 0.;
-        interior_rows<-1>(sh, tabp(c, T_OUTI), tabp(c, T_OUT1N), tabp(c, T_OUTAU), d * (int)ld + k, (int)ld, u1max,
+        if (!(c.dbg & 1)) interior_rows<-1>(sh, tabp(c, T_OUTI), tabp(c, T_OUT1N), tabp(c, T_OUTAU), d * (int)ld + k, (int)ld, u1max,
                           maxu2, ddmax, sl, is.SI, sI, s1, sA);
         accI = M.mmI[t2][sq1][sp1] * sI + M.mm1n[t2][sq1][sp1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
         for (int s = sl; s < RP_N_SPECIAL; s += is.SI) {
@@ -693,14 +695,14 @@ RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int t
     // PR(k,l) = sum_b Mc[d+2+b][k] * qm[b][l+1], b = TURN+1 .. n-l-2   [k is the closing 5' end]
     if (l + 2 <= n && ss(c, l, l + 1)) {
       const int cnt = n - l - 2 - TURN;
-      if (cnt > 0)
+      if (cnt > 0 && !(c.dbg & 2))
         accP = strided_dot(tabp(c, T_MC) + (size_t)(d + 3 + TURN) * ld + k, ld,
                            tabp(c, T_QM) + (size_t)(TURN + 1) * ld + l + 1, ld, cnt, slice, sp.S, -1);
     }
     // ML-left(k,l) = sum_cc PRML[d+2+cc][k-2-cc] * qm[cc][k-1-cc], cc = TURN+1 .. k-3
     if (l < n && k > 2 && ss(c, k - 1, k) && ss(c, l, l + 1) && posp(c)[(size_t)d * ld + k + 1] != posp(c)[(size_t)d * ld + k]) {
       const int cnt = k - 3 - TURN;
-      if (cnt > 0 && TB(c, T_QB, d, k) != 0.)
+      if (cnt > 0 && !(c.dbg & 2) && TB(c, T_QB, d, k) != 0.)
         accL = strided_dot(tabp(c, T_PRML) + (size_t)(d + 3 + TURN) * ld + k - 3 - TURN, ld - 1,
                            tabp(c, T_QM) + (size_t)(TURN + 1) * ld + k - 2 - TURN, ld - 1, cnt, slice, sp.S, -1);
     }
@@ -800,6 +802,19 @@ RP_HD void unstru_hairpin(Ctx& c, int tid, int T) {
 // product of two table rows that already carry the pair factors:
 //   side 0:  sum_l  outX(p, l+1+u2) * qbX(k, l)          (both advance one diagonal per l)
 //   side 1:  sum_p  outX(p, o)      * qbX(p+1+u1, l)     (both step one diagonal down, one cell right)
+// Up to 8 dot products that share the streamed operand A:
+//   acc[t] += sum_{x<cnt} A[x*sa] * B[t*tb + x*sb],  t < nu
+// The B streams of neighbouring t overlap (a sliding window), so all but one of the B loads of
+// an iteration hit L1: per 8 FMAs only two new values travel from L2.
+RP_HD void multi_dot(const double* A, int sa, const double* B, int sb, int tb, int cnt, int nu, double* acc) {
+  for (int x = 0; x < cnt; x++, A += sa, B += sb) {
+    const double a = *A;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+      if (t < nu) acc[t] += a * B[t * tb];
+  }
+}
+
 RP_HD int special_index(int u1, int u2) {
   // inverse of special_uv: (0,0)->0 (1,0)->1 (0,1)->2 (1,1)->3 (1,2)->4 (2,1)->5 (2,2)->6 (2,3)->7 (3,2)->8
   if (u1 == 0) return u2 == 0 ? 0 : 2;
@@ -810,7 +825,7 @@ RP_HD int special_index(int u1, int u2) {
 RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
   const DevModel& M = *c.M;
   const int n = c.n, ld = c.ld;
-  const int items = n * (MAXLOOP + 1);
+  const int items = (c.dbg & 4) ? 0 : n * (MAXLOOP + 1);
   const int tabO[3] = {T_OUTI, T_OUT1N, T_OUTAU};
   const int tabQ[3] = {T_QBI, T_QB1N, T_QBAU};
   for (int x = tid; x < items; x += T) {
@@ -821,14 +836,28 @@ RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
     double acc = 0.;
     if (side == 0) {
       const int p = a, k = b, u1 = ug;
-      for (int u2 = 0; u1 + u2 <= MAXLOOP; u2++) {
-        const int lmin = k + TURN + 1, lmax = n - 1 - u2;
-        if (lmax < lmin) break;
+      const int lmin = k + TURN + 1;
+      for (int u2 = 0; u1 + u2 <= MAXLOOP;) {
+        if (n - 1 - u2 < lmin) break;
         const int cls = M.gcls[u1][u2];
         if (cls != CLS_SPECIAL) {
-          acc += M.gfull[u1][u2] * dot_range(tabp(c, tabO[cls]) + (size_t)(lmin + 1 + u2 - p) * ld + p, ld,
-                                             tabp(c, tabQ[cls]) + (size_t)(lmin - k) * ld + k, ld, 0, lmax - lmin + 1, 0, 1);
+          // run of up to 8 consecutive u2 of the same class
+          int nu = 1;
+          while (nu < 8 && u1 + u2 + nu <= MAXLOOP && M.gcls[u1][u2 + nu] == cls && n - 1 - (u2 + nu) >= lmin) nu++;
+          double av[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+          const double* Q = tabp(c, tabQ[cls]) + (size_t)(lmin - k) * ld + k;           // qbX(k,l), one diagonal per l
+          const double* O = tabp(c, tabO[cls]) + (size_t)(lmin + 1 + u2 - p) * ld + p;  // outX(p,l+1+u2), +ld per u2
+          const int cmain = n - 1 - (u2 + nu - 1) - lmin + 1;  // l range valid for every u2 of the run
+          multi_dot(Q, ld, O, ld, ld, cmain, nu, av);
+          for (int t = 0; t < nu; t++) {
+            // the shorter shifts reach further: l up to n-1-(u2+t)
+            const int cnt = n - 1 - (u2 + t) - lmin + 1;
+            if (cnt > cmain) av[t] += dot_range(Q, ld, O + (size_t)t * ld, ld, cmain, cnt, 0, 1);
+            acc += M.gfull[u1][u2 + t] * av[t];
+          }
+          u2 += nu;
         } else {
+          const int lmax = n - 1 - u2;
           const int sidx = special_index(u1, u2);
           const int sp1 = base(c, k - 1), si1 = base(c, p + 1);
           for (int l = lmin; l <= lmax; l++) {
@@ -840,18 +869,30 @@ RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
             acc += ou * qb * special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
                                           si1, base(c, o - 1), sp1, base(c, l + 1));
           }
+          u2++;
         }
       }
     } else {
       const int l = a, o = b, u2 = ug;
-      for (int u1 = 0; u1 + u2 <= MAXLOOP; u1++) {
-        const int pmax = l - TURN - 2 - u1;  // k = p+1+u1 <= l-TURN-1
-        if (pmax < 1) break;
+      for (int u1 = 0; u1 + u2 <= MAXLOOP;) {
+        if (l - TURN - 2 - u1 < 1) break;  // k = p+1+u1 <= l-TURN-1 needs p >= 1
         const int cls = M.gcls[u1][u2];
         if (cls != CLS_SPECIAL) {
-          acc += M.gfull[u1][u2] * dot_range(tabp(c, tabO[cls]) + (size_t)(o - 1) * ld + 1, 1 - ld,
-                                             tabp(c, tabQ[cls]) + (size_t)(l - 2 - u1) * ld + 2 + u1, 1 - ld, 0, pmax, 0, 1);
+          int nu = 1;
+          while (nu < 8 && u1 + nu + u2 <= MAXLOOP && M.gcls[u1 + nu][u2] == cls && l - TURN - 2 - (u1 + nu) >= 1) nu++;
+          double av[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+          const double* O = tabp(c, tabO[cls]) + (size_t)(o - 1) * ld + 1;               // outX(p,o): one diagonal down, one cell right per p
+          const double* Q = tabp(c, tabQ[cls]) + (size_t)(l - 2 - u1) * ld + 2 + u1;     // qbX(p+1+u1,l); per u1: 1-ld
+          const int cmain = l - TURN - 2 - (u1 + nu - 1);  // p = 1..cmain valid for every u1 of the run
+          multi_dot(O, 1 - ld, Q, 1 - ld, 1 - ld, cmain, nu, av);
+          for (int t = 0; t < nu; t++) {
+            const int cnt = l - TURN - 2 - (u1 + t);
+            if (cnt > cmain) av[t] += dot_range(O, 1 - ld, Q + (long)t * (1 - ld), 1 - ld, cmain, cnt, 0, 1);
+            acc += M.gfull[u1 + t][u2] * av[t];
+          }
+          u1 += nu;
         } else {
+          const int pmax = l - TURN - 2 - u1;
           const int sidx = special_index(u1, u2);
           const int sq1 = base(c, l + 1), sj1 = base(c, o - 1);
           for (int p = 1; p <= pmax; p++) {
@@ -863,6 +904,7 @@ RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
             acc += ou * qb * special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
                                           base(c, p + 1), sj1, base(c, k - 1), sq1);
           }
+          u1++;
         }
       }
     }

@@ -15,7 +15,7 @@ struct SerialExec {
   int T;
   int nthreads() const { return T; }
   template <class F>
-  void phase(F f) {
+  void phase(int, F f) {
     for (int t = 0; t < T; t++) f(t);
   }
 };
