@@ -30,6 +30,14 @@ struct rp_ctx {
   int device = 0;
   int sm_count = 0;
   int ctas_per_sm = 0;
+  int ls_threads = RP_LS_THREADS;
+  int ls_ctas_per_sm = 0;
+  // The batch-lockstep schedule is OFF by default: measured on B200 (1000 MicA x ompA shuffles) it
+  // runs 113 ms against 80 ms for the general kernel -- interleaving 8 problems per CTA puts their
+  // interior-loop bands (8 x 161 KB) out of L1's reach and the dense (uncompacted) interior sums
+  // then stream ~600 MB per pair through L2.  RP_LOCKSTEP=1 enables it (kept for the next round:
+  // it needs shared-memory staging / register tiling of the interior window to pay off).
+  bool lockstep = false;
   int threads = RP_MCC_THREADS;  // CTA width of the wavefront kernel (RP_MCC_THREADS env var narrows it: tuning aid)
   rp::DevModel* d_model = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -63,6 +71,13 @@ struct rp_batch {
   uint8_t* d_seq = nullptr;
   Problem* d_probs = nullptr;
   int* d_order = nullptr;
+  // lockstep groups (same-shape problems, RP_LS_G per CTA)
+  std::vector<rp::GroupDev> groups;
+  int n_general = 0;          // problems left to the general kernel (first n_general entries of order)
+  int ls_maxn = 0;
+  rp::GroupDev* d_groups = nullptr;
+  uint8_t* d_gseq = nullptr;
+  int* d_gcounter = nullptr;
   int* d_counter = nullptr;
   float* d_dense = nullptr;
   double* d_logz = nullptr;
@@ -305,6 +320,12 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
     if (t >= 64 && t <= RP_MCC_THREADS) ctx->threads = t;
   }
   ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads);
+  if (const char* e = std::getenv("RP_LS_THREADS")) {
+    int t = std::atoi(e) / 32 * 32;
+    if (t >= 32 && t <= RP_LS_THREADS) ctx->ls_threads = t;
+  }
+  if (const char* e = std::getenv("RP_LOCKSTEP")) ctx->lockstep = std::atoi(e) != 0;
+  ctx->ls_ctas_per_sm = rp::lockstep_max_ctas_per_sm(ctx->ls_threads);
   if (ctx->ctas_per_sm < 1)
     return bail(RP_ERR_CUDA, "rp_create: kernel image not loadable on this device (built for sm_100a)");
   *out = ctx;
@@ -351,7 +372,7 @@ int rp_batch_destroy(rp_batch* b) {
   if (b->ctx) {
     rp_ctx* ctx = b->ctx;
     for (void* p : {(void*)b->d_seq, (void*)b->d_probs, (void*)b->d_order, (void*)b->d_counter, (void*)b->d_dense,
-                    (void*)b->d_logz, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
+                    (void*)b->d_logz, (void*)b->d_groups, (void*)b->d_gseq, (void*)b->d_gcounter, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
       pool_release(ctx, p);
   }
   delete b;
@@ -422,15 +443,61 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     b->maxn = std::max(b->maxn, std::max(pr.n1, pr.n2));
     b->alg_flops += rp_alg_flops_mcc(pr.n1) + rp_alg_flops_mcc(pr.n2);
   }
-  b->n_mcc = (int)b->probs.size() - b->n_duplex;
-  b->slot_doubles = std::max(rp::slot_doubles(b->maxn), ws_need);
-  // queue order: most expensive first (LPT), ties by index for determinism
-  b->order.resize(b->probs.size());
-  std::iota(b->order.begin(), b->order.end(), 0);
-  std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) {
-    auto cost = [&](const Problem& q) { return q.kind == rp::KIND_DUPLEX ? 0.0 : (double)q.n * q.n * (q.n + 1500.0); };
-    return cost(b->probs[x]) > cost(b->probs[y]);
-  });
+  // Same-shape problems go to the lockstep kernel in groups of RP_LS_G: the shuffles of a z-score
+  // batch all share the lengths of the original pair.  Everything else (ragged batches, leftovers
+  // of a shape with fewer than RP_LS_G problems, --duplex) goes to the general kernel.
+  auto cost = [&](const Problem& q) { return q.kind == rp::KIND_DUPLEX ? 0.0 : (double)q.n * q.n * (q.n + 1500.0); };
+  std::vector<char> in_group(b->probs.size(), 0);
+  std::vector<uint8_t> gseq;
+  if (ctx->lockstep && ctx->ls_ctas_per_sm > 0) {
+    std::vector<int> idx(b->probs.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    auto key_less = [&](int x, int y) {
+      const Problem &p = b->probs[x], &q = b->probs[y];
+      if (p.kind != q.kind) return p.kind < q.kind;
+      if (p.n != q.n) return p.n > q.n;
+      if (p.cp != q.cp) return p.cp < q.cp;
+      return x < y;
+    };
+    std::stable_sort(idx.begin(), idx.end(), key_less);
+    size_t a = 0;
+    while (a < idx.size()) {
+      size_t e2 = a;
+      const Problem& p0 = b->probs[idx[a]];
+      while (e2 < idx.size() && b->probs[idx[e2]].kind == p0.kind && b->probs[idx[e2]].n == p0.n && b->probs[idx[e2]].cp == p0.cp) e2++;
+      if (p0.kind != rp::KIND_DUPLEX && e2 - a >= (size_t)RP_LS_G && p0.n >= 5) {
+        for (size_t g0 = a; g0 < e2; g0 += RP_LS_G) {
+          rp::GroupDev grp;
+          grp.n = p0.n;
+          grp.seq_off = (long long)gseq.size();
+          gseq.resize(gseq.size() + (size_t)(p0.n + 2) * RP_LS_G, 0);
+          for (int g = 0; g < RP_LS_G; g++) {
+            const bool live = g0 + g < e2;
+            const int pi = idx[live ? g0 + g : e2 - 1];
+            grp.prob[g] = live ? pi : -1;
+            if (live) in_group[pi] = 1;
+            const Problem& q = b->probs[pi];
+            for (int i = 1; i <= q.n; i++) gseq[grp.seq_off + (size_t)i * RP_LS_G + g] = seq[q.seq_off + i - 1];
+          }
+          b->groups.push_back(grp);
+          b->ls_maxn = std::max(b->ls_maxn, p0.n);
+        }
+      }
+      a = e2;
+    }
+    // groups are already ordered by decreasing n within a kind; put the costliest first overall
+    std::stable_sort(b->groups.begin(), b->groups.end(), [](const rp::GroupDev& x, const rp::GroupDev& y) { return x.n > y.n; });
+  }
+  // general queue: most expensive first (LPT), ties by index for determinism
+  for (size_t k = 0; k < b->probs.size(); k++)
+    if (!in_group[k]) b->order.push_back((int)k);
+  std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) { return cost(b->probs[x]) > cost(b->probs[y]); });
+  b->n_general = (int)b->order.size();
+  int gen_maxn = 0, gen_mcc = 0;
+  for (int k : b->order)
+    if (b->probs[k].kind != rp::KIND_DUPLEX) { gen_maxn = std::max(gen_maxn, b->probs[k].n); gen_mcc++; }
+  b->n_mcc = gen_mcc;
+  b->slot_doubles = std::max(gen_mcc ? rp::slot_doubles(gen_maxn) : (size_t)0, ws_need);
 
   auto bail = [&](cudaError_t e, const char* what) {
     rp_batch_destroy(b);
@@ -442,13 +509,20 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   if ((e = pool_alloc(ctx, &b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
   if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
   if ((e = pool_alloc(ctx, &b->d_counter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
+  if ((e = pool_alloc(ctx, &b->d_gcounter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc gcounter");
+  if ((e = pool_alloc(ctx, &b->d_groups, std::max<size_t>(1, b->groups.size()) * sizeof(rp::GroupDev))) != cudaSuccess) return bail(e, "cudaMalloc groups");
+  if ((e = pool_alloc(ctx, &b->d_gseq, gseq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc gseq");
   if ((e = pool_alloc(ctx, &b->d_dense, std::max<size_t>(1, b->total_floats) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense");
   if ((e = pool_alloc(ctx, &b->d_logz, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logz");
   cudaStream_t st = ctx->stream;
   if ((e = cudaMemcpyAsync(b->d_seq, seq.data(), seq.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D seq");
   if (np) {
     if ((e = cudaMemcpyAsync(b->d_probs, b->probs.data(), np * sizeof(Problem), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D probs");
-    if ((e = cudaMemcpyAsync(b->d_order, b->order.data(), np * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D order");
+    if (!b->order.empty() && (e = cudaMemcpyAsync(b->d_order, b->order.data(), b->order.size() * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D order");
+  }
+  if (!b->groups.empty()) {
+    if ((e = cudaMemcpyAsync(b->d_groups, b->groups.data(), b->groups.size() * sizeof(rp::GroupDev), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D groups");
+    if ((e = cudaMemcpyAsync(b->d_gseq, gseq.data(), gseq.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D gseq");
   }
   if ((e = cudaMemsetAsync(b->d_logz, 0, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double), st)) != cudaSuccess) return bail(e, "memset logz");
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "sync");  // host vectors go out of scope
@@ -465,13 +539,32 @@ int rp_batch_run(rp_batch* b) {
   ctx->timing.alg_flops = b->alg_flops;
   if (nprob == 0) { ctx->timing_pending = false; return RP_OK; }
   const size_t slot_bytes = b->slot_doubles * sizeof(double);
-  const int grid = grid_for(ctx, nprob, slot_bytes);
-  int rc = ensure_workspace(ctx, (size_t)grid * slot_bytes);
+  const int grid = b->n_general > 0 ? grid_for(ctx, b->n_general, std::max<size_t>(slot_bytes, 8)) : 0;
+  // lockstep: one CTA slot holds RP_LS_G problem workspaces
+  const int ngroups = (int)b->groups.size();
+  const size_t ls_slot_doubles = ngroups ? rp::slot_doubles(b->ls_maxn) * RP_LS_G : 0;
+  int ls_grid = 0;
+  if (ngroups) {
+    ls_grid = std::min(ngroups, ctx->sm_count * std::max(1, ctx->ls_ctas_per_sm));
+    if (const char* e = std::getenv("RP_GRID")) {
+      int v = std::atoi(e);
+      if (v >= 1 && v < ls_grid) ls_grid = v;
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      size_t budget = (free_b + ctx->ws_bytes) / 10 * 7;
+      while (ls_grid > 1 && (size_t)ls_grid * ls_slot_doubles * sizeof(double) > budget) ls_grid--;
+    }
+  }
+  // the two kernels run one after the other on the stream and share the workspace
+  int rc = ensure_workspace(ctx, std::max((size_t)grid * slot_bytes, (size_t)ls_grid * ls_slot_doubles * sizeof(double)));
   if (rc) return rc;
   rp::BatchDev d;
-  d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order; d.nprob = nprob;
-  d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = grid;
+  d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order; d.nprob = b->n_general;
+  d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = std::max(grid, 1);
   d.dense = b->d_dense; d.logz = b->d_logz;
+  d.groups = b->d_groups; d.ngroups = ngroups; d.gcounter = b->d_gcounter; d.gseq = b->d_gseq;
+  d.ls_slot_stride = ls_slot_doubles;
   d.prof = nullptr;
   d.dbg = std::getenv("RP_DEBUG_SKIP") ? std::atoi(std::getenv("RP_DEBUG_SKIP")) : 0;
   static long long* d_prof = nullptr;
@@ -483,14 +576,19 @@ int rp_batch_run(rp_batch* b) {
   }
   cudaStream_t st = ctx->stream;
   CU(cudaMemsetAsync(b->d_counter, 0, sizeof(int), st));
+  CU(cudaMemsetAsync(b->d_gcounter, 0, sizeof(int), st));
   CU(cudaEventRecord(ctx->ev[0], st));
   int launches = 0;
+  if (ngroups > 0) {
+    CU(rp::launch_lockstep(d, ls_grid, ctx->ls_threads, st));
+    launches++;
+  }
   if (b->n_mcc > 0) {
     CU(rp::launch_mcc(d, grid, ctx->threads, st));
     launches++;
   }
   if (b->n_duplex > 0) {
-    CU(rp::launch_duplex(d, std::min(grid, nprob), st));
+    CU(rp::launch_duplex(d, std::max(1, std::min(grid, b->n_general)), st));
     launches++;
   }
   CU(cudaEventRecord(ctx->ev[1], st));

@@ -9,13 +9,30 @@
 #include "ractip_prob.h"
 
 #ifndef RP_MCC_THREADS
-#define RP_MCC_THREADS 1024
+#define RP_MCC_THREADS 512
 #endif
 #ifndef RP_MCC_MIN_CTAS
-#define RP_MCC_MIN_CTAS 1
+#define RP_MCC_MIN_CTAS 2
+#endif
+// batch-lockstep kernel: RP_LS_G same-shape problems per CTA
+#ifndef RP_LS_G
+#define RP_LS_G 8
+#endif
+#ifndef RP_LS_THREADS
+#define RP_LS_THREADS 512
+#endif
+#ifndef RP_LS_MIN_CTAS
+#define RP_LS_MIN_CTAS 2
 #endif
 
 namespace rp {
+
+// one lockstep group: RP_LS_G problems of identical (kind, n, cp, max_w, n1, n2)
+struct GroupDev {
+  int n;
+  long long seq_off;        // offset of the group's interleaved sequences S[i*G+g] in BatchDev::gseq
+  int prob[RP_LS_G];        // problem indices; -1 = padding lane (repeats the last real problem, writes nothing)
+};
 
 struct BatchDev {
   const DevModel* model;
@@ -29,6 +46,12 @@ struct BatchDev {
   int nslots;
   float* dense;            // dense fp32 outputs (reference layouts)
   double* logz;            // 3 per pair, may be null
+  // lockstep part of the batch
+  const GroupDev* groups;
+  int ngroups;
+  int* gcounter;           // group-queue head
+  const uint8_t* gseq;     // interleaved sequences of all groups
+  size_t ls_slot_stride;   // doubles per lockstep CTA slot (RP_LS_G problem workspaces)
   long long* prof;         // 64 counters (cycles, calls per phase id) or null
   int dbg;                 // RP_DEBUG_SKIP bits (tuning aid; results are wrong when set)
 };
@@ -53,6 +76,8 @@ struct SparseDev {
 
 int mcc_max_ctas_per_sm(int threads);
 cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, cudaStream_t st);
+int lockstep_max_ctas_per_sm(int threads);
+cudaError_t launch_lockstep(const BatchDev& b, int grid, int threads, cudaStream_t st);
 cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st);
 cudaError_t launch_sparse(const SparseDev& s, int n_pairs, cudaStream_t st);
 cudaError_t launch_peak_fp64(double* out, int grid, int iters, cudaStream_t st);

@@ -1,5 +1,5 @@
 // mcc_core.h -- the McCaskill wavefront, written once as per-thread phase
-// functions.  The CUDA kernel (kernels.cu) runs them with tid = threadIdx.x and
+// functions.  The CUDA kernels (kernels.cu) run them with tid = threadIdx.x and
 // __syncthreads() between phases; tests/emul compiles the SAME functions for
 // the host and runs the threads of a CTA one after another, so kernel logic is
 // debugged on a CPU-only box.  (The emulator is test infrastructure; the
@@ -12,11 +12,19 @@
 // with dangles=2, TURN=3, MAXLOOP=30, pf_scale from DevModel.
 //
 // Layout: every O(n^2) table is stored DIAGONAL-MAJOR: cell (i,j), 1<=i<=j<=n,
-// lives at [d*ld + i] with d=j-i, ld=n+1.  Cells of one anti-diagonal wavefront
-// are contiguous, so "thread t handles cell i0+t" makes every operand stream of
-// every recurrence a unit-stride (coalesced) access:
+// lives at element d*ld + i with d=j-i, ld=n+1.  Cells of one anti-diagonal
+// wavefront are contiguous, so every operand stream of every recurrence is a
+// constant-stride walk:
 //   sum_k A(i,k-1)*B(k,j)  ->  sum_a A[a][i] * B[d-1-a][i+1+a]
-//   interior window        ->  sum_taps g * B[d-dd][i+po]
+//   interior rows          ->  sum_u2 g[u1][u2] * B[d-2-u1-u2][i+1+u1]
+//
+// Two ways of laying problems out, behind the same code (the context type C):
+//   Ctx      one problem per CTA, elements contiguous; work of a cell is SLICED
+//            over threads (general kernel: any mix of lengths).
+//   LCtx<G>  G problems of identical shape interleaved element by element
+//            (element e of problem g at e*G+g): lane = problem, a thread does
+//            WHOLE cells of its own problem (batch-lockstep kernel: the shuffle
+//            batch, where every problem has the same lengths).
 #ifndef RP_MCC_CORE_H
 #define RP_MCC_CORE_H
 
@@ -27,16 +35,14 @@
 
 #ifdef __CUDACC__
 #define RP_HD __host__ __device__ __forceinline__
-#define RP_D __device__ __forceinline__
 #else
 #define RP_HD inline
-#define RP_D inline
 #endif
 
 namespace rp {
 
 // ---------------------------------------------------------------------------
-// problem descriptor and per-slot workspace
+// problem descriptor and workspace
 // ---------------------------------------------------------------------------
 enum { KIND_LINEAR = 0, KIND_COFOLD = 1, KIND_DUPLEX = 2 };
 
@@ -60,7 +66,7 @@ enum {
   T_Q = 0, T_QQ, T_QM, T_QM1, T_QM2, T_QB, T_QBI, T_QB1N, T_QBAU,
   T_OUT, T_OUTI, T_OUT1N, T_OUTAU, T_MC, T_PR, T_PRML, T_PMLB, T_PL,
   T_DG, T_RR, T_LL, T_XX,
-  T_LIST,   // not doubles: per-diagonal lists of pairable cells (uint16), see listp()/posp()
+  T_LIST,   // not doubles: per-diagonal lists of pairable cells (uint16), general kernel only
   T_COUNT
 };
 enum {
@@ -69,6 +75,11 @@ enum {
   V_COUNT
 };
 
+RP_HD size_t table_elems(int n) { return (size_t)n * (size_t)(n + 1) + 8; }
+RP_HD size_t vector_elems(int n) { return (size_t)n + 8; }
+RP_HD size_t slot_doubles(int n) { return T_COUNT * table_elems(n) + V_COUNT * vector_elems(n); }
+
+// one problem, contiguous elements
 struct Ctx {
   const DevModel* M;
   const uint8_t* S;   // S[1..n]; low 3 bits base code 0..4, bit 3 = "letter is not A/C/G/U"
@@ -77,11 +88,31 @@ struct Ctx {
   size_t te, ve;      // elements per table / per vector
   double invZ;        // set after the inside pass
   int dbg;            // tuning aid (RP_DEBUG_SKIP): 1 skip interior rows, 2 skip split sums, 4 skip gap sums
+  RP_HD double& tb(int t, int d, int i) const { return ws[(size_t)t * te + (size_t)d * ld + i]; }
+  RP_HD double* ptr(int t, int d, int i) const { return ws + ((size_t)t * te + (size_t)d * ld + i); }
+  RP_HD double& v(int vv, int k) const { return ws[(size_t)T_COUNT * te + (size_t)vv * ve + k]; }
+  RP_HD int dstep() const { return ld; }   // one diagonal up, same position
+  RP_HD int pstep() const { return 1; }    // same diagonal, next position
+  RP_HD int sraw(int i) const { return S[i]; }
 };
 
-RP_HD size_t table_elems(int n) { return (size_t)n * (size_t)(n + 1) + 8; }
-RP_HD size_t vector_elems(int n) { return (size_t)n + 8; }
-RP_HD size_t slot_doubles(int n) { return T_COUNT * table_elems(n) + V_COUNT * vector_elems(n); }
+// G problems of identical (n, cp), interleaved: element e of lane g at e*G+g
+template <int G>
+struct LCtx {
+  const DevModel* M;
+  const uint8_t* S;   // S[i*G] of this lane (pointer already offset by the lane)
+  int n, cp, ld, kind, max_w;
+  double* ws;         // group workspace, already offset by the lane
+  size_t te, ve;
+  double invZ;
+  int dbg;
+  RP_HD double& tb(int t, int d, int i) const { return ws[((size_t)t * te + (size_t)d * ld + i) * G]; }
+  RP_HD double* ptr(int t, int d, int i) const { return ws + ((size_t)t * te + (size_t)d * ld + i) * G; }
+  RP_HD double& v(int vv, int k) const { return ws[((size_t)T_COUNT * te + (size_t)vv * ve + k) * G]; }
+  RP_HD int dstep() const { return ld * G; }
+  RP_HD int pstep() const { return G; }
+  RP_HD int sraw(int i) const { return S[(size_t)i * G]; }
+};
 
 RP_HD void bind_ctx(Ctx& c, const DevModel* M, const uint8_t* S, const Problem& p, double* ws) {
   c.M = M; c.S = S; c.n = p.n; c.cp = p.cp; c.ld = p.n + 1; c.kind = p.kind; c.max_w = p.max_w;
@@ -89,27 +120,33 @@ RP_HD void bind_ctx(Ctx& c, const DevModel* M, const uint8_t* S, const Problem& 
   c.invZ = 0;
   c.dbg = 0;
 }
-RP_HD double* tabp(const Ctx& c, int t) { return c.ws + (size_t)t * c.te; }
-RP_HD double* vecp(const Ctx& c, int v) { return c.ws + (size_t)T_COUNT * c.te + (size_t)v * c.ve; }
+template <int G>
+RP_HD void bind_lctx(LCtx<G>& c, const DevModel* M, const uint8_t* S_group, const Problem& p, double* ws_group, int g) {
+  c.M = M; c.S = S_group + g; c.n = p.n; c.cp = p.cp; c.ld = p.n + 1; c.kind = p.kind; c.max_w = p.max_w;
+  c.ws = ws_group + g; c.te = table_elems(p.n); c.ve = vector_elems(p.n);
+  c.invZ = 0;
+  c.dbg = 0;
+}
 
-#define TB(c, t, d, i) (tabp(c, t)[(size_t)(d) * (c).ld + (i)])
+#define TB(c, t, d, i) ((c).tb(t, d, i))
+#define VEC(c, vec_id, k) ((c).v(vec_id, k))
 
-// Per-diagonal compaction of the cells that can pair (static per sequence):
+// Per-diagonal compaction of the cells that can pair (static per sequence; general kernel):
 //   LIST[d*ld + r] = i of the r-th pairable cell (i,i+d);  POS[d*ld + i] = #pairable cells (i',i'+d), i' < i.
 // Interior-loop work is dealt out over these lists, so no thread idles on a cell that cannot pair.
-RP_HD uint16_t* listp(const Ctx& c) { return reinterpret_cast<uint16_t*>(tabp(c, T_LIST)); }
-RP_HD uint16_t* posp(const Ctx& c) { return reinterpret_cast<uint16_t*>(tabp(c, T_LIST)) + c.te * 2; }
+RP_HD uint16_t* listp(const Ctx& c) { return reinterpret_cast<uint16_t*>(c.ptr(T_LIST, 0, 0)); }
+RP_HD uint16_t* posp(const Ctx& c) { return reinterpret_cast<uint16_t*>(c.ptr(T_LIST, 0, 0)) + c.te * 2; }
 
 // CTA-shared scratch (CUDA shared memory; a heap block in the host emulation)
-constexpr int RP_SMEM_SEQ = 4096;  // sequences up to this length are staged in shared memory
+constexpr int RP_SMEM_SEQ = 4096;  // sequence bytes staged in shared memory (n+2 general, (n+2)*G lockstep)
 struct Shared {
   int T;
-  double* part;     // [3][T] partial sums of the current phase
+  double* part;     // [3][T] partial sums of the current phase (general kernel)
   double* grow;     // [MAXLOOP+1][GROW_LD] run weights of the factorised interior loops (DevModel::grow)
   double* ghead_b;  // [GROW_LD]
   double* ghead_1;  // [GROW_LD]
   double* red;      // [128] small reductions (nick sums)
-  uint8_t* S;       // [RP_SMEM_SEQ + 8] staged sequence
+  uint8_t* S;       // [RP_SMEM_SEQ + 8] staged sequence(s)
 };
 RP_HD size_t shared_bytes(int T) {
   return sizeof(double) * (3 * (size_t)T + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
@@ -128,7 +165,8 @@ RP_HD void carve_shared(Shared& sh, void* base, int T) {
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
-RP_HD int base(const Ctx& c, int i) { return c.S[i] & 7; }
+template <class C>
+RP_HD int base(const C& c, int i) { return c.sraw(i) & 7; }
 
 RP_HD int pair_type(int a, int b) {
   // CG=1 GC=2 GU=3 UG=4 AU=5 UA=6 ; a,b in 0..4 (N,A,C,G,U).  One nibble per (a-1,b-1).
@@ -140,7 +178,8 @@ RP_HD int pair_type(int a, int b) {
 RP_HD int rtype(int t) { return t == 0 ? 0 : (t == 7 ? 7 : ((t - 1) ^ 1) + 1); }
 
 // ViennaRNA SAME_STRAND(a,b) for a<b
-RP_HD bool ss(const Ctx& c, int a, int b) { return c.cp <= 0 || a >= c.cp || b < c.cp; }
+template <class C>
+RP_HD bool ss(const C& c, int a, int b) { return c.cp <= 0 || a >= c.cp || b < c.cp; }
 
 RP_HD double ext_stem(const DevModel& M, int type, int s5, int s3) {
   double e = 1.0;
@@ -159,32 +198,6 @@ RP_HD double ml_stem(const DevModel& M, int type, int s5, int s3) {
   return e * M.expMLintern;
 }
 
-// Interior-loop weight (unscaled) for the table-driven small cases and, for
-// completeness, every other case.  type2 is rtype of the inner pair.
-RP_HD double int_loop(const DevModel& M, int u1, int u2, int type, int type2, int si1, int sj1, int sp1, int sq1) {
-  const int ul = u1 > u2 ? u1 : u2, us = u1 > u2 ? u2 : u1;
-  if (ul == 0) return M.expstack[type][type2];
-  if (us == 0) {
-    double z = M.expbulge[ul];
-    if (ul == 1) z *= M.expstack[type][type2];
-    else {
-      if (type > 2) z *= M.expTermAU;
-      if (type2 > 2) z *= M.expTermAU;
-    }
-    return z;
-  }
-  if (us == 1) {
-    if (ul == 1) return M.int11[type][type2][si1][sj1];
-    if (ul == 2) return u1 == 1 ? M.int21[type][type2][si1][sq1][sj1] : M.int21[type2][type][sq1][si1][sp1];
-    return M.expinternal[ul + us] * M.mm1n[type][si1][sj1] * M.mm1n[type2][sq1][sp1] * M.expninio[ul - us];
-  }
-  if (us == 2) {
-    if (ul == 2) return M.int22[type][type2][si1][sp1][sq1][sj1];
-    if (ul == 3) return M.expinternal[5] * M.mm23[type][si1][sj1] * M.mm23[type2][sq1][sp1] * M.expninio[1];
-  }
-  return M.expinternal[ul + us] * M.mmI[type][si1][sj1] * M.mmI[type2][sq1][sp1] * M.expninio[ul - us];
-}
-
 // the nine (u1,u2) combinations that do not factorise
 #define RP_N_SPECIAL 9
 RP_HD void special_uv(int s, int& u1, int& u2) {
@@ -192,136 +205,43 @@ RP_HD void special_uv(int s, int& u1, int& u2) {
   const int U2[RP_N_SPECIAL] = {0, 0, 1, 1, 2, 1, 2, 3, 2};
   u1 = U1[s]; u2 = U2[s];
 }
+RP_HD int special_index(int u1, int u2) {
+  // inverse of special_uv: (0,0)->0 (1,0)->1 (0,1)->2 (1,1)->3 (1,2)->4 (2,1)->5 (2,2)->6 (2,3)->7 (3,2)->8
+  if (u1 == 0) return u2 == 0 ? 0 : 2;
+  if (u1 == 1) return u2 == 0 ? 1 : (u2 == 1 ? 3 : 4);
+  if (u1 == 2) return u2 == 1 ? 5 : (u2 == 2 ? 6 : 7);
+  return 8;
+}
+// weight (incl. scale) of special shape s: closing pair `type` with neighbours
+// (si1,sj1), inner pair of reversed type t2r with neighbours (sp1,sq1)
+RP_HD double special_loop(const DevModel& M, int s, int type, int t2r, int si1, int sj1, int sp1, int sq1) {
+  switch (s) {
+    case 0: return M.expstack[type][t2r] * M.scale_small[2];
+    case 1:
+    case 2: return M.expbulge[1] * M.expstack[type][t2r] * M.scale_small[3];
+    case 3: return M.int11[type][t2r][si1][sj1] * M.scale_small[4];
+    case 4: return M.int21[type][t2r][si1][sq1][sj1] * M.scale_small[5];   // u1=1,u2=2
+    case 5: return M.int21[t2r][type][sq1][si1][sp1] * M.scale_small[5];   // u1=2,u2=1
+    case 6: return M.int22[type][t2r][si1][sp1][sq1][sj1] * M.scale_small[6];
+    default: return M.expinternal[5] * M.expninio[1] * M.mm23[type][si1][sj1] * M.mm23[t2r][sq1][sp1] * M.scale_small[7];
+  }
+}
 
 // hairpin weight of pair (i,j), including scale[u+2]
-RP_HD double hairpin(const Ctx& c, int i, int j, int type) {
+template <class C>
+RP_HD double hairpin(const C& c, int i, int j, int type) {
   const int u = j - i - 1;
   if (c.M->special_hp) {
-    if (u == 4 && vecp(c, V_SP4)[i] >= 0.) return vecp(c, V_SP4)[i];  // type==7 never occurs for ACGU pairs
-    if (u == 6 && vecp(c, V_SP6)[i] >= 0.) return vecp(c, V_SP6)[i];
+    if (u == 4 && VEC(c, V_SP4, i) >= 0.) return VEC(c, V_SP4, i);  // type==7 never occurs for ACGU pairs
+    if (u == 6 && VEC(c, V_SP6, i) >= 0.) return VEC(c, V_SP6, i);
     if (u == 3) {
-      if (vecp(c, V_SP3)[i] >= 0.) return vecp(c, V_SP3)[i];
-      return type > 2 ? vecp(c, V_HPW)[3] * c.M->expTermAU : vecp(c, V_HPW)[3];
+      if (VEC(c, V_SP3, i) >= 0.) return VEC(c, V_SP3, i);
+      return type > 2 ? VEC(c, V_HPW, 3) * c.M->expTermAU : VEC(c, V_HPW, 3);
     }
   }
-  return vecp(c, V_HPW)[u] * c.M->mmH[type][base(c, i + 1)][base(c, j - 1)];
+  return VEC(c, V_HPW, u) * c.M->mmH[type][base(c, i + 1)][base(c, j - 1)];
 }
 
-// partition of a chunk of `C` cells over T threads: Cp cells x S slices
-struct Split {
-  int Cp, S;
-};
-RP_HD Split make_split(int C, int T) {
-  Split s;
-  int Cp = (C + 31) & ~31;
-  if (Cp > T) Cp = T;
-  s.Cp = Cp;
-  s.S = T / Cp;
-  if (s.S < 1) s.S = 1;
-  return s;
-}
-
-// ---------------------------------------------------------------------------
-// prologue: shared tap tables, per-problem vectors, pair lists, d<=TURN diagonals
-// ---------------------------------------------------------------------------
-// copy S[0..n+1] into shared memory (the caller then points c.S at sh.S)
-RP_HD void stage_sequence(const Ctx& c, const Shared& sh, int tid) {
-  for (int x = tid; x <= c.n + 1; x += sh.T) sh.S[x] = c.S[x];
-}
-
-RP_HD void prologue(Ctx& c, const Shared& sh, int tid) {
-  const DevModel& M = *c.M;
-  const int n = c.n, T = sh.T;
-  // interior-loop run weights into shared memory
-  for (int x = tid; x < (MAXLOOP + 1) * GROW_LD; x += T) sh.grow[x] = M.grow[x / GROW_LD][x % GROW_LD];
-  for (int x = tid; x < GROW_LD; x += T) {
-    sh.ghead_b[x] = M.ghead_b[x];
-    sh.ghead_1[x] = M.ghead_1[x];
-  }
-  // scale[k] = pf_scale^-k, mlb[k] = (expMLbase/pf_scale)^k: built by repeated
-  // multiplication by one thread so that every consumer sees the same values
-  if (tid == 0) {
-    double s = 1.0, b = 1.0;
-    double* sc = vecp(c, V_SCALE);
-    double* ml = vecp(c, V_MLB);
-    for (int k = 0; k <= n + 2; k++) {
-      sc[k] = s;
-      ml[k] = b;
-      s *= M.scale1;
-      b *= M.mlb1;
-    }
-  }
-  // pair lists: one thread per diagonal
-  uint16_t* LIST = listp(c);
-  uint16_t* POS = posp(c);
-  for (int d = tid; d < n; d += T) {
-    uint16_t* L = LIST + (size_t)d * c.ld;
-    uint16_t* P = POS + (size_t)d * c.ld;
-    int cnt = 0;
-    for (int i = 1; i <= n - d; i++) {
-      P[i] = (uint16_t)cnt;
-      if (d > TURN && pair_type(base(c, i), base(c, i + d))) L[cnt++] = (uint16_t)i;
-    }
-    P[n - d + 1 <= n ? n - d + 1 : n] = (uint16_t)cnt;  // d = 0: i = n+1 does not exist and is never asked for
-    if (d == 0) P[n] = 0;
-  }
-}
-RP_HD void prologue2(Ctx& c, const Shared& sh, int tid) {
-  const DevModel& M = *c.M;
-  const int n = c.n, T = sh.T;
-  for (int u = tid; u <= n; u += T) {
-    double q;
-    if (u <= 30) q = M.exphairpin[u];
-    else q = M.exphairpin[30] * exp(-(M.lxc * log(u / 30.)) * 10. / M.kT);
-    vecp(c, V_HPW)[u] = q * vecp(c, V_SCALE)[u + 2];
-  }
-  for (int i = tid; i <= n + 1; i += T) {
-    double s3 = -1., s4 = -1., s6 = -1.;
-    if (i >= 1) {
-      // window codes: base-8 digits, 7 for letters that cannot match a list entry
-      int code = 0;
-      bool in = true;
-      for (int k = 0; k < 8; k++) {
-        int p = i + k;
-        int dgt = 0;
-        if (p <= n) dgt = (c.S[p] & 8) ? 7 : (c.S[p] & 7);
-        else in = false;
-        code = code * 8 + dgt;
-        // a hairpin window never spans the nick (hairpins need ss(i,j))
-        if (k == 4 && in) {
-          for (int e = 0; e < M.n_tri; e++)
-            if (M.tri_code[e] == code) { s3 = M.exptri[e] * vecp(c, V_SCALE)[5]; break; }
-        } else if (k == 5 && in) {
-          for (int e = 0; e < M.n_tetra; e++)
-            if (M.tetra_code[e] == code) { s4 = M.exptetra[e] * vecp(c, V_SCALE)[6]; break; }
-        } else if (k == 7 && in) {
-          for (int e = 0; e < M.n_hex; e++)
-            if (M.hex_code[e] == code) { s6 = M.exphex[e] * vecp(c, V_SCALE)[8]; break; }
-        }
-      }
-    }
-    vecp(c, V_SP3)[i] = s3; vecp(c, V_SP4)[i] = s4; vecp(c, V_SP6)[i] = s6;
-    vecp(c, V_U0)[i] = 0.; vecp(c, V_U1)[i] = 0.;
-    vecp(c, V_QR)[i] = 0.; vecp(c, V_QROUT)[i] = 0.; vecp(c, V_QL)[i] = 0.; vecp(c, V_QLOUT)[i] = 0.;
-  }
-  // diagonals 0..TURN: q = scale[d+1], everything else 0
-  const int dmax = TURN < n - 1 ? TURN : n - 1;
-  const int cells = (dmax + 1) * c.ld;
-  for (int x = tid; x < cells; x += T) {
-    int d = x / c.ld, i = x % c.ld;
-    bool valid = i >= 1 && i + d <= n;
-    TB(c, T_Q, d, i) = valid ? vecp(c, V_SCALE)[d + 1] : 0.;
-    TB(c, T_QQ, d, i) = 0.; TB(c, T_QM, d, i) = 0.; TB(c, T_QM1, d, i) = 0.; TB(c, T_QM2, d, i) = 0.;
-    TB(c, T_QB, d, i) = 0.; TB(c, T_QBI, d, i) = 0.; TB(c, T_QB1N, d, i) = 0.; TB(c, T_QBAU, d, i) = 0.;
-    TB(c, T_OUT, d, i) = 0.; TB(c, T_OUTI, d, i) = 0.; TB(c, T_OUT1N, d, i) = 0.; TB(c, T_OUTAU, d, i) = 0.;
-    TB(c, T_MC, d, i) = 0.; TB(c, T_PR, d, i) = 0.; TB(c, T_PRML, d, i) = 0.; TB(c, T_PMLB, d, i) = 0.;
-    TB(c, T_PL, d, i) = 0.; TB(c, T_DG, d, i) = 0.;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// shared pieces of the inside and outside phases
-// ---------------------------------------------------------------------------
 // weighted sum along one row of the factorised interior loops:
 //   sum_{u2=lo..hi} g[u2] * p[u2*step]
 RP_HD double row_sum(const double* g, const double* p, int step, int lo, int hi) {
@@ -349,12 +269,13 @@ RP_HD double row_sum(const double* g, const double* p, int step, int lo, int hi)
 // row pairs (q, 30-q), q = sl, sl+SI, ... (each pair holds 32 terms, so slices
 // are balanced).  SIGN=+1: inside, inner pair (i+1+u1, j-1-u2) lies u1+u2+2
 // diagonals below the cell; SIGN=-1: outside, enclosing pair (k-1-u1, l+1+u2)
-// lies above.  cell0 = d*ld + i.  Bounds: u1 <= u1max, u2 <= u2cap,
-// u1+u2+2 <= ddmax; every element touched is a valid cell, so no guards.
+// lies above.  TI/T1/TA point at the cell's own entry of the three class
+// tables; ds/ps are the diagonal and position strides.  Bounds: u1 <= u1max,
+// u2 <= u2cap, u1+u2+2 <= ddmax; every element touched is a valid cell.
 template <int SIGN>
-RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, const double* TA, int cell0, int ld,
+RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, const double* TA, int ds, int ps,
                          int u1max, int u2cap, int ddmax, int sl, int SI, double& sI, double& s1, double& sA) {
-  const int step = -SIGN * ld;
+  const int step = -SIGN * ds;
   for (int q = sl; q <= MAXLOOP / 2; q += SI) {
     for (int h = 0; h < 2; h++) {
       const int u1 = h == 0 ? q : MAXLOOP - q;
@@ -364,7 +285,7 @@ RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, c
       if (u2cap < u2hi) u2hi = u2cap;
       if (ddmax - 2 - u1 < u2hi) u2hi = ddmax - 2 - u1;
       if (u2hi < 0) continue;
-      const int o0 = cell0 - SIGN * ((u1 + 2) * ld - (1 + u1));  // element (u1, u2=0)
+      const long o0 = -(long)SIGN * ((long)(u1 + 2) * ds - (long)(1 + u1) * ps);  // element (u1, u2=0)
       const double* g = sh.grow + u1 * GROW_LD;
       if (u1 == 0) {
         if (u2hi >= 2) sA += row_sum(g, TA + o0, step, 2, u2hi);
@@ -376,21 +297,6 @@ RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, c
         if (u2hi >= 2) sI += row_sum(g, TI + o0, step, 2, u2hi);
       }
     }
-  }
-}
-
-// the nine loop shapes that do not factorise, closing pair `type` with
-// neighbours (si1,sj1), inner pair of reversed type t2r with neighbours (sp1,sq1)
-RP_HD double special_loop(const DevModel& M, int s, int type, int t2r, int si1, int sj1, int sp1, int sq1) {
-  switch (s) {
-    case 0: return M.expstack[type][t2r] * M.scale_small[2];
-    case 1:
-    case 2: return M.expbulge[1] * M.expstack[type][t2r] * M.scale_small[3];
-    case 3: return M.int11[type][t2r][si1][sj1] * M.scale_small[4];
-    case 4: return M.int21[type][t2r][si1][sq1][sj1] * M.scale_small[5];   // u1=1,u2=2
-    case 5: return M.int21[t2r][type][sq1][si1][sp1] * M.scale_small[5];   // u1=2,u2=1
-    case 6: return M.int22[type][t2r][si1][sp1][sq1][sj1] * M.scale_small[6];
-    default: return M.expinternal[5] * M.expninio[1] * M.mm23[type][si1][sj1] * M.mm23[t2r][sq1][sp1] * M.scale_small[7];
   }
 }
 
@@ -423,7 +329,30 @@ RP_HD double strided_dot(const double* A, int sa, const double* B, int sb, int c
   if (skip < 0 || skip >= cnt) return dot_range(A, sa, B, sb, 0, cnt, s, S);
   return dot_range(A, sa, B, sb, 0, skip, s, S) + dot_range(A, sa, B, sb, skip + 1, cnt, s, S);
 }
+// Up to 8 dot products that share the streamed operand A:
+//   acc[t] += sum_{x<cnt} A[x*sa] * B[t*tb + x*sb],  t < nu
+RP_HD void multi_dot(const double* A, int sa, const double* B, int sb, int tb, int cnt, int nu, double* acc) {
+  for (int x = 0; x < cnt; x++, A += sa, B += sb) {
+    const double a = *A;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+      if (t < nu) acc[t] += a * B[t * tb];
+  }
+}
 
+// partition of a chunk of `C` cells over T threads: Cp cells x S slices (general kernel)
+struct Split {
+  int Cp, S;
+};
+RP_HD Split make_split(int C, int T) {
+  Split s;
+  int Cp = (C + 31) & ~31;
+  if (Cp > T) Cp = T;
+  s.Cp = Cp;
+  s.S = T / Cp;
+  if (s.S < 1) s.S = 1;
+  return s;
+}
 // work split of the interior-loop items of a chunk: cnt pairable cells x SI slices
 struct ISplit {
   int lo, cnt, cntp, SI;
@@ -443,94 +372,174 @@ RP_HD ISplit make_isplit(const Ctx& c, int d, int i0, int C, int T) {
 }
 
 // ---------------------------------------------------------------------------
-// inside pass, diagonal d >= TURN+1; cells i0 .. i0+C-1 handled as a chunk
-// sh.part: [3][T] doubles (interior, QM2, q-split)
+// prologue.  (ct, nct) = index and number of the threads that share one problem:
+// (tid, T) in the general kernel, (tid/G, T/G) in the lockstep kernel.
 // ---------------------------------------------------------------------------
-RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
-  const DevModel& M = *c.M;
-  const int T = sh.T;
-  const long ld = c.ld;
-  // --- (1) interior loops: items = (pairable cell, slice) ---------------------
-  const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
-  if (ddmax >= 2) {
-    const ISplit is = make_isplit(c, d, i0, C, T);
-    const int r = tid % is.cntp, sl = tid / is.cntp;
-    if (sl < is.SI && r < is.cnt) {
-      const int i = listp(c)[(size_t)d * ld + is.lo + r], j = i + d;
-      const int type = pair_type(base(c, i), base(c, j));
-      // strand guards: inner 5' end must stay on i's strand, inner 3' end on j's
-      const int maxpo = (c.cp > 0 && i < c.cp) ? c.cp - 1 - i : 1000;
-      const int maxu2 = (c.cp > 0 && j >= c.cp) ? j - 1 - c.cp : 1000;
-      const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
-      int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
-      if (maxpo - 1 < u1max) u1max = maxpo - 1;
-      double sI = 0., s1 = 0., sA = 0.;
-      if (!(c.dbg & 1)) interior_rows<1>(sh, tabp(c, T_QBI), tabp(c, T_QB1N), tabp(c, T_QBAU), d * (int)ld + i, (int)ld, u1max, maxu2,
-                       ddmax, sl, is.SI, sI, s1, sA);
-      double accI = M.mmI[type][si1][sj1] * sI + M.mm1n[type][si1][sj1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
-      // table-driven small loops
-      for (int s = sl; s < RP_N_SPECIAL; s += is.SI) {
-        int u1, u2;
-        special_uv(s, u1, u2);
-        const int dd = u1 + u2 + 2;
-        if (dd > ddmax || u1 + 1 > maxpo || u2 > maxu2) continue;
-        const int k = i + 1 + u1, l = j - 1 - u2;
-        const int t2 = pair_type(base(c, k), base(c, l));
-        if (!t2) continue;
-        accI += TB(c, T_QB, d - dd, k) * special_loop(M, s, type, rtype(t2), si1, sj1, base(c, k - 1), base(c, l + 1));
-      }
-      sh.part[tid] = accI;
-    }
-  }
-  // --- (2) split sums: items = (cell, slice) ---------------------------------
-  const Split sp = make_split(C, T);
-  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
-  if (slice < sp.S && cell < C) {
-    const int i = i0 + cell;
-    // QM2(i,j) = sum_a qm[a][i] * qm1[d-1-a][i+1+a], a = TURN+1 .. d-2-TURN; the split k=i+1+a may not be the nick
-    const int cntM = d - 2 * TURN - 2;   // number of terms
-    double accM = 0., accQ = 0.;
-    if (cntM > 0 && !(c.dbg & 2)) {
-      const int skip = c.cp > 0 ? c.cp - 1 - i - (TURN + 1) : -1;  // a = cp-1-i  <=> k = cp
-      accM = strided_dot(tabp(c, T_QM) + (size_t)(TURN + 1) * ld + i, ld,
-                         tabp(c, T_QM1) + (size_t)(d - 2 - TURN) * ld + i + TURN + 2, 1 - ld, cntM, slice, sp.S, skip);
-    }
-    // sum_a q[a][i] * qq[d-1-a][i+1+a], a = 0 .. d-2-TURN
-    const int cntQ = d - 1 - TURN;
-    if (cntQ > 0 && !(c.dbg & 2))
-      accQ = strided_dot(tabp(c, T_Q) + i, ld, tabp(c, T_QQ) + (size_t)(d - 1) * ld + i + 1, 1 - ld, cntQ, slice, sp.S, -1);
-    sh.part[T + tid] = accM;
-    sh.part[2 * T + tid] = accQ;
+RP_HD void load_shared_model(const DevModel& M, const Shared& sh, int tid) {
+  for (int x = tid; x < (MAXLOOP + 1) * GROW_LD; x += sh.T) sh.grow[x] = M.grow[x / GROW_LD][x % GROW_LD];
+  for (int x = tid; x < GROW_LD; x += sh.T) {
+    sh.ghead_b[x] = M.ghead_b[x];
+    sh.ghead_1[x] = M.ghead_1[x];
   }
 }
 
-RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+template <class C>
+RP_HD void prologue_vectors(C& c, int ct, int nct) {
   const DevModel& M = *c.M;
-  const int T = sh.T;
-  const Split sp = make_split(C, T);
-  if (tid >= sp.Cp || tid >= C) return;
-  const int i = i0 + tid, j = i + d, n = c.n;
-  double sI = 0., sM = 0., sQ = 0.;
-  for (int s = 0; s < sp.S; s++) {
-    sM += sh.part[T + s * sp.Cp + tid];
-    sQ += sh.part[2 * T + s * sp.Cp + tid];
+  const int n = c.n;
+  // scale[k] = pf_scale^-k, mlb[k] = (expMLbase/pf_scale)^k: built by repeated
+  // multiplication by one thread so that every consumer sees the same values
+  if (ct == 0) {
+    double s = 1.0, b = 1.0;
+    for (int k = 0; k <= n + 2; k++) {
+      VEC(c, V_SCALE, k) = s;
+      VEC(c, V_MLB, k) = b;
+      s *= M.scale1;
+      b *= M.mlb1;
+    }
   }
-  const int type = pair_type(base(c, i), base(c, j));
-  const double* scale = vecp(c, V_SCALE);
+  (void)nct;
+}
+
+// pair lists of the general kernel: one thread per diagonal
+RP_HD void prologue_lists(Ctx& c, int tid, int T) {
+  const int n = c.n;
+  uint16_t* LIST = listp(c);
+  uint16_t* POS = posp(c);
+  for (int d = tid; d < n; d += T) {
+    uint16_t* L = LIST + (size_t)d * c.ld;
+    uint16_t* P = POS + (size_t)d * c.ld;
+    int cnt = 0;
+    for (int i = 1; i <= n - d; i++) {
+      P[i] = (uint16_t)cnt;
+      if (d > TURN && pair_type(base(c, i), base(c, i + d))) L[cnt++] = (uint16_t)i;
+    }
+    P[n - d + 1 <= n ? n - d + 1 : n] = (uint16_t)cnt;  // d = 0: i = n+1 does not exist and is never asked for
+    if (d == 0) P[n] = 0;
+  }
+}
+
+template <class C>
+RP_HD void prologue2(C& c, int ct, int nct) {
+  const DevModel& M = *c.M;
+  const int n = c.n;
+  for (int u = ct; u <= n; u += nct) {
+    double q;
+    if (u <= 30) q = M.exphairpin[u];
+    else q = M.exphairpin[30] * exp(-(M.lxc * log(u / 30.)) * 10. / M.kT);
+    VEC(c, V_HPW, u) = q * VEC(c, V_SCALE, u + 2);
+  }
+  for (int i = ct; i <= n + 1; i += nct) {
+    double s3 = -1., s4 = -1., s6 = -1.;
+    if (i >= 1) {
+      // window codes: base-8 digits, 7 for letters that cannot match a list entry
+      int code = 0;
+      bool in = true;
+      for (int k = 0; k < 8; k++) {
+        int p = i + k;
+        int dgt = 0;
+        if (p <= n) dgt = (c.sraw(p) & 8) ? 7 : (c.sraw(p) & 7);
+        else in = false;
+        code = code * 8 + dgt;
+        // a hairpin window never spans the nick (hairpins need ss(i,j))
+        if (k == 4 && in) {
+          for (int e = 0; e < M.n_tri; e++)
+            if (M.tri_code[e] == code) { s3 = M.exptri[e] * VEC(c, V_SCALE, 5); break; }
+        } else if (k == 5 && in) {
+          for (int e = 0; e < M.n_tetra; e++)
+            if (M.tetra_code[e] == code) { s4 = M.exptetra[e] * VEC(c, V_SCALE, 6); break; }
+        } else if (k == 7 && in) {
+          for (int e = 0; e < M.n_hex; e++)
+            if (M.hex_code[e] == code) { s6 = M.exphex[e] * VEC(c, V_SCALE, 8); break; }
+        }
+      }
+    }
+    VEC(c, V_SP3, i) = s3; VEC(c, V_SP4, i) = s4; VEC(c, V_SP6, i) = s6;
+    VEC(c, V_U0, i) = 0.; VEC(c, V_U1, i) = 0.;
+    VEC(c, V_QR, i) = 0.; VEC(c, V_QROUT, i) = 0.; VEC(c, V_QL, i) = 0.; VEC(c, V_QLOUT, i) = 0.;
+  }
+  // diagonals 0..TURN: q = scale[d+1], everything else 0
+  const int dmax = TURN < n - 1 ? TURN : n - 1;
+  const int cells = (dmax + 1) * c.ld;
+  for (int x = ct; x < cells; x += nct) {
+    int d = x / c.ld, i = x % c.ld;
+    bool valid = i >= 1 && i + d <= n;
+    TB(c, T_Q, d, i) = valid ? VEC(c, V_SCALE, d + 1) : 0.;
+    TB(c, T_QQ, d, i) = 0.; TB(c, T_QM, d, i) = 0.; TB(c, T_QM1, d, i) = 0.; TB(c, T_QM2, d, i) = 0.;
+    TB(c, T_QB, d, i) = 0.; TB(c, T_QBI, d, i) = 0.; TB(c, T_QB1N, d, i) = 0.; TB(c, T_QBAU, d, i) = 0.;
+    TB(c, T_OUT, d, i) = 0.; TB(c, T_OUTI, d, i) = 0.; TB(c, T_OUT1N, d, i) = 0.; TB(c, T_OUTAU, d, i) = 0.;
+    TB(c, T_MC, d, i) = 0.; TB(c, T_PR, d, i) = 0.; TB(c, T_PRML, d, i) = 0.; TB(c, T_PMLB, d, i) = 0.;
+    TB(c, T_PL, d, i) = 0.; TB(c, T_DG, d, i) = 0.;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// inside pass, cell (i, j=i+d), d >= TURN+1
+// ---------------------------------------------------------------------------
+// slice sl of SI of the interior-loop sum of a cell that can pair
+template <class C>
+RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int type, int sl, int SI) {
+  const DevModel& M = *c.M;
+  const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
+  if (ddmax < 2) return 0.;
+  const int j = i + d;
+  // strand guards: inner 5' end must stay on i's strand, inner 3' end on j's
+  const int maxpo = (c.cp > 0 && i < c.cp) ? c.cp - 1 - i : 1000;
+  const int maxu2 = (c.cp > 0 && j >= c.cp) ? j - 1 - c.cp : 1000;
+  const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
+  int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
+  if (maxpo - 1 < u1max) u1max = maxpo - 1;
+  double sI = 0., s1 = 0., sA = 0.;
+  if (!(c.dbg & 1))
+    interior_rows<1>(sh, c.ptr(T_QBI, d, i), c.ptr(T_QB1N, d, i), c.ptr(T_QBAU, d, i), c.dstep(), c.pstep(), u1max, maxu2,
+                     ddmax, sl, SI, sI, s1, sA);
+  double accI = M.mmI[type][si1][sj1] * sI + M.mm1n[type][si1][sj1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
+  // table-driven small loops
+  for (int s = sl; s < RP_N_SPECIAL; s += SI) {
+    int u1, u2;
+    special_uv(s, u1, u2);
+    const int dd = u1 + u2 + 2;
+    if (dd > ddmax || u1 + 1 > maxpo || u2 > maxu2) continue;
+    const int k = i + 1 + u1, l = j - 1 - u2;
+    const int t2 = pair_type(base(c, k), base(c, l));
+    if (!t2) continue;
+    accI += TB(c, T_QB, d - dd, k) * special_loop(M, s, type, rtype(t2), si1, sj1, base(c, k - 1), base(c, l + 1));
+  }
+  return accI;
+}
+
+// slice `slice` of S of the two split sums of cell (i,j)
+template <class C>
+RP_HD void inside_splits(const C& c, int d, int i, int slice, int S, double& accM, double& accQ) {
+  const int ds = c.dstep(), ps = c.pstep();
+  accM = 0.; accQ = 0.;
+  if (c.dbg & 2) return;
+  // QM2(i,j) = sum_a qm[a][i] * qm1[d-1-a][i+1+a], a = TURN+1 .. d-2-TURN; the split k=i+1+a may not be the nick
+  const int cntM = d - 2 * TURN - 2;
+  if (cntM > 0) {
+    const int skip = c.cp > 0 ? c.cp - 1 - i - (TURN + 1) : -1;  // a = cp-1-i  <=> k = cp
+    accM = strided_dot(c.ptr(T_QM, TURN + 1, i), ds, c.ptr(T_QM1, d - 2 - TURN, i + TURN + 2), ps - ds, cntM, slice, S, skip);
+  }
+  // sum_a q[a][i] * qq[d-1-a][i+1+a], a = 0 .. d-2-TURN
+  const int cntQ = d - 1 - TURN;
+  if (cntQ > 0) accQ = strided_dot(c.ptr(T_Q, 0, i), ds, c.ptr(T_QQ, d - 1, i + 1), ps - ds, cntQ, slice, S, -1);
+}
+
+// combine: everything of cell (i,j) that is O(1) once the three sums are known
+template <class C>
+RP_HD void inside_finish(C& c, int d, int i, int type, double sI, double sM, double sQ) {
+  const DevModel& M = *c.M;
+  const int j = i + d, n = c.n;
+  const double scale2 = VEC(c, V_SCALE, 2);
   double qb = 0.;
   if (type) {
-    if (d - (TURN + 1) >= 2) {
-      const ISplit is = make_isplit(c, d, i0, C, T);
-      const int r = (int)posp(c)[(size_t)d * c.ld + i] - is.lo;
-      for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
-    }
     if (ss(c, i, j)) qb += hairpin(c, i, j, type);
     qb += sI;
     if (ss(c, i, i + 1) && ss(c, j - 1, j))
-      qb += TB(c, T_QM2, d - 2, i + 1) * M.expMLclosing * ml_stem(M, rtype(type), base(c, j - 1), base(c, i + 1)) * scale[2];
+      qb += TB(c, T_QM2, d - 2, i + 1) * M.expMLclosing * ml_stem(M, rtype(type), base(c, j - 1), base(c, i + 1)) * scale2;
     if (!ss(c, i, j)) {
       // the loop that contains the nick is an exterior loop
-      double t = scale[2];
+      double t = scale2;
       if (i + 1 <= c.cp - 1) t *= TB(c, T_Q, c.cp - 2 - i, i + 1);
       if (c.cp <= j - 1) t *= TB(c, T_Q, j - 1 - c.cp, c.cp);
       t *= ext_stem(M, rtype(type), ss(c, j - 1, j) ? base(c, j - 1) : -1, ss(c, i, i + 1) ? base(c, i + 1) : -1);
@@ -555,10 +564,9 @@ RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
     qm1 += qb * ml_stem(M, type, i > 1 ? base(c, i - 1) : -1, j < n ? base(c, j + 1) : -1);
   TB(c, T_QM1, d, i) = qm1;
   // U(i,j) = sum_k mlb[k-i] qm1(k,j) = mlb1*(qm1(i+1,j) + U(i+1,j)), cut at the nick
-  const double* Uprev = vecp(c, (d & 1) ? V_U0 : V_U1);
-  double* Ucur = vecp(c, (d & 1) ? V_U1 : V_U0);
-  const double U = ss(c, i, i + 1) ? M.mlb1 * (TB(c, T_QM1, d - 1, i + 1) + Uprev[i + 1]) : 0.;
-  Ucur[i] = U;
+  const int vprev = (d & 1) ? V_U0 : V_U1, vcur = (d & 1) ? V_U1 : V_U0;
+  const double U = ss(c, i, i + 1) ? M.mlb1 * (TB(c, T_QM1, d - 1, i + 1) + VEC(c, vprev, i + 1)) : 0.;
+  VEC(c, vcur, i) = U;
   TB(c, T_QM, d, i) = qm1 + sM + U;
   // exterior
   double qq = TB(c, T_QQ, d - 1, i) * M.scale1;
@@ -566,163 +574,205 @@ RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
     qq += qb * ext_stem(M, type, (i > 1 && ss(c, i - 1, i)) ? base(c, i - 1) : -1,
                         (j < n && ss(c, j, j + 1)) ? base(c, j + 1) : -1);
   TB(c, T_QQ, d, i) = qq;
-  TB(c, T_Q, d, i) = scale[d + 1] + qq + sQ;
+  TB(c, T_Q, d, i) = VEC(c, V_SCALE, d + 1) + qq + sQ;
 }
 
-RP_HD void inside_end(Ctx& c) { c.invZ = 1.0 / TB(c, T_Q, c.n - 1, 1); }
+template <class C>
+RP_HD void inside_end(C& c) { c.invZ = 1.0 / TB(c, T_Q, c.n - 1, 1); }
+
+// general kernel, phase A: sliced work items, partials to sh.part [3][T] (interior, QM2, q-split)
+RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if (d - (TURN + 1) >= 2) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = tid % is.cntp, sl = tid / is.cntp;
+    if (sl < is.SI && r < is.cnt) {
+      const int i = listp(c)[(size_t)d * c.ld + is.lo + r];
+      sh.part[tid] = inside_interior(c, sh, d, i, pair_type(base(c, i), base(c, i + d)), sl, is.SI);
+    }
+  }
+  const Split sp = make_split(C, T);
+  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
+  if (slice < sp.S && cell < C) {
+    double accM, accQ;
+    inside_splits(c, d, i0 + cell, slice, sp.S, accM, accQ);
+    sh.part[T + tid] = accM;
+    sh.part[2 * T + tid] = accQ;
+  }
+}
+// general kernel, phase B: one thread per cell
+RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  const Split sp = make_split(C, T);
+  if (tid >= sp.Cp || tid >= C) return;
+  const int i = i0 + tid;
+  double sI = 0., sM = 0., sQ = 0.;
+  for (int s = 0; s < sp.S; s++) {
+    sM += sh.part[T + s * sp.Cp + tid];
+    sQ += sh.part[2 * T + s * sp.Cp + tid];
+  }
+  const int type = pair_type(base(c, i), base(c, i + d));
+  if (type && d - (TURN + 1) >= 2) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = (int)posp(c)[(size_t)d * c.ld + i] - is.lo;
+    for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+  }
+  inside_finish(c, d, i, type, sI, sM, sQ);
+}
+// lockstep kernel: a thread does whole cells of its own problem
+template <class C>
+RP_HD void inside_cells(C& c, const Shared& sh, int d, int ct, int nct) {
+  const int cells = c.n - d;
+  for (int cell = ct; cell < cells; cell += nct) {
+    const int i = 1 + cell;
+    const int type = pair_type(base(c, i), base(c, i + d));
+    const double sI = type ? inside_interior(c, sh, d, i, type, 0, 1) : 0.;
+    double sM, sQ;
+    inside_splits(c, d, i, 0, 1, sM, sQ);
+    inside_finish(c, d, i, type, sI, sM, sQ);
+  }
+}
 
 // ---------------------------------------------------------------------------
 // outside pass, diagonal d from n-1 down to TURN+1.
 // out(k,l) = Z_outside(k,l)/Z  (ViennaRNA's probs[] before the final *qb).
 // ---------------------------------------------------------------------------
-// two-strand only, twice per diagonal before outside_A: the closing pairs that
+// two-strand only, twice per diagonal before the cells: the closing pairs that
 // straddle the nick feed the stems sitting directly in the nicked loop.
 //   Qr(r)    = sum_{p<cp} out(p,r) ExtClose(p,r) scale[2] q(p+1,cp-1)        complete after diag r-cp+1
 //   Qrout(l) = sum_{r>l} Qr(r) q(l+1,r-1)
 //   Ql(p)    = sum_{r>=cp} out(p,r) ExtClose(p,r) scale[2] q(cp,r-1)         complete after diag cp-p
 //   Qlout(k) = sum_{p<k} Ql(p) q(p+1,k-1)
-// Step d finalises Qr(d+cp), Qrout(d+cp-1), Ql(cp-1-d), Qlout(cp-d).  Each sum
-// is split over 32 threads (fixed partition => deterministic), partials in sh.red.
-RP_HD double nick_close(const Ctx& c, int p, int r) {
+// Step d finalises Qr(d+cp), Qrout(d+cp-1), Ql(cp-1-d), Qlout(cp-d).  Each of the
+// four sums is split over `np` threads (fixed partition => deterministic);
+// partial (job, lane) goes to red[(job*np+lane)*rs].
+template <class C>
+RP_HD double nick_close(const C& c, int p, int r) {
   const int tp = pair_type(base(c, p), base(c, r));
   if (!tp || r - p <= TURN) return 0.;
   const double o = TB(c, T_OUT, r - p, p);
   if (o == 0.) return 0.;
-  return o * vecp(c, V_SCALE)[2] *
+  return o * VEC(c, V_SCALE, 2) *
          ext_stem(*c.M, rtype(tp), ss(c, r - 1, r) ? base(c, r - 1) : -1, ss(c, p, p + 1) ? base(c, p + 1) : -1);
 }
-RP_HD void outside_nick1(Ctx& c, const Shared& sh, int d, int tid) {
+template <class C>
+RP_HD void outside_nick1(C& c, double* red, int rs, int np, int d, int ct, int nct) {
   if (c.cp <= 0) return;
   const int n = c.n, cp = c.cp;
-  for (int w = tid; w < 128; w += sh.T) {
-    const int lane = w & 31, job = w >> 5;
+  for (int w = ct; w < 4 * np; w += nct) {
+    const int lane = w % np, job = w / np;
     double s = 0.;
     if (job == 0) {          // Qr(r), r = d+cp: closing pairs (p,r), all of diag >= d+1
       const int r = d + cp;
       if (r >= cp && r <= n)
-        for (int p = 1 + lane; p < cp; p += 32) {
+        for (int p = 1 + lane; p < cp; p += np) {
           const double v = nick_close(c, p, r);
           if (v != 0.) s += v * (p + 1 <= cp - 1 ? TB(c, T_Q, cp - 2 - p, p + 1) : 1.0);
         }
     } else if (job == 1) {   // Ql(p), p = cp-1-d
       const int p = cp - 1 - d;
       if (p >= 1 && p < cp)
-        for (int rr = cp + lane; rr <= n; rr += 32) {
+        for (int rr = cp + lane; rr <= n; rr += np) {
           const double v = nick_close(c, p, rr);
           if (v != 0.) s += v * (cp <= rr - 1 ? TB(c, T_Q, rr - 1 - cp, cp) : 1.0);
         }
     } else if (job == 2) {   // part of Qrout(l), l = d+cp-1, that uses Qr(r), r >= l+2 (earlier steps)
       const int l = d + cp - 1;
       if (l >= cp && l < n)
-        for (int r = l + 2 + lane; r <= n; r += 32) s += vecp(c, V_QR)[r] * TB(c, T_Q, r - 2 - l, l + 1);
+        for (int r = l + 2 + lane; r <= n; r += np) s += VEC(c, V_QR, r) * TB(c, T_Q, r - 2 - l, l + 1);
     } else {                 // part of Qlout(k), k = cp-d, that uses Ql(p), p <= k-2 (earlier steps)
       const int k = cp - d;
       if (k >= 2 && k < cp)
-        for (int p = 1 + lane; p <= k - 2; p += 32) s += vecp(c, V_QL)[p] * TB(c, T_Q, k - 2 - p, p + 1);
+        for (int p = 1 + lane; p <= k - 2; p += np) s += VEC(c, V_QL, p) * TB(c, T_Q, k - 2 - p, p + 1);
     }
-    sh.red[w] = s;
+    red[(size_t)w * rs] = s;
   }
 }
-RP_HD void outside_nick2(Ctx& c, const Shared& sh, int d, int tid) {
+template <class C>
+RP_HD void outside_nick2(C& c, const double* red, int rs, int np, int d, int ct, int nct) {
   if (c.cp <= 0) return;
   const int n = c.n, cp = c.cp;
-  if (tid == 0) {
+  const int second = nct > np ? np : (nct > 1 ? 1 : 0);  // a thread of another warp when there is one
+  if (ct == 0) {
     double qr = 0., rest = 0.;
-    for (int t = 0; t < 32; t++) { qr += sh.red[t]; rest += sh.red[64 + t]; }
+    for (int t = 0; t < np; t++) { qr += red[(size_t)t * rs]; rest += red[(size_t)(2 * np + t) * rs]; }
     const int r = d + cp, l = d + cp - 1;
-    if (r >= cp && r <= n) vecp(c, V_QR)[r] = qr;
+    if (r >= cp && r <= n) VEC(c, V_QR, r) = qr;
     // Qrout(l) = Qr(l+1)*q(l+1,l) + rest, q of the empty segment is 1
-    if (l >= cp && l < n) vecp(c, V_QROUT)[l] = qr + rest;
-  } else if (tid == 32 || (sh.T <= 32 && tid == 1)) {
+    if (l >= cp && l < n) VEC(c, V_QROUT, l) = qr + rest;
+  }
+  if (ct == second) {
     double ql = 0., rest = 0.;
-    for (int t = 0; t < 32; t++) { ql += sh.red[32 + t]; rest += sh.red[96 + t]; }
+    for (int t = 0; t < np; t++) { ql += red[(size_t)(np + t) * rs]; rest += red[(size_t)(3 * np + t) * rs]; }
     const int p = cp - 1 - d, k = cp - d;
-    if (p >= 1 && p < cp) vecp(c, V_QL)[p] = ql;
-    if (k >= 2 && k < cp) vecp(c, V_QLOUT)[k] = ql + rest;
+    if (p >= 1 && p < cp) VEC(c, V_QL, p) = ql;
+    if (k >= 2 && k < cp) VEC(c, V_QLOUT, k) = ql + rest;
   }
 }
 
-// sh.part: [3][T] doubles (interior, PR, ML-left)
-RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+// slice sl of SI of the interior-loop sum seen from the inner pair (k,l) (which can pair)
+template <class C>
+RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl, int SI) {
   const DevModel& M = *c.M;
-  const int T = sh.T, n = c.n;
-  const long ld = c.ld;
-  // --- (1) interior loops seen from the inner pair (k,l): items = (pairable cell, slice)
+  const int n = c.n, l = k + d;
   const int ddmax = n - 1 - d < MAXLOOP + 2 ? n - 1 - d : MAXLOOP + 2;
-  if (ddmax >= 2) {
-    const ISplit is = make_isplit(c, d, i0, C, T);
-    const int r = tid % is.cntp, sl = tid / is.cntp;
-    if (sl < is.SI && r < is.cnt) {
-      const int k = listp(c)[(size_t)d * ld + is.lo + r], l = k + d;
-      double accI = 0.;
-      // enclosing pair (i,j) = (k-po, l+1+u2)
-      int maxpo = k - 1, maxu2 = n - l - 1;
-      if (c.cp > 0) {
-        if (k >= c.cp && k - c.cp < maxpo) maxpo = k - c.cp;        // i must stay on k's strand
-        if (l < c.cp && c.cp - 2 - l < maxu2) maxu2 = c.cp - 2 - l;  // j must stay on l's strand
-      }
-      if (maxpo >= 1 && maxu2 >= 0 && TB(c, T_QB, d, k) != 0.) {
-        const int type = pair_type(base(c, k), base(c, l));
-        const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
-        int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
-        if (maxpo - 1 < u1max) u1max = maxpo - 1;
-        double sI = 0., s1 = 0., sA = 0.;
-        if (!(c.dbg & 1)) interior_rows<-1>(sh, tabp(c, T_OUTI), tabp(c, T_OUT1N), tabp(c, T_OUTAU), d * (int)ld + k, (int)ld, u1max,
-                          maxu2, ddmax, sl, is.SI, sI, s1, sA);
-        accI = M.mmI[t2][sq1][sp1] * sI + M.mm1n[t2][sq1][sp1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
-        for (int s = sl; s < RP_N_SPECIAL; s += is.SI) {
-          int u1, u2;
-          special_uv(s, u1, u2);
-          const int dd = u1 + u2 + 2;
-          if (dd > ddmax || u1 + 1 > maxpo || u2 > maxu2) continue;
-          const int i = k - 1 - u1, j = l + 1 + u2;
-          const int t1 = pair_type(base(c, i), base(c, j));
-          if (!t1) continue;
-          const double o = TB(c, T_OUT, d + dd, i);
-          if (o == 0.) continue;
-          accI += o * special_loop(M, s, t1, t2, base(c, i + 1), base(c, j - 1), sp1, sq1);
-        }
-      }
-      sh.part[tid] = accI;
-    }
+  if (ddmax < 2) return 0.;
+  // enclosing pair (i,j) = (k-1-u1, l+1+u2)
+  int maxpo = k - 1, maxu2 = n - l - 1;
+  if (c.cp > 0) {
+    if (k >= c.cp && k - c.cp < maxpo) maxpo = k - c.cp;        // i must stay on k's strand
+    if (l < c.cp && c.cp - 2 - l < maxu2) maxu2 = c.cp - 2 - l;  // j must stay on l's strand
   }
-  // --- (2) multiloop sums: items = (cell, slice) --------------------------------
-  const Split sp = make_split(C, T);
-  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
-  if (slice < sp.S && cell < C) {
-    const int k = i0 + cell, l = k + d;
-    double accP = 0., accL = 0.;
-    // PR(k,l) = sum_b Mc[d+2+b][k] * qm[b][l+1], b = TURN+1 .. n-l-2   [k is the closing 5' end]
-    if (l + 2 <= n && ss(c, l, l + 1)) {
-      const int cnt = n - l - 2 - TURN;
-      if (cnt > 0 && !(c.dbg & 2))
-        accP = strided_dot(tabp(c, T_MC) + (size_t)(d + 3 + TURN) * ld + k, ld,
-                           tabp(c, T_QM) + (size_t)(TURN + 1) * ld + l + 1, ld, cnt, slice, sp.S, -1);
-    }
-    // ML-left(k,l) = sum_cc PRML[d+2+cc][k-2-cc] * qm[cc][k-1-cc], cc = TURN+1 .. k-3
-    if (l < n && k > 2 && ss(c, k - 1, k) && ss(c, l, l + 1) && posp(c)[(size_t)d * ld + k + 1] != posp(c)[(size_t)d * ld + k]) {
-      const int cnt = k - 3 - TURN;
-      if (cnt > 0 && !(c.dbg & 2) && TB(c, T_QB, d, k) != 0.)
-        accL = strided_dot(tabp(c, T_PRML) + (size_t)(d + 3 + TURN) * ld + k - 3 - TURN, ld - 1,
-                           tabp(c, T_QM) + (size_t)(TURN + 1) * ld + k - 2 - TURN, ld - 1, cnt, slice, sp.S, -1);
-    }
-    sh.part[T + tid] = accP;
-    sh.part[2 * T + tid] = accL;
+  if (maxpo < 1 || maxu2 < 0 || TB(c, T_QB, d, k) == 0.) return 0.;
+  const int type = pair_type(base(c, k), base(c, l));
+  const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
+  int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
+  if (maxpo - 1 < u1max) u1max = maxpo - 1;
+  double sI = 0., s1 = 0., sA = 0.;
+  if (!(c.dbg & 1))
+    interior_rows<-1>(sh, c.ptr(T_OUTI, d, k), c.ptr(T_OUT1N, d, k), c.ptr(T_OUTAU, d, k), c.dstep(), c.pstep(), u1max,
+                      maxu2, ddmax, sl, SI, sI, s1, sA);
+  double accI = M.mmI[t2][sq1][sp1] * sI + M.mm1n[t2][sq1][sp1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
+  for (int s = sl; s < RP_N_SPECIAL; s += SI) {
+    int u1, u2;
+    special_uv(s, u1, u2);
+    const int dd = u1 + u2 + 2;
+    if (dd > ddmax || u1 + 1 > maxpo || u2 > maxu2) continue;
+    const int i = k - 1 - u1, j = l + 1 + u2;
+    const int t1 = pair_type(base(c, i), base(c, j));
+    if (!t1) continue;
+    const double o = TB(c, T_OUT, d + dd, i);
+    if (o == 0.) continue;
+    accI += o * special_loop(M, s, t1, t2, base(c, i + 1), base(c, j - 1), sp1, sq1);
+  }
+  return accI;
+}
+
+// slice of the two multiloop sums of cell (k,l); `pairs` = the cell can pair
+template <class C>
+RP_HD void outside_splits(const C& c, int d, int k, bool pairs, int slice, int S, double& accP, double& accL) {
+  const int ds = c.dstep(), ps = c.pstep(), n = c.n, l = k + d;
+  accP = 0.; accL = 0.;
+  if (c.dbg & 2) return;
+  // PR(k,l) = sum_b Mc[d+2+b][k] * qm[b][l+1], b = TURN+1 .. n-l-2   [k is the closing 5' end]
+  if (l + 2 <= n && ss(c, l, l + 1)) {
+    const int cnt = n - l - 2 - TURN;
+    if (cnt > 0) accP = strided_dot(c.ptr(T_MC, d + 3 + TURN, k), ds, c.ptr(T_QM, TURN + 1, l + 1), ds, cnt, slice, S, -1);
+  }
+  // ML-left(k,l) = sum_cc PRML[d+2+cc][k-2-cc] * qm[cc][k-1-cc], cc = TURN+1 .. k-3
+  if (pairs && l < n && k > 2 && ss(c, k - 1, k) && ss(c, l, l + 1)) {
+    const int cnt = k - 3 - TURN;
+    if (cnt > 0 && TB(c, T_QB, d, k) != 0.)
+      accL = strided_dot(c.ptr(T_PRML, d + 3 + TURN, k - 3 - TURN), ds - ps, c.ptr(T_QM, TURN + 1, k - 2 - TURN), ds - ps, cnt,
+                         slice, S, -1);
   }
 }
 
-RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+template <class C>
+RP_HD void outside_finish(C& c, int d, int k, int type, double sI, double sP, double sL) {
   const DevModel& M = *c.M;
-  const int T = sh.T;
-  const Split sp = make_split(C, T);
-  if (tid >= sp.Cp || tid >= C) return;
-  const int k = i0 + tid, l = k + d, n = c.n;
-  double sI = 0., sP = 0., sL = 0.;
-  for (int s = 0; s < sp.S; s++) {
-    sP += sh.part[T + s * sp.Cp + tid];
-    sL += sh.part[2 * T + s * sp.Cp + tid];
-  }
-  const double* scale = vecp(c, V_SCALE);
+  const int l = k + d, n = c.n;
+  const double scale2 = VEC(c, V_SCALE, 2);
   const bool mlr = l < n && ss(c, l, l + 1);  // something may follow l inside a multiloop
   // right side all unpaired: PL(k,l) = sum_{j>l} Mc(k,j) mlb^(j-l-1)
   const double PL = mlr ? TB(c, T_PL, d + 1, k) * M.mlb1 + TB(c, T_MC, d + 1, k) : 0.;
@@ -735,28 +785,22 @@ RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   if (k > 1 && ss(c, k - 1, k)) PMLB = TB(c, T_PMLB, d + 1, k - 1) * M.mlb1 + TB(c, T_PR, d + 1, k - 1);
   TB(c, T_PMLB, d, k) = PMLB;
 
-  const int type = pair_type(base(c, k), base(c, l));
   double out = 0.;
   if (type && TB(c, T_QB, d, k) != 0.) {
-    if ((n - 1 - d) >= 2) {
-      const ISplit is = make_isplit(c, d, i0, C, T);
-      const int r = (int)posp(c)[(size_t)d * c.ld + k] - is.lo;
-      for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
-    }
     const double q5 = k > 1 ? TB(c, T_Q, k - 2, 1) : 1.0;
     const double q3 = l < n ? TB(c, T_Q, n - l - 1, l + 1) : 1.0;
     out = q5 * q3 * c.invZ *
           ext_stem(M, type, (k > 1 && ss(c, k - 1, k)) ? base(c, k - 1) : -1, (l < n && ss(c, l, l + 1)) ? base(c, l + 1) : -1);
     out += sI;
-    if (mlr && k > 1 && ss(c, k - 1, k)) out += (PMLB + sL) * ml_stem(M, type, base(c, k - 1), base(c, l + 1)) * scale[2];
+    if (mlr && k > 1 && ss(c, k - 1, k)) out += (PMLB + sL) * ml_stem(M, type, base(c, k - 1), base(c, l + 1)) * scale2;
     if (c.cp > 0) {
       if (k >= c.cp) {
-        const double qo = vecp(c, V_QROUT)[l];
+        const double qo = VEC(c, V_QROUT, l);
         if (qo != 0.)
           out += qo * (k > c.cp ? TB(c, T_Q, k - 1 - c.cp, c.cp) : 1.0) *
                  ext_stem(M, type, k > c.cp ? base(c, k - 1) : -1, base(c, l + 1));
       } else if (l < c.cp) {
-        const double qo = vecp(c, V_QLOUT)[k];
+        const double qo = VEC(c, V_QLOUT, k);
         if (qo != 0.)
           out += qo * (l + 1 <= c.cp - 1 ? TB(c, T_Q, c.cp - 2 - l, l + 1) : 1.0) *
                  ext_stem(M, type, base(c, k - 1), l + 1 < c.cp ? base(c, l + 1) : -1);
@@ -778,11 +822,65 @@ RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   TB(c, T_MC, d, k) = mc;
 }
 
+// general kernel: sh.part [3][T] (interior, PR, ML-left)
+RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if (c.n - 1 - d >= 2) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = tid % is.cntp, sl = tid / is.cntp;
+    if (sl < is.SI && r < is.cnt) {
+      const int k = listp(c)[(size_t)d * c.ld + is.lo + r];
+      sh.part[tid] = outside_interior(c, sh, d, k, sl, is.SI);
+    }
+  }
+  const Split sp = make_split(C, T);
+  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
+  if (slice < sp.S && cell < C) {
+    const int k = i0 + cell;
+    const uint16_t* P = posp(c) + (size_t)d * c.ld;
+    double accP, accL;
+    outside_splits(c, d, k, P[k + 1] != P[k], slice, sp.S, accP, accL);
+    sh.part[T + tid] = accP;
+    sh.part[2 * T + tid] = accL;
+  }
+}
+RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  const Split sp = make_split(C, T);
+  if (tid >= sp.Cp || tid >= C) return;
+  const int k = i0 + tid;
+  double sI = 0., sP = 0., sL = 0.;
+  for (int s = 0; s < sp.S; s++) {
+    sP += sh.part[T + s * sp.Cp + tid];
+    sL += sh.part[2 * T + s * sp.Cp + tid];
+  }
+  const int type = pair_type(base(c, k), base(c, k + d));
+  if (type && c.n - 1 - d >= 2 && TB(c, T_QB, d, k) != 0.) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = (int)posp(c)[(size_t)d * c.ld + k] - is.lo;
+    for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+  }
+  outside_finish(c, d, k, type, sI, sP, sL);
+}
+template <class C>
+RP_HD void outside_cells(C& c, const Shared& sh, int d, int ct, int nct) {
+  const int cells = c.n - d;
+  for (int cell = ct; cell < cells; cell += nct) {
+    const int k = 1 + cell;
+    const int type = pair_type(base(c, k), base(c, k + d));
+    const double sI = type ? outside_interior(c, sh, d, k, 0, 1) : 0.;
+    double sP, sL;
+    outside_splits(c, d, k, type != 0, 0, 1, sP, sL);
+    outside_finish(c, d, k, type, sI, sP, sL);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // unpaired windows (single strand): up(i,d) = P(i..i+d unpaired), d < max_w
 // ---------------------------------------------------------------------------
 // U1: DG(p,o) = out(p,o)*hairpin(p,o)   (loop whose unpaired run is (p,o))
-RP_HD void unstru_hairpin(Ctx& c, int tid, int T) {
+template <class C>
+RP_HD void unstru_hairpin(C& c, int tid, int T) {
   const int n = c.n;
   const size_t total = (size_t)n * c.ld;
   for (size_t x = tid; x < total; x += T) {
@@ -802,29 +900,11 @@ RP_HD void unstru_hairpin(Ctx& c, int tid, int T) {
 // product of two table rows that already carry the pair factors:
 //   side 0:  sum_l  outX(p, l+1+u2) * qbX(k, l)          (both advance one diagonal per l)
 //   side 1:  sum_p  outX(p, o)      * qbX(p+1+u1, l)     (both step one diagonal down, one cell right)
-// Up to 8 dot products that share the streamed operand A:
-//   acc[t] += sum_{x<cnt} A[x*sa] * B[t*tb + x*sb],  t < nu
-// The B streams of neighbouring t overlap (a sliding window), so all but one of the B loads of
-// an iteration hit L1: per 8 FMAs only two new values travel from L2.
-RP_HD void multi_dot(const double* A, int sa, const double* B, int sb, int tb, int cnt, int nu, double* acc) {
-  for (int x = 0; x < cnt; x++, A += sa, B += sb) {
-    const double a = *A;
-#pragma unroll
-    for (int t = 0; t < 8; t++)
-      if (t < nu) acc[t] += a * B[t * tb];
-  }
-}
-
-RP_HD int special_index(int u1, int u2) {
-  // inverse of special_uv: (0,0)->0 (1,0)->1 (0,1)->2 (1,1)->3 (1,2)->4 (2,1)->5 (2,2)->6 (2,3)->7 (3,2)->8
-  if (u1 == 0) return u2 == 0 ? 0 : 2;
-  if (u1 == 1) return u2 == 0 ? 1 : (u2 == 1 ? 3 : 4);
-  if (u1 == 2) return u2 == 1 ? 5 : (u2 == 2 ? 6 : 7);
-  return 8;
-}
-RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
+// Runs of up to 8 shifts of one class share the streamed operand (multi_dot).
+template <class C>
+RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
   const DevModel& M = *c.M;
-  const int n = c.n, ld = c.ld;
+  const int n = c.n, ds = c.dstep(), ps = c.pstep();
   const int items = (c.dbg & 4) ? 0 : n * (MAXLOOP + 1);
   const int tabO[3] = {T_OUTI, T_OUT1N, T_OUTAU};
   const int tabQ[3] = {T_QBI, T_QB1N, T_QBAU};
@@ -845,14 +925,14 @@ RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
           int nu = 1;
           while (nu < 8 && u1 + u2 + nu <= MAXLOOP && M.gcls[u1][u2 + nu] == cls && n - 1 - (u2 + nu) >= lmin) nu++;
           double av[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-          const double* Q = tabp(c, tabQ[cls]) + (size_t)(lmin - k) * ld + k;           // qbX(k,l), one diagonal per l
-          const double* O = tabp(c, tabO[cls]) + (size_t)(lmin + 1 + u2 - p) * ld + p;  // outX(p,l+1+u2), +ld per u2
-          const int cmain = n - 1 - (u2 + nu - 1) - lmin + 1;  // l range valid for every u2 of the run
-          multi_dot(Q, ld, O, ld, ld, cmain, nu, av);
+          const double* Q = c.ptr(tabQ[cls], lmin - k, k);           // qbX(k,l), one diagonal per l
+          const double* O = c.ptr(tabO[cls], lmin + 1 + u2 - p, p);  // outX(p,l+1+u2), one diagonal per u2
+          const int cmain = n - 1 - (u2 + nu - 1) - lmin + 1;        // l range valid for every u2 of the run
+          multi_dot(Q, ds, O, ds, ds, cmain, nu, av);
           for (int t = 0; t < nu; t++) {
             // the shorter shifts reach further: l up to n-1-(u2+t)
             const int cnt = n - 1 - (u2 + t) - lmin + 1;
-            if (cnt > cmain) av[t] += dot_range(Q, ld, O + (size_t)t * ld, ld, cmain, cnt, 0, 1);
+            if (cnt > cmain) av[t] += dot_range(Q, ds, O + (long)t * ds, ds, cmain, cnt, 0, 1);
             acc += M.gfull[u1][u2 + t] * av[t];
           }
           u2 += nu;
@@ -881,13 +961,13 @@ RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
           int nu = 1;
           while (nu < 8 && u1 + nu + u2 <= MAXLOOP && M.gcls[u1 + nu][u2] == cls && l - TURN - 2 - (u1 + nu) >= 1) nu++;
           double av[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-          const double* O = tabp(c, tabO[cls]) + (size_t)(o - 1) * ld + 1;               // outX(p,o): one diagonal down, one cell right per p
-          const double* Q = tabp(c, tabQ[cls]) + (size_t)(l - 2 - u1) * ld + 2 + u1;     // qbX(p+1+u1,l); per u1: 1-ld
-          const int cmain = l - TURN - 2 - (u1 + nu - 1);  // p = 1..cmain valid for every u1 of the run
-          multi_dot(O, 1 - ld, Q, 1 - ld, 1 - ld, cmain, nu, av);
+          const double* O = c.ptr(tabO[cls], o - 1, 1);               // outX(p,o): one diagonal down, one cell right per p
+          const double* Q = c.ptr(tabQ[cls], l - 2 - u1, 2 + u1);     // qbX(p+1+u1,l); per u1 likewise
+          const int cmain = l - TURN - 2 - (u1 + nu - 1);             // p = 1..cmain valid for every u1 of the run
+          multi_dot(O, ps - ds, Q, ps - ds, ps - ds, cmain, nu, av);
           for (int t = 0; t < nu; t++) {
             const int cnt = l - TURN - 2 - (u1 + t);
-            if (cnt > cmain) av[t] += dot_range(O, 1 - ld, Q + (long)t * (1 - ld), 1 - ld, cmain, cnt, 0, 1);
+            if (cnt > cmain) av[t] += dot_range(O, ps - ds, Q + (long)t * (ps - ds), ps - ds, cmain, cnt, 0, 1);
             acc += M.gfull[u1 + t][u2] * av[t];
           }
           u1 += nu;
@@ -912,7 +992,8 @@ RP_HD void unstru_gaps(Ctx& c, int side, int tid, int T) {
   }
 }
 // U4a: suffix sums over b for each a ; U4b: prefix sums over a for each b
-RP_HD void unstru_dom_rows(Ctx& c, int tid, int T) {
+template <class C>
+RP_HD void unstru_dom_rows(C& c, int tid, int T) {
   const int n = c.n;
   for (int a = 1 + tid; a <= n; a += T) {
     double s = 0.;
@@ -922,7 +1003,8 @@ RP_HD void unstru_dom_rows(Ctx& c, int tid, int T) {
     }
   }
 }
-RP_HD void unstru_dom_cols(Ctx& c, int tid, int T) {
+template <class C>
+RP_HD void unstru_dom_cols(C& c, int tid, int T) {
   const int n = c.n;
   for (int b = 2 + tid; b <= n; b += T) {
     double s = 0.;
@@ -935,22 +1017,20 @@ RP_HD void unstru_dom_cols(Ctx& c, int tid, int T) {
 // U5: RR(p,j) = sum_{o>=j+2} Mc(p,o) QM2(j+1,o-1)
 //     LL(i,o) = sum_{p<=i-2} Mc(p,o) QM2(p+1,i-1)
 //     XX(i,o) = sum_{p<=i-2} Mc(p,o) qm (p+1,i-1)
-RP_HD void unstru_ml_tables(Ctx& c, int tid, int T) {
+template <class C>
+RP_HD void unstru_ml_tables(C& c, int tid, int T) {
   const int n = c.n;
   const size_t total = (size_t)n * c.ld;
-  const double* MC = tabp(c, T_MC);
-  const double* QM2 = tabp(c, T_QM2);
-  const double* QM = tabp(c, T_QM);
   for (size_t x = tid; x < total; x += T) {
     const int e = (int)(x / c.ld), i = (int)(x % c.ld);
     if (i < 1 || i + e > n) continue;
     const int o = i + e;  // cell (i,o); also (p,j) for RR
     double r = 0., l2 = 0., l1 = 0.;
-    for (int b = 2 * TURN + 3; b <= n - o - 2; b++) r += MC[(size_t)(e + 2 + b) * c.ld + i] * QM2[(size_t)b * c.ld + o + 1];
+    for (int b = 2 * TURN + 3; b <= n - o - 2; b++) r += TB(c, T_MC, e + 2 + b, i) * TB(c, T_QM2, b, o + 1);
     for (int cc = TURN + 1; cc <= i - 3; cc++) {
-      const double m = MC[(size_t)(e + 2 + cc) * c.ld + i - 2 - cc];
-      l2 += m * QM2[(size_t)cc * c.ld + i - 1 - cc];
-      l1 += m * QM[(size_t)cc * c.ld + i - 1 - cc];
+      const double m = TB(c, T_MC, e + 2 + cc, i - 2 - cc);
+      l2 += m * TB(c, T_QM2, cc, i - 1 - cc);
+      l1 += m * TB(c, T_QM, cc, i - 1 - cc);
     }
     TB(c, T_RR, e, i) = r;
     TB(c, T_LL, e, i) = l2;
@@ -958,25 +1038,24 @@ RP_HD void unstru_ml_tables(Ctx& c, int tid, int T) {
   }
 }
 // U6: assemble; writes fp32 in the reference layout up[(i-1)*max_w + d]
-RP_HD void unstru_windows(Ctx& c, float* up, int tid, int T) {
+template <class C>
+RP_HD void unstru_windows(C& c, float* up, int tid, int T) {
   const int n = c.n, w = c.max_w;
-  const double* scale = vecp(c, V_SCALE);
-  const double* mlb = vecp(c, V_MLB);
   for (int x = tid; x < n * w; x += T) {
     const int i = x / w + 1, dd = x % w, j = i + dd;
     double v = 0.;
     if (j <= n) {
       const double q5 = i > 1 ? TB(c, T_Q, i - 2, 1) : 1.0;
       const double q3 = j < n ? TB(c, T_Q, n - j - 1, j + 1) : 1.0;
-      v = q5 * scale[dd + 1] * q3 * c.invZ;
+      v = q5 * VEC(c, V_SCALE, dd + 1) * q3 * c.invZ;
       if (i > 1 && j < n) {
         v += TB(c, T_DG, j - i + 2, i - 1);
         double m1 = 0., m2 = 0., m3 = 0.;
-        for (int p = 1; p < i; p++) m1 += mlb[j - p] * TB(c, T_RR, j - p, p);
-        for (int o = j + 1; o <= n; o++) m2 += mlb[o - i] * TB(c, T_LL, o - i, i);
+        for (int p = 1; p < i; p++) m1 += VEC(c, V_MLB, j - p) * TB(c, T_RR, j - p, p);
+        for (int o = j + 1; o <= n; o++) m2 += VEC(c, V_MLB, o - i) * TB(c, T_LL, o - i, i);
         for (int o = j + 2 + TURN + 1; o <= n; o++) m3 += TB(c, T_QM, o - j - 2, j + 1) * TB(c, T_XX, o - i, i);
         // Mc carries no scale factor for the closing pair's two bases: apply it here
-        v += (m1 + m2 + m3 * mlb[dd + 1]) * scale[2];
+        v += (m1 + m2 + m3 * VEC(c, V_MLB, dd + 1)) * VEC(c, V_SCALE, 2);
       }
     }
     up[x] = (float)v;
@@ -987,12 +1066,14 @@ RP_HD void unstru_windows(Ctx& c, float* up, int tid, int T) {
 // outputs in the reference's layouts
 // ---------------------------------------------------------------------------
 // bp[offset[i]+j] = (float) pr(i,j), offset[i] = i*(2L+1-i)/2   (src/ractip.cpp:314-317,365-367)
-RP_HD void write_bp(const Ctx& c, float* bp, int tid, int T) {
+template <class C>
+RP_HD void write_bp(const C& c, float* bp, int tid, int T) {
   const int L = c.n;
   const size_t total = (size_t)(L + 1) * (L + 2) / 2;
   for (size_t x = tid; x < total; x += T) bp[x] = 0.f;
 }
-RP_HD void write_bp2(const Ctx& c, float* bp, int tid, int T) {
+template <class C>
+RP_HD void write_bp2(const C& c, float* bp, int tid, int T) {
   const int L = c.n;
   const size_t total = (size_t)L * c.ld;
   for (size_t x = tid; x < total; x += T) {
@@ -1003,7 +1084,8 @@ RP_HD void write_bp2(const Ctx& c, float* bp, int tid, int T) {
   }
 }
 // hp[i][j-cp+1] = p if i<cp<=j and p>th_hy (float compare)   (src/ractip.cpp:404-405,447-453)
-RP_HD void write_hp(const Ctx& c, float* hp, int n1, int n2, float th_hy, int tid, int T) {
+template <class C>
+RP_HD void write_hp(const C& c, float* hp, int n1, int n2, float th_hy, int tid, int T) {
   const int cp = c.cp;
   const int total = (n1 + 1) * (n2 + 1);
   for (int x = tid; x < total; x += T) {

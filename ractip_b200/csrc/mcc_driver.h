@@ -1,7 +1,11 @@
-// mcc_driver.h -- the phase schedule of one problem, written once against an
-// "executor" that runs a per-thread phase function on every thread of the CTA
-// and then synchronises them.  kernels.cu instantiates it with a CTA executor
+// mcc_driver.h -- the phase schedules, written once against an "executor" that
+// runs a per-thread phase function on every thread of the CTA and then
+// synchronises them.  kernels.cu instantiates them with a CTA executor
 // (threadIdx.x + __syncthreads); tests/emul with a serial one.
+//
+//   solve_mcc       one problem per CTA, work of a cell sliced over threads (any lengths)
+//   solve_lockstep  G same-shape problems per CTA, lane = problem, a thread does whole
+//                   cells of its own problem; one barrier per anti-diagonal
 #ifndef RP_MCC_DRIVER_H
 #define RP_MCC_DRIVER_H
 
@@ -9,18 +13,66 @@
 
 namespace rp {
 
-// sh: CTA-shared scratch (see Shared).  dense: base of the dense
-// float output.  logz: 3 doubles per pair (s1, s2, s1&s2) or nullptr.
+enum {
+  PH_STAGE = 0, PH_PROLOGUE, PH_PROLOGUE2, PH_INSIDE_A, PH_INSIDE_B, PH_NICK1, PH_NICK2, PH_OUTSIDE_A, PH_OUTSIDE_B,
+  PH_WRITE_BP, PH_UN_HAIRPIN, PH_UN_GAPS0, PH_UN_GAPS1, PH_UN_DOMROWS, PH_UN_DOMCOLS, PH_UN_MLTAB, PH_UN_WINDOWS,
+  PH_WRITE_HP, PH_LOGZ, PH_COUNT
+};
+
+// outputs of finished problems; probs[g] is lane g's problem (G = 1 in the general kernel)
+template <class Exec, class Get>
+RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* dense) {
+  const int nct = ex.nthreads() / G;
+  if (probs[0].kind == KIND_LINEAR) {
+    ex.phase(PH_WRITE_BP, [&](int tid) {
+      const Problem& p = probs[tid % G];
+      if (p.out_bp >= 0) write_bp(get(tid % G), dense + p.out_bp, tid / G, nct);
+    });
+    ex.phase(PH_WRITE_BP, [&](int tid) {
+      const Problem& p = probs[tid % G];
+      if (p.out_bp >= 0) write_bp2(get(tid % G), dense + p.out_bp, tid / G, nct);
+    });
+    if (probs[0].max_w > 0) {
+      ex.phase(PH_UN_HAIRPIN, [&](int tid) { unstru_hairpin(get(tid % G), tid / G, nct); });
+      ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(get(tid % G), 0, tid / G, nct); });
+      ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(get(tid % G), 1, tid / G, nct); });
+      ex.phase(PH_UN_DOMROWS, [&](int tid) { unstru_dom_rows(get(tid % G), tid / G, nct); });
+      ex.phase(PH_UN_DOMCOLS, [&](int tid) { unstru_dom_cols(get(tid % G), tid / G, nct); });
+      ex.phase(PH_UN_MLTAB, [&](int tid) { unstru_ml_tables(get(tid % G), tid / G, nct); });
+      ex.phase(PH_UN_WINDOWS, [&](int tid) {
+        const Problem& p = probs[tid % G];
+        if (p.out_up >= 0) unstru_windows(get(tid % G), dense + p.out_up, tid / G, nct);
+      });
+    }
+  } else if (probs[0].kind == KIND_COFOLD) {
+    ex.phase(PH_WRITE_HP, [&](int tid) {
+      const Problem& p = probs[tid % G];
+      if (p.out_hp >= 0) write_hp(get(tid % G), dense + p.out_hp, p.n1, p.n2, p.th_hy, tid / G, nct);
+    });
+  }
+}
+
+// ---------------------------------------------------------------------------
+// general kernel: one problem, sliced cells.  dense: base of the dense float
+// output.  logz: 3 doubles per pair (s1, s2, s1&s2) or nullptr.
+// ---------------------------------------------------------------------------
 template <class Exec>
 RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* logz, const Shared& sh) {
   const int T = sh.T;
   const int n = c.n;
   if (n + 2 <= RP_SMEM_SEQ) {
-    ex.phase(0, [&](int tid) { stage_sequence(c, sh, tid); });
+    const uint8_t* gS = c.S;
+    ex.phase(PH_STAGE, [&](int tid) {
+      for (int x = tid; x <= n + 1; x += T) sh.S[x] = gS[x];
+    });
     c.S = sh.S;
   }
-  ex.phase(1, [&](int tid) { prologue(c, sh, tid); });
-  ex.phase(2, [&](int tid) { prologue2(c, sh, tid); });
+  ex.phase(PH_PROLOGUE, [&](int tid) {
+    load_shared_model(*c.M, sh, tid);
+    prologue_vectors(c, tid, T);
+    prologue_lists(c, tid, T);
+  });
+  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, tid, T); });
 
   // ---- inside: anti-diagonal wavefront, shortest spans first
   for (int d = TURN + 1; d <= n - 1; d++) {
@@ -28,13 +80,13 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
     const int chunk = make_split(cells, T).Cp;
     for (int i0 = 1; i0 <= cells; i0 += chunk) {
       const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
-      ex.phase(3, [&](int tid) { inside_A(c, sh, d, i0, C, tid); });
-      ex.phase(4, [&](int tid) { inside_B(c, sh, d, i0, C, tid); });
+      ex.phase(PH_INSIDE_A, [&](int tid) { inside_A(c, sh, d, i0, C, tid); });
+      ex.phase(PH_INSIDE_B, [&](int tid) { inside_B(c, sh, d, i0, C, tid); });
     }
   }
   inside_end(c);
   if (logz) {
-    ex.phase(18, [&](int tid) {
+    ex.phase(PH_LOGZ, [&](int tid) {
       if (tid == 0) logz[(size_t)p.pair * 3 + p.which] = log(TB(c, T_Q, n - 1, 1)) + n * log(c.M->pf_scale);
     });
   }
@@ -42,41 +94,62 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
   // ---- outside: longest spans first
   for (int d = n - 1; d >= TURN + 1; d--) {
     if (c.cp > 0) {
-      ex.phase(5, [&](int tid) { outside_nick1(c, sh, d, tid); });
-      ex.phase(6, [&](int tid) { outside_nick2(c, sh, d, tid); });
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, sh.red, 1, 32, d, tid, T); });
+      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
     }
     const int cells = n - d;
     const int chunk = make_split(cells, T).Cp;
     for (int i0 = 1; i0 <= cells; i0 += chunk) {
       const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
-      ex.phase(7, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
-      ex.phase(8, [&](int tid) { outside_B(c, sh, d, i0, C, tid); });
+      ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
+      ex.phase(PH_OUTSIDE_B, [&](int tid) { outside_B(c, sh, d, i0, C, tid); });
     }
   }
+  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense);
+}
 
-  // ---- outputs
-  if (p.kind == KIND_LINEAR) {
-    if (p.out_bp >= 0) {
-      float* bp = dense + p.out_bp;
-      ex.phase(9, [&](int tid) { write_bp(c, bp, tid, T); });
-      ex.phase(9, [&](int tid) { write_bp2(c, bp, tid, T); });
-    }
-    if (p.out_up >= 0 && p.max_w > 0) {
-      float* up = dense + p.out_up;
-      ex.phase(10, [&](int tid) { unstru_hairpin(c, tid, T); });
-      ex.phase(11, [&](int tid) { unstru_gaps(c, 0, tid, T); });
-      ex.phase(12, [&](int tid) { unstru_gaps(c, 1, tid, T); });
-      ex.phase(13, [&](int tid) { unstru_dom_rows(c, tid, T); });
-      ex.phase(14, [&](int tid) { unstru_dom_cols(c, tid, T); });
-      ex.phase(15, [&](int tid) { unstru_ml_tables(c, tid, T); });
-      ex.phase(16, [&](int tid) { unstru_windows(c, up, tid, T); });
-    }
-  } else if (p.kind == KIND_COFOLD) {
-    if (p.out_hp >= 0) {
-      float* hp = dense + p.out_hp;
-      ex.phase(17, [&](int tid) { write_hp(c, hp, p.n1, p.n2, p.th_hy, tid, T); });
-    }
+// ---------------------------------------------------------------------------
+// lockstep kernel: G problems of identical (kind, n, cp, max_w) per CTA.
+// Thread tid serves lane g = tid % G with cell-thread index ct = tid / G.
+// `get(g)` returns the lane's context (the calling thread's own on the GPU).
+// probs[g].pair < 0 marks a padding lane (computed, never written out).
+// gS: the group's interleaved sequences, S[i*G+g], i = 0..n+1.
+// ---------------------------------------------------------------------------
+template <int G, class Exec, class Get>
+RP_HD void solve_lockstep(Exec& ex, Get get, const Problem* probs, const uint8_t* gS, float* dense, double* logz,
+                          const Shared& sh) {
+  const int T = sh.T, nct = T / G;
+  const int n = probs[0].n, cp = probs[0].cp;
+  if ((size_t)(n + 2) * G <= RP_SMEM_SEQ) {
+    ex.phase(PH_STAGE, [&](int tid) {
+      for (int x = tid; x < (n + 2) * G; x += T) sh.S[x] = gS[x];
+    });
+    ex.phase(PH_STAGE, [&](int tid) { get(tid % G).S = sh.S + (tid % G); });
   }
+  ex.phase(PH_PROLOGUE, [&](int tid) {
+    load_shared_model(*get(tid % G).M, sh, tid);
+    prologue_vectors(get(tid % G), tid / G, nct);
+  });
+  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(get(tid % G), tid / G, nct); });
+
+  for (int d = TURN + 1; d <= n - 1; d++)
+    ex.phase(PH_INSIDE_A, [&](int tid) { inside_cells(get(tid % G), sh, d, tid / G, nct); });
+  ex.phase(PH_LOGZ, [&](int tid) {
+    auto& c = get(tid % G);
+    inside_end(c);
+    const Problem& p = probs[tid % G];
+    if (logz && tid / G == 0 && p.pair >= 0)
+      logz[(size_t)p.pair * 3 + p.which] = log(TB(c, T_Q, n - 1, 1)) + n * log(c.M->pf_scale);
+  });
+
+  for (int d = n - 1; d >= TURN + 1; d--) {
+    if (cp > 0) {
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(get(tid % G), sh.red + (tid % G), G, 1, d, tid / G, nct); });
+      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(get(tid % G), sh.red + (tid % G), G, 1, d, tid / G, nct); });
+    }
+    ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_cells(get(tid % G), sh, d, tid / G, nct); });
+  }
+  emit_outputs(ex, get, probs, G, dense);
 }
 
 }  // namespace rp

@@ -1,6 +1,6 @@
-// emul.cpp -- TEST INFRASTRUCTURE.  Runs the kernel's per-thread phase
+// emul.cpp -- TEST INFRASTRUCTURE.  Runs the kernels' per-thread phase
 // functions (ractip_b200/csrc/mcc_core.h, mcc_driver.h) on the host, one
-// emulated thread after another, so that the CUDA kernel's logic can be checked
+// emulated thread after another, so that the CUDA kernels' logic can be checked
 // against the oracle on a CPU-only box.  Never loaded by the product.
 #include <cstdlib>
 #include <cstring>
@@ -19,12 +19,20 @@ struct SerialExec {
     for (int t = 0; t < T; t++) f(t);
   }
 };
+
+rp::DevModel g_model;  // large
+
+void layout(int n, int max_w, int n1, int n2, size_t& nbp, size_t& nup, size_t& nhp) {
+  nbp = (size_t)(n + 1) * (n + 2) / 2;
+  nup = (size_t)n * (max_w > 0 ? max_w : 0);
+  nhp = (size_t)(n1 + 1) * (n2 + 1);
+}
 }  // namespace
 
+// general kernel: one problem
 extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
                             float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
-  static rp::DevModel M;  // large
-  int rc = rp::build_dev_model(*m, &M);
+  int rc = rp::build_dev_model(*m, &g_model);
   if (rc) return rc;
   std::vector<uint8_t> S(n + 16, 0);
   for (int i = 1; i <= n; i++) S[i] = rp::encode_base(seq[i - 1]);
@@ -32,8 +40,8 @@ extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, i
   std::memset(&p, 0, sizeof p);
   p.seq_off = 0; p.n = n; p.cp = cp; p.kind = kind; p.pair = 0; p.which = 0; p.max_w = max_w;
   p.n1 = n1; p.n2 = n2; p.th_hy = th_hy;
-  // lay the three outputs out in one float buffer
-  size_t nbp = (size_t)(n + 1) * (n + 2) / 2, nup = (size_t)n * (max_w > 0 ? max_w : 0), nhp = (size_t)(n1 + 1) * (n2 + 1);
+  size_t nbp, nup, nhp;
+  layout(n, max_w, n1, n2, nbp, nup, nhp);
   std::vector<float> dense(nbp + nup + nhp + 8, 0.f);
   p.out_bp = (kind == rp::KIND_LINEAR && bp) ? 0 : -1;
   p.out_up = (kind == rp::KIND_LINEAR && up && max_w > 0) ? (long long)nbp : -1;
@@ -44,7 +52,7 @@ extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, i
   rp::carve_shared(sh, smem.data(), T);
   double lz[3] = {0, 0, 0};
   rp::Ctx c;
-  rp::bind_ctx(c, &M, S.data(), p, ws.data());
+  rp::bind_ctx(c, &g_model, S.data(), p, ws.data());
   SerialExec ex{T};
   rp::solve_mcc(ex, c, p, dense.data(), lz, sh);
   if (p.out_bp >= 0) std::memcpy(bp, dense.data(), nbp * sizeof(float));
@@ -52,4 +60,56 @@ extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, i
   if (p.out_hp >= 0) std::memcpy(hp, dense.data() + nbp + nup, nhp * sizeof(float));
   if (logz) *logz = lz[0];
   return 0;
+}
+
+// lockstep kernel: `count` (<= G) same-shape problems; seqs = count*n letters, outputs count blocks
+template <int G>
+static int lockstep_run(const char* seqs, int count, int n, int cp, int kind, int max_w, int n1, int n2, float th_hy,
+                        int T, float* bp, float* up, float* hp, double* logz) {
+  size_t nbp, nup, nhp;
+  layout(n, max_w, n1, n2, nbp, nup, nhp);
+  const size_t per = nbp + nup + nhp;
+  std::vector<float> dense(per * G + 8, 0.f);
+  std::vector<uint8_t> S((size_t)(n + 2) * G + 16, 0);
+  std::vector<rp::Problem> probs(G);
+  for (int g = 0; g < G; g++) {
+    const int src = g < count ? g : count - 1;
+    for (int i = 1; i <= n; i++) S[(size_t)i * G + g] = rp::encode_base(seqs[(size_t)src * n + i - 1]);
+    rp::Problem& p = probs[g];
+    std::memset(&p, 0, sizeof p);
+    p.n = n; p.cp = cp; p.kind = kind; p.pair = g < count ? g : -1; p.which = 0; p.max_w = max_w;
+    p.n1 = n1; p.n2 = n2; p.th_hy = th_hy;
+    const bool live = g < count;
+    p.out_bp = (live && kind == rp::KIND_LINEAR && bp) ? (long long)(per * g) : -1;
+    p.out_up = (live && kind == rp::KIND_LINEAR && up && max_w > 0) ? (long long)(per * g + nbp) : -1;
+    p.out_hp = (live && kind == rp::KIND_COFOLD && hp) ? (long long)(per * g + nbp + nup) : -1;
+  }
+  std::vector<double> ws(rp::slot_doubles(n) * G, 1e300);
+  std::vector<double> smem(rp::shared_bytes(T) / sizeof(double) + 2, 0.0);
+  rp::Shared sh;
+  rp::carve_shared(sh, smem.data(), T);
+  std::vector<double> lz((size_t)G * 3, 0.0);
+  std::vector<rp::LCtx<G> > cs(G);
+  for (int g = 0; g < G; g++) rp::bind_lctx<G>(cs[g], &g_model, S.data(), probs[g], ws.data(), g);
+  SerialExec ex{T};
+  rp::solve_lockstep<G>(ex, [&](int g) -> rp::LCtx<G>& { return cs[g]; }, probs.data(), S.data(), dense.data(), lz.data(), sh);
+  for (int g = 0; g < count; g++) {
+    if (probs[g].out_bp >= 0) std::memcpy(bp + nbp * g, dense.data() + per * g, nbp * sizeof(float));
+    if (probs[g].out_up >= 0) std::memcpy(up + nup * g, dense.data() + per * g + nbp, nup * sizeof(float));
+    if (probs[g].out_hp >= 0) std::memcpy(hp + nhp * g, dense.data() + per * g + nbp + nup, nhp * sizeof(float));
+    if (logz) logz[g] = lz[(size_t)g * 3];
+  }
+  return 0;
+}
+
+extern "C" int emul_lockstep(const rp_model* m, int G, const char* seqs, int count, int n, int cp, int kind, int max_w,
+                             int n1, int n2, float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
+  int rc = rp::build_dev_model(*m, &g_model);
+  if (rc) return rc;
+  if (count < 1 || count > G || T % G) return 1;
+  switch (G) {
+    case 8: return lockstep_run<8>(seqs, count, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
+    case 4: return lockstep_run<4>(seqs, count, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
+    default: return 1;
+  }
 }
