@@ -73,6 +73,7 @@ struct rp_batch {
   int* d_order = nullptr;
   // lockstep groups (same-shape problems, RP_LS_G per CTA)
   std::vector<rp::GroupDev> groups;
+  int grid_cached = -1, ls_grid_cached = -1;  // launch shapes, fixed at the first run (cudaMemGetInfo is slow)
   int n_general = 0;          // problems left to the general kernel (first n_general entries of order)
   int ls_maxn = 0;
   rp::GroupDev* d_groups = nullptr;
@@ -539,12 +540,13 @@ int rp_batch_run(rp_batch* b) {
   ctx->timing.alg_flops = b->alg_flops;
   if (nprob == 0) { ctx->timing_pending = false; return RP_OK; }
   const size_t slot_bytes = b->slot_doubles * sizeof(double);
-  const int grid = b->n_general > 0 ? grid_for(ctx, b->n_general, std::max<size_t>(slot_bytes, 8)) : 0;
+  if (b->grid_cached < 0) b->grid_cached = b->n_general > 0 ? grid_for(ctx, b->n_general, std::max<size_t>(slot_bytes, 8)) : 0;
+  const int grid = b->grid_cached;
   // lockstep: one CTA slot holds RP_LS_G problem workspaces
   const int ngroups = (int)b->groups.size();
   const size_t ls_slot_doubles = ngroups ? rp::slot_doubles(b->ls_maxn) * RP_LS_G : 0;
-  int ls_grid = 0;
-  if (ngroups) {
+  int ls_grid = b->ls_grid_cached < 0 ? 0 : b->ls_grid_cached;
+  if (ngroups && b->ls_grid_cached < 0) {
     ls_grid = std::min(ngroups, ctx->sm_count * std::max(1, ctx->ls_ctas_per_sm));
     if (const char* e = std::getenv("RP_GRID")) {
       int v = std::atoi(e);
@@ -556,6 +558,7 @@ int rp_batch_run(rp_batch* b) {
       while (ls_grid > 1 && (size_t)ls_grid * ls_slot_doubles * sizeof(double) > budget) ls_grid--;
     }
   }
+  b->ls_grid_cached = ls_grid;
   // the two kernels run one after the other on the stream and share the workspace
   int rc = ensure_workspace(ctx, std::max((size_t)grid * slot_bytes, (size_t)ls_grid * ls_slot_doubles * sizeof(double)));
   if (rc) return rc;
