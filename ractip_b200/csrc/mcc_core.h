@@ -66,6 +66,7 @@ enum {
   T_Q = 0, T_QQ, T_QM, T_QM1, T_QM2, T_QB, T_QBI, T_QB1N, T_QBAU,
   T_OUT, T_OUTI, T_OUT1N, T_OUTAU, T_MC, T_PR, T_PRML, T_PMLB, T_PL,
   T_DG, T_RR, T_LL, T_XX,
+  T_QS, T_PRB, T_MLB,   // band-bulk split sums of the general kernel (see inside_band_A / outside_band_A)
   T_LIST,   // not doubles: per-diagonal lists of pairable cells (uint16), general kernel only
   T_COUNT
 };
@@ -137,11 +138,16 @@ RP_HD void bind_lctx(LCtx<G>& c, const DevModel* M, const uint8_t* S_group, cons
 RP_HD uint16_t* listp(const Ctx& c) { return reinterpret_cast<uint16_t*>(c.ptr(T_LIST, 0, 0)); }
 RP_HD uint16_t* posp(const Ctx& c) { return reinterpret_cast<uint16_t*>(c.ptr(T_LIST, 0, 0)) + c.te * 2; }
 
+// Width of a band of diagonals whose O(n) split sums depend only on diagonals finished before the
+// band starts: qm, qm1 and qq vanish on diagonals <= TURN, so the terms of diagonal d reach back at
+// least TURN+2 diagonals.
+constexpr int BAND = TURN + 2;
+
 // CTA-shared scratch (CUDA shared memory; a heap block in the host emulation)
 constexpr int RP_SMEM_SEQ = 4096;  // sequence bytes staged in shared memory (n+2 general, (n+2)*G lockstep)
 struct Shared {
   int T;
-  double* part;     // [3][T] partial sums of the current phase (general kernel)
+  double* part;     // [2*BAND][T] partial sums of the current phase (general kernel)
   double* grow;     // [MAXLOOP+1][GROW_LD] run weights of the factorised interior loops (DevModel::grow)
   double* ghead_b;  // [GROW_LD]
   double* ghead_1;  // [GROW_LD]
@@ -149,12 +155,12 @@ struct Shared {
   uint8_t* S;       // [RP_SMEM_SEQ + 8] staged sequence(s)
 };
 RP_HD size_t shared_bytes(int T) {
-  return sizeof(double) * (3 * (size_t)T + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
+  return sizeof(double) * (2 * BAND * (size_t)T + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
 }
 RP_HD void carve_shared(Shared& sh, void* base, int T) {
   sh.T = T;
   double* p = static_cast<double*>(base);
-  sh.part = p; p += 3 * (size_t)T;
+  sh.part = p; p += 2 * BAND * (size_t)T;
   sh.grow = p; p += (MAXLOOP + 1) * GROW_LD;
   sh.ghead_b = p; p += GROW_LD;
   sh.ghead_1 = p; p += GROW_LD;
@@ -580,37 +586,106 @@ RP_HD void inside_finish(C& c, int d, int i, int type, double sI, double sM, dou
 template <class C>
 RP_HD void inside_end(C& c) { c.invZ = 1.0 / TB(c, T_Q, c.n - 1, 1); }
 
-// general kernel, phase A: sliced work items, partials to sh.part [3][T] (interior, QM2, q-split)
-RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+// General kernel.  The two O(n) split sums of the inside pass are computed a BAND of diagonals at
+// a time (inside_band_A/B): for row i the cells (i, i+d0+e), e < BAND, share the operand qm[a][i]
+// (resp. q[a][i]), so one thread keeps BAND accumulators and loads 1+BAND values per BAND FMAs
+// instead of 2 per FMA, and every operand lies on a diagonal < d0, already final.
+//   M[e] = QM2(i,i+d0+e) = sum_{a=TURN+1}^{d0+e-TURN-2} qm[a][i] * qm1[d0+e-1-a][i+1+a]   (complete)
+//   Q[e] = sum_{a=e}^{d0+e-TURN-2} q[a][i] * qq[d0+e-1-a][i+1+a]   (the e terms a<e touch qq on
+//          diagonals >= d0 and are added when the cell is finished)
+// partials: sh.part[(w*BAND+e)*T + tid], w = 0 (M), 1 (Q)
+RP_HD int band_start_inside(int d) { return TURN + 1 + (d - TURN - 1) / BAND * BAND; }
+RP_HD void inside_band_A(const Ctx& c, const Shared& sh, int d0, int i0, int C, int tid) {
   const int T = sh.T;
-  if (d - (TURN + 1) >= 2) {
-    const ISplit is = make_isplit(c, d, i0, C, T);
-    const int r = tid % is.cntp, sl = tid / is.cntp;
-    if (sl < is.SI && r < is.cnt) {
-      const int i = listp(c)[(size_t)d * c.ld + is.lo + r];
-      sh.part[tid] = inside_interior(c, sh, d, i, pair_type(base(c, i), base(c, i + d)), sl, is.SI);
+  const Split sp = make_split(C, T);
+  const int cell = tid % sp.Cp, slice = tid / sp.Cp, S = sp.S;
+  if (slice >= S || cell >= C) return;
+  const int i = i0 + cell, ds = c.dstep();
+  double m[BAND], q[BAND];
+#pragma unroll
+  for (int e = 0; e < BAND; e++) m[e] = q[e] = 0.;
+  if (!(c.dbg & 2)) {
+    const int amax = d0 - 1;                    // largest a any diagonal of the band needs
+    const int lim = d0 - TURN - 2;              // term a belongs to diagonal d0+e iff a <= lim + e
+    const int askip = c.cp > 0 ? c.cp - 1 - i : -1;  // split k = i+1+a on the nick (M only)
+    const long es = ds;                         // per e: one diagonal up, same position
+    // head of the q-split, a <= TURN: only e <= a is not "recent"
+    for (int a = slice; a <= TURN && a <= amax; a += S) {
+      const double A = TB(c, T_Q, a, i);
+      const double* B = c.ptr(T_QQ, d0 - 1 - a, i + 1 + a);
+      const int emin = a - lim;
+#pragma unroll
+      for (int e = 0; e < BAND; e++)
+        if (e >= emin && e <= a) q[e] += A * B[e * es];
+    }
+    // main part, TURN < a <= lim: every diagonal of the band takes the term; both sums share the walk
+    int a = TURN + 1 + slice;
+    for (; a <= lim; a += S) {
+      const double Am = (a == askip) ? 0. : TB(c, T_QM, a, i);
+      const double Aq = TB(c, T_Q, a, i);
+      const double* Bm = c.ptr(T_QM1, d0 - 1 - a, i + 1 + a);
+      const double* Bq = c.ptr(T_QQ, d0 - 1 - a, i + 1 + a);
+      double bm[BAND], bq[BAND];
+#pragma unroll
+      for (int e = 0; e < BAND; e++) { bm[e] = Bm[e * es]; bq[e] = Bq[e * es]; }
+#pragma unroll
+      for (int e = 0; e < BAND; e++) { m[e] += Am * bm[e]; q[e] += Aq * bq[e]; }
+    }
+    // tail, lim < a <= amax: the term only reaches the later diagonals of the band
+    for (; a <= amax; a += S) {
+      const double Am = (a == askip) ? 0. : TB(c, T_QM, a, i);
+      const double Aq = TB(c, T_Q, a, i);
+      const double* Bm = c.ptr(T_QM1, d0 - 1 - a, i + 1 + a);
+      const double* Bq = c.ptr(T_QQ, d0 - 1 - a, i + 1 + a);
+      const int emin = a - lim;
+#pragma unroll
+      for (int e = 0; e < BAND; e++)
+        if (e >= emin) { m[e] += Am * Bm[e * es]; q[e] += Aq * Bq[e * es]; }
     }
   }
-  const Split sp = make_split(C, T);
-  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
-  if (slice < sp.S && cell < C) {
-    double accM, accQ;
-    inside_splits(c, d, i0 + cell, slice, sp.S, accM, accQ);
-    sh.part[T + tid] = accM;
-    sh.part[2 * T + tid] = accQ;
+#pragma unroll
+  for (int e = 0; e < BAND; e++) {
+    sh.part[(size_t)e * T + tid] = m[e];
+    sh.part[(size_t)(BAND + e) * T + tid] = q[e];
   }
 }
-// general kernel, phase B: one thread per cell
-RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+RP_HD void inside_band_B(Ctx& c, const Shared& sh, int d0, int i0, int C, int tid) {
   const int T = sh.T;
   const Split sp = make_split(C, T);
-  if (tid >= sp.Cp || tid >= C) return;
-  const int i = i0 + tid;
-  double sI = 0., sM = 0., sQ = 0.;
-  for (int s = 0; s < sp.S; s++) {
-    sM += sh.part[T + s * sp.Cp + tid];
-    sQ += sh.part[2 * T + s * sp.Cp + tid];
+  for (int x = tid; x < BAND * C; x += T) {
+    const int e = x / C, cell = x % C, i = i0 + cell;
+    if (i + d0 + e > c.n) continue;
+    double m = 0., q = 0.;
+    for (int s = 0; s < sp.S; s++) {
+      m += sh.part[(size_t)e * T + s * sp.Cp + cell];
+      q += sh.part[(size_t)(BAND + e) * T + s * sp.Cp + cell];
+    }
+    TB(c, T_QM2, d0 + e, i) = m;
+    TB(c, T_QS, d0 + e, i) = q;
   }
+}
+// per diagonal, phase A: interior-loop work items (pairable cell, slice), partials to sh.part[tid]
+RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if (d - (TURN + 1) < 2) return;
+  const ISplit is = make_isplit(c, d, i0, C, T);
+  const int r = tid % is.cntp, sl = tid / is.cntp;
+  if (sl < is.SI && r < is.cnt) {
+    const int i = listp(c)[(size_t)d * c.ld + is.lo + r];
+    sh.part[tid] = inside_interior(c, sh, d, i, pair_type(base(c, i), base(c, i + d)), sl, is.SI);
+  }
+}
+// per diagonal, phase B: one thread per cell
+RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if (tid >= C) return;
+  const int i = i0 + tid;
+  double sI = 0.;
+  const double sM = TB(c, T_QM2, d, i);
+  double sQ = TB(c, T_QS, d, i);
+  // the terms of the q-split that the band pass could not see yet: a < e, qq on diagonals >= d0
+  const int e = d - band_start_inside(d);
+  for (int a = 0; a < e && a <= d - TURN - 2; a++) sQ += TB(c, T_Q, a, i) * TB(c, T_QQ, d - 1 - a, i + 1 + a);
   const int type = pair_type(base(c, i), base(c, i + d));
   if (type && d - (TURN + 1) >= 2) {
     const ISplit is = make_isplit(c, d, i0, C, T);
@@ -822,38 +897,120 @@ RP_HD void outside_finish(C& c, int d, int k, int type, double sI, double sP, do
   TB(c, T_MC, d, k) = mc;
 }
 
-// general kernel: sh.part [3][T] (interior, PR, ML-left)
-RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+// General kernel, outside pass: the two multiloop sums are computed for a band of diagonals
+// d0, d0-1, ..., d0-BAND+1 at once (all of their operands lie on diagonals > d0+1 or in the inside
+// tables).  Item r serves row k = 1+r for PR and column l = d0-BAND+2+r for ML-left:
+//   PR(k, k+d0-e)   = sum_{j} Mc(k,j) * qm(l+1, j-1),  j = l+2+TURN+1 .. n      share Mc(k,j)   over e
+//   MLL(l-d0+e, l)  = sum_{i} PRML(i,l) * qm(i+1, k-1), i = 1 .. k-3-TURN        share PRML(i,l) over e
+// partials: sh.part[(w*BAND+e)*T + tid], w = 0 (PR), 1 (MLL)
+RP_HD void outside_band_A(const Ctx& c, const Shared& sh, int d0, int r0, int C, int tid) {
   const int T = sh.T;
-  if (c.n - 1 - d >= 2) {
-    const ISplit is = make_isplit(c, d, i0, C, T);
-    const int r = tid % is.cntp, sl = tid / is.cntp;
-    if (sl < is.SI && r < is.cnt) {
-      const int k = listp(c)[(size_t)d * c.ld + is.lo + r];
-      sh.part[tid] = outside_interior(c, sh, d, k, sl, is.SI);
+  const Split sp = make_split(C, T);
+  const int cell = tid % sp.Cp, slice = tid / sp.Cp, S = sp.S;
+  if (slice >= S || cell >= C) return;
+  const int r = r0 + cell, n = c.n, ds = c.dstep(), ps = c.pstep();
+  double pr[BAND], ml[BAND];
+#pragma unroll
+  for (int e = 0; e < BAND; e++) pr[e] = ml[e] = 0.;
+  if (!(c.dbg & 2)) {
+    {  // PR, row k; t = j - (k+d0+TURN+3), valid for diagonal d0-e iff t >= -e
+      const int k = 1 + r;
+      const int tmax = n - k - d0 - (TURN + 3);
+      int ecell = k + d0 - n;  // the cell (k, k+d0-e) exists iff e >= ecell
+      if (ecell < 0) ecell = 0;
+      const long es = ds - ps;  // per e one diagonal up, one cell left
+      int t = -(BAND - 1) + slice;
+      for (; t < 0 && t <= tmax; t += S) {  // head: the term only reaches the lower diagonals of the band
+        const double A = TB(c, T_MC, d0 + TURN + 3 + t, k);
+        const double* B = c.ptr(T_QM, TURN + 1 + t, k + d0 + 1);
+        const int emin = -t > ecell ? -t : ecell;
+#pragma unroll
+        for (int e = 0; e < BAND; e++)
+          if (e >= emin) pr[e] += A * B[e * es];
+      }
+      for (; t <= tmax; t += S) {           // main: every existing cell of the row takes the term
+        const double A = TB(c, T_MC, d0 + TURN + 3 + t, k);
+        const double* B = c.ptr(T_QM, TURN + 1 + t, k + d0 + 1);
+        double bv[BAND];
+#pragma unroll
+        for (int e = 0; e < BAND; e++) bv[e] = B[e * es];
+#pragma unroll
+        for (int e = 0; e < BAND; e++)
+          if (e >= ecell) pr[e] += A * bv[e];
+      }
+    }
+    {  // ML-left, column l; cells (k0+e, l), k0 = l-d0; i <= k0+e-TURN-3
+      const int l = d0 - BAND + 2 + r, k0 = l - d0;
+      if (l <= n) {
+        unsigned need = 0;
+        for (int e = 0; e < BAND; e++) {
+          const int k = k0 + e, d = d0 - e;
+          if (k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) && TB(c, T_QB, d, k) != 0.) need |= 1u << e;
+        }
+        if (need) {
+          const int imax = k0 + (BAND - 1) - TURN - 3, imain = k0 - TURN - 3;
+          int i = 1 + slice;
+          for (; i <= imain; i += S) {       // main: every needed cell of the column takes the term
+            const double A = TB(c, T_PRML, l - i, i);
+            const double* B = c.ptr(T_QM, 0, i + 1) + (long)(k0 - 2 - i) * ds;
+            double bv[BAND];
+#pragma unroll
+            for (int e = 0; e < BAND; e++) bv[e] = ((need >> e) & 1) ? B[(long)e * ds] : 0.;
+#pragma unroll
+            for (int e = 0; e < BAND; e++) ml[e] += A * bv[e];
+          }
+          for (; i <= imax; i += S) {        // tail: only the cells further right (larger k)
+            const double A = TB(c, T_PRML, l - i, i);
+            const double* B = c.ptr(T_QM, 0, i + 1) + (long)(k0 - 2 - i) * ds;  // e = 0 may lie below diagonal 0: not read then
+            const int emin = i - k0 + TURN + 3;
+#pragma unroll
+            for (int e = 0; e < BAND; e++)
+              if (e >= emin && ((need >> e) & 1)) ml[e] += A * B[(long)e * ds];
+          }
+        }
+      }
     }
   }
+#pragma unroll
+  for (int e = 0; e < BAND; e++) {
+    sh.part[(size_t)e * T + tid] = pr[e];
+    sh.part[(size_t)(BAND + e) * T + tid] = ml[e];
+  }
+}
+RP_HD void outside_band_B(Ctx& c, const Shared& sh, int d0, int r0, int C, int tid) {
+  const int T = sh.T, n = c.n;
   const Split sp = make_split(C, T);
-  const int cell = tid % sp.Cp, slice = tid / sp.Cp;
-  if (slice < sp.S && cell < C) {
-    const int k = i0 + cell;
-    const uint16_t* P = posp(c) + (size_t)d * c.ld;
-    double accP, accL;
-    outside_splits(c, d, k, P[k + 1] != P[k], slice, sp.S, accP, accL);
-    sh.part[T + tid] = accP;
-    sh.part[2 * T + tid] = accL;
+  for (int x = tid; x < BAND * C; x += T) {
+    const int e = x / C, cell = x % C, r = r0 + cell, d = d0 - e;
+    if (d < 1) continue;
+    double a = 0., b = 0.;
+    for (int s = 0; s < sp.S; s++) {
+      a += sh.part[(size_t)e * T + s * sp.Cp + cell];
+      b += sh.part[(size_t)(BAND + e) * T + s * sp.Cp + cell];
+    }
+    const int k = 1 + r;                       // PR cell (k, k+d)
+    if (k + d <= n) TB(c, T_PRB, d, k) = a;
+    const int l = d0 - BAND + 2 + r, k2 = l - d;  // MLL cell (l-d, l)
+    if (l <= n && k2 >= 1) TB(c, T_MLB, d, k2) = b;
+  }
+}
+// per diagonal, phase A: interior-loop items, partials to sh.part[tid]
+RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if (c.n - 1 - d < 2) return;
+  const ISplit is = make_isplit(c, d, i0, C, T);
+  const int r = tid % is.cntp, sl = tid / is.cntp;
+  if (sl < is.SI && r < is.cnt) {
+    const int k = listp(c)[(size_t)d * c.ld + is.lo + r];
+    sh.part[tid] = outside_interior(c, sh, d, k, sl, is.SI);
   }
 }
 RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   const int T = sh.T;
-  const Split sp = make_split(C, T);
-  if (tid >= sp.Cp || tid >= C) return;
+  if (tid >= C) return;
   const int k = i0 + tid;
-  double sI = 0., sP = 0., sL = 0.;
-  for (int s = 0; s < sp.S; s++) {
-    sP += sh.part[T + s * sp.Cp + tid];
-    sL += sh.part[2 * T + s * sp.Cp + tid];
-  }
+  double sI = 0.;
+  const double sP = TB(c, T_PRB, d, k), sL = TB(c, T_MLB, d, k);
   const int type = pair_type(base(c, k), base(c, k + d));
   if (type && c.n - 1 - d >= 2 && TB(c, T_QB, d, k) != 0.) {
     const ISplit is = make_isplit(c, d, i0, C, T);

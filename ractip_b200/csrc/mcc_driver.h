@@ -16,7 +16,7 @@ namespace rp {
 enum {
   PH_STAGE = 0, PH_PROLOGUE, PH_PROLOGUE2, PH_INSIDE_A, PH_INSIDE_B, PH_NICK1, PH_NICK2, PH_OUTSIDE_A, PH_OUTSIDE_B,
   PH_WRITE_BP, PH_UN_HAIRPIN, PH_UN_GAPS0, PH_UN_GAPS1, PH_UN_DOMROWS, PH_UN_DOMCOLS, PH_UN_MLTAB, PH_UN_WINDOWS,
-  PH_WRITE_HP, PH_LOGZ, PH_COUNT
+  PH_WRITE_HP, PH_LOGZ, PH_BAND_A, PH_BAND_B, PH_COUNT
 };
 
 // outputs of finished problems; probs[g] is lane g's problem (G = 1 in the general kernel)
@@ -74,10 +74,19 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
   });
   ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, tid, T); });
 
-  // ---- inside: anti-diagonal wavefront, shortest spans first
+  // ---- inside: anti-diagonal wavefront, shortest spans first; split sums one band ahead
   for (int d = TURN + 1; d <= n - 1; d++) {
+    if (d == band_start_inside(d)) {
+      const int rows = n - d;
+      const int chunk = make_split(rows, T).Cp;
+      for (int i0 = 1; i0 <= rows; i0 += chunk) {
+        const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) { inside_band_A(c, sh, d, i0, C, tid); });
+        ex.phase(PH_BAND_B, [&](int tid) { inside_band_B(c, sh, d, i0, C, tid); });
+      }
+    }
     const int cells = n - d;
-    const int chunk = make_split(cells, T).Cp;
+    const int chunk = cells < T ? cells : T;
     for (int i0 = 1; i0 <= cells; i0 += chunk) {
       const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
       ex.phase(PH_INSIDE_A, [&](int tid) { inside_A(c, sh, d, i0, C, tid); });
@@ -97,8 +106,17 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
       ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, sh.red, 1, 32, d, tid, T); });
       ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
     }
+    if ((n - 1 - d) % BAND == 0) {  // a band of diagonals d, d-1, ..., d-BAND+1 starts here
+      const int rows = n - d + BAND - 1;
+      const int chunk = make_split(rows, T).Cp;
+      for (int r0 = 0; r0 < rows; r0 += chunk) {
+        const int C = rows - r0 < chunk ? rows - r0 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) { outside_band_A(c, sh, d, r0, C, tid); });
+        ex.phase(PH_BAND_B, [&](int tid) { outside_band_B(c, sh, d, r0, C, tid); });
+      }
+    }
     const int cells = n - d;
-    const int chunk = make_split(cells, T).Cp;
+    const int chunk = cells < T ? cells : T;
     for (int i0 = 1; i0 <= cells; i0 += chunk) {
       const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
       ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
