@@ -38,6 +38,10 @@ struct rp_ctx {
   // then stream ~600 MB per pair through L2.  RP_LOCKSTEP=1 enables it (kept for the next round:
   // it needs shared-memory staging / register tiling of the interior window to pay off).
   bool lockstep = false;
+  // Band kernel (mcc_band.h): problems whose 32-diagonal ring fits in shared memory.  Class L: 512
+  // threads, one CTA per SM; class S: 256 threads, two CTAs per SM.  RP_BAND=0 disables it (A/B aid).
+  bool band = true;
+  size_t smem_optin = 0;       // max dynamic shared memory per CTA
   int threads = RP_MCC_THREADS;  // CTA width of the wavefront kernel (RP_MCC_THREADS env var narrows it: tuning aid)
   rp::DevModel* d_model = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -74,7 +78,11 @@ struct rp_batch {
   // lockstep groups (same-shape problems, RP_LS_G per CTA)
   std::vector<rp::GroupDev> groups;
   int grid_cached = -1, ls_grid_cached = -1;  // launch shapes, fixed at the first run (cudaMemGetInfo is slow)
-  int n_general = 0;          // problems left to the general kernel (first n_general entries of order)
+  int n_general = 0;          // problems left to the general kernel + duplex (entries of order after the band classes)
+  // band classes: order = [class L | class S | general]
+  int n_band[2] = {0, 0};
+  int band_maxn[2] = {0, 0};
+  int band_grid[2] = {-1, -1};
   int ls_maxn = 0;
   rp::GroupDev* d_groups = nullptr;
   uint8_t* d_gseq = nullptr;
@@ -308,6 +316,8 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (const char* e = std::getenv("RP_BAND")) ctx->band = std::atoi(e) != 0;
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   ctx->stream = ctx->own_stream;
@@ -493,10 +503,32 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   for (size_t k = 0; k < b->probs.size(); k++)
     if (!in_group[k]) b->order.push_back((int)k);
   std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) { return cost(b->probs[x]) > cost(b->probs[y]); });
-  b->n_general = (int)b->order.size();
+  if (ctx->band) {
+    // class of a problem: 0 = L (512 threads, ring needs more than half an SM), 1 = S (256 threads, 2 CTAs/SM), -1 = general
+    const size_t half_sm = (ctx->smem_optin + 1024) / 2 - 1024;
+    auto cls = [&](const Problem& q) {
+      if (q.kind == rp::KIND_DUPLEX) return -1;
+      if (rp::band_shared_bytes(q.n, 256) <= half_sm) return 1;
+      if (rp::band_shared_bytes(q.n, 512) <= ctx->smem_optin) return 0;
+      return -1;
+    };
+    std::vector<int> part[3];
+    for (int k : b->order) {
+      const int c = cls(b->probs[k]);
+      part[c < 0 ? 2 : c].push_back(k);
+      if (c >= 0) b->band_maxn[c] = std::max(b->band_maxn[c], b->probs[k].n);
+    }
+    b->n_band[0] = (int)part[0].size();
+    b->n_band[1] = (int)part[1].size();
+    b->order.clear();
+    for (auto& v : part) b->order.insert(b->order.end(), v.begin(), v.end());
+  }
+  b->n_general = (int)b->order.size() - b->n_band[0] - b->n_band[1];
   int gen_maxn = 0, gen_mcc = 0;
-  for (int k : b->order)
+  for (size_t x = (size_t)b->n_band[0] + b->n_band[1]; x < b->order.size(); x++) {
+    const int k = b->order[x];
     if (b->probs[k].kind != rp::KIND_DUPLEX) { gen_maxn = std::max(gen_maxn, b->probs[k].n); gen_mcc++; }
+  }
   b->n_mcc = gen_mcc;
   b->slot_doubles = std::max(gen_mcc ? rp::slot_doubles(gen_maxn) : (size_t)0, ws_need);
 
@@ -509,7 +541,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   if ((e = pool_alloc(ctx, &b->d_seq, seq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc seq");
   if ((e = pool_alloc(ctx, &b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
   if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
-  if ((e = pool_alloc(ctx, &b->d_counter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
+  if ((e = pool_alloc(ctx, &b->d_counter, 4 * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
   if ((e = pool_alloc(ctx, &b->d_gcounter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc gcounter");
   if ((e = pool_alloc(ctx, &b->d_groups, std::max<size_t>(1, b->groups.size()) * sizeof(rp::GroupDev))) != cudaSuccess) return bail(e, "cudaMalloc groups");
   if ((e = pool_alloc(ctx, &b->d_gseq, gseq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc gseq");
@@ -560,10 +592,31 @@ int rp_batch_run(rp_batch* b) {
   }
   b->ls_grid_cached = ls_grid;
   // the two kernels run one after the other on the stream and share the workspace
-  int rc = ensure_workspace(ctx, std::max((size_t)grid * slot_bytes, (size_t)ls_grid * ls_slot_doubles * sizeof(double)));
+  // band classes: grid = resident CTAs, one workspace slot each, placed after the general kernel's slots
+  const int band_threads[2] = {512, 256};
+  size_t band_smem[2] = {0, 0}, band_slot[2] = {0, 0};
+  for (int k = 0; k < 2; k++) {
+    if (!b->n_band[k]) { b->band_grid[k] = 0; continue; }
+    band_smem[k] = rp::band_shared_bytes(b->band_maxn[k], band_threads[k]);
+    band_slot[k] = rp::slot_doubles(b->band_maxn[k]);
+    if (b->band_grid[k] < 0) {
+      const int occ = rp::band_max_ctas_per_sm(band_threads[k], band_smem[k]);
+      if (occ < 1) return fail(ctx, RP_ERR_CUDA, "rp_batch_run: band kernel does not fit on this device");
+      b->band_grid[k] = std::min(b->n_band[k], ctx->sm_count * occ);
+      if (const char* e = std::getenv("RP_GRID")) {
+        int v = std::atoi(e);
+        if (v >= 1 && v < b->band_grid[k]) b->band_grid[k] = v;
+      }
+    }
+  }
+  const size_t gen_bytes = std::max((size_t)grid * slot_bytes, (size_t)ls_grid * ls_slot_doubles * sizeof(double));
+  const size_t bandL_bytes = (size_t)b->band_grid[0] * band_slot[0] * sizeof(double);
+  const size_t bandS_bytes = (size_t)b->band_grid[1] * band_slot[1] * sizeof(double);
+  int rc = ensure_workspace(ctx, gen_bytes + bandL_bytes + bandS_bytes);
   if (rc) return rc;
+  const int n_bandall = b->n_band[0] + b->n_band[1];
   rp::BatchDev d;
-  d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order; d.nprob = b->n_general;
+  d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order + n_bandall; d.nprob = b->n_general;
   d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = std::max(grid, 1);
   d.dense = b->d_dense; d.logz = b->d_logz;
   d.groups = b->d_groups; d.ngroups = ngroups; d.gcounter = b->d_gcounter; d.gseq = b->d_gseq;
@@ -578,10 +631,26 @@ int rp_batch_run(rp_batch* b) {
     d.prof = d_prof;
   }
   cudaStream_t st = ctx->stream;
-  CU(cudaMemsetAsync(b->d_counter, 0, sizeof(int), st));
+  CU(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), st));
   CU(cudaMemsetAsync(b->d_gcounter, 0, sizeof(int), st));
   CU(cudaEventRecord(ctx->ev[0], st));
   int launches = 0;
+  {
+    size_t ws_off = gen_bytes / sizeof(double);
+    int ord_off = 0;
+    for (int k = 0; k < 2; k++) {
+      if (b->n_band[k]) {
+        rp::BatchDev db = d;
+        db.order = b->d_order + ord_off; db.nprob = b->n_band[k];
+        db.counter = b->d_counter + 1 + k;
+        db.ws = ctx->ws + ws_off; db.slot_stride = band_slot[k]; db.nslots = b->band_grid[k];
+        CU(rp::launch_band(db, b->band_grid[k], band_threads[k], band_smem[k], st));
+        launches++;
+      }
+      ws_off += (size_t)b->band_grid[k] * band_slot[k];
+      ord_off += b->n_band[k];
+    }
+  }
   if (ngroups > 0) {
     CU(rp::launch_lockstep(d, ls_grid, ctx->ls_threads, st));
     launches++;

@@ -56,6 +56,31 @@ __global__ void __launch_bounds__(RP_MCC_THREADS, RP_MCC_MIN_CTAS) mcc_persisten
   }
 }
 
+// mcc_band_kernel: the shared-memory band formulation (mcc_band.h).  Same persistent-CTA queue as
+// mcc_persistent, but the interior-loop operands of the last 32 diagonals live in a shared-memory
+// ring and are summed densely, 8 cells per thread, from registers.  Dynamic shared memory =
+// band_shared_bytes(longest problem of the launch, T).  Instantiated for the two launch shapes:
+// <512,1> one CTA per SM (rings of up to ~215 nt) and <256,2> two CTAs per SM (short problems).
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) mcc_band_kernel(BatchDev b) {
+  extern __shared__ double smem_raw[];
+  __shared__ int s_next;
+  CtaExec ex;
+  ex.prof = b.prof;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(b.counter, 1);
+    __syncthreads();
+    const int q = s_next;
+    __syncthreads();
+    if (q >= b.nprob) break;
+    const Problem p = b.probs[b.order[q]];
+    Ctx c;
+    bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)blockIdx.x * b.slot_stride);
+    c.dbg = b.dbg;
+    solve_band(ex, c, p, b.dense, b.logz, smem_raw);
+  }
+}
+
 // lockstep_kernel: one CTA per GROUP of RP_LS_G problems of identical shape (the shuffles of a
 // z-score batch all have the lengths of the original pair).  Lane = problem: thread tid works
 // for problem tid % G and computes whole cells of it, so there are no partial sums, no cell
@@ -358,6 +383,31 @@ int mcc_max_ctas_per_sm(int threads) {
 cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, cudaStream_t st) {
   size_t smem = shared_bytes(threads);
   mcc_persistent<<<grid, threads, smem, st>>>(b);
+  return cudaGetLastError();
+}
+
+int band_max_ctas_per_sm(int threads, size_t smem) {
+  int n = 0;
+  cudaError_t e;
+  if (threads == 512) {
+    if (cudaFuncSetAttribute(mcc_band_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mcc_band_kernel<512, 1>, 512, smem);
+  } else {
+    if (cudaFuncSetAttribute(mcc_band_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mcc_band_kernel<256, 2>, 256, smem);
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, cudaStream_t st) {
+  if (threads == 512) {
+    cudaFuncSetAttribute(mcc_band_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mcc_band_kernel<512, 1><<<grid, 512, smem, st>>>(b);
+  } else {
+    cudaFuncSetAttribute(mcc_band_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mcc_band_kernel<256, 2><<<grid, 256, smem, st>>>(b);
+  }
   return cudaGetLastError();
 }
 

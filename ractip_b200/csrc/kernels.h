@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mcc_band.h"
 #include "mcc_core.h"
 #include "ractip_prob.h"
 
@@ -76,6 +77,8 @@ struct SparseDev {
 
 int mcc_max_ctas_per_sm(int threads);
 cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, cudaStream_t st);
+int band_max_ctas_per_sm(int threads, size_t smem);   // threads = 512 or 256
+cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, cudaStream_t st);
 int lockstep_max_ctas_per_sm(int threads);
 cudaError_t launch_lockstep(const BatchDev& b, int grid, int threads, cudaStream_t st);
 cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st);

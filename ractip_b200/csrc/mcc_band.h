@@ -1,0 +1,613 @@
+// mcc_band.h -- the shared-memory "band" formulation of the McCaskill wavefront
+// (same recurrences and reference call sites as mcc_core.h; this file only
+// changes WHERE the operands of the interior-loop sums live and HOW they are
+// summed).
+//
+// The interior-loop sum of cell (i,j) on anti-diagonal d reaches back at most
+// MAXLOOP+2 = 32 diagonals:  inner pair (i+1+u1, j-1-u2) lies on diagonal
+// d-2-s, s = u1+u2 <= 30, at position i+1+u1.  Seen along one earlier
+// diagonal ("row" s) the sum is a 1-D correlation of that row with the weights
+// g(u1, s-u1): neighbouring cells use overlapping windows of the same row.
+// So:
+//   * the three factorised class tables (generic / 1xn / bulge, see
+//     dev_model.h) of the last 32 diagonals live in a shared-memory ring
+//     (3 x 32 rows), written by the thread that finishes a cell;
+//   * a thread owns a GROUP of 8 neighbouring cells and walks a row with a
+//     sliding 8-wide register window: one shared load + one weight per 8 DFMA;
+//   * rows are stored "mod-8 transposed" (position p at (p&7)*LD8 + (p>>3)), so
+//     the 16 lanes of a half-warp, which own 16 consecutive groups, read 16
+//     consecutive doubles: no bank conflicts although every lane strides by 8;
+//   * the sum is DENSE (cells that cannot pair are computed and multiplied by
+//     a zero closing factor): no compaction lists, no divergence;
+//   * the 31 rows are dealt out as 16 balanced row pairs (q, 30-q) = 16 slices;
+//     a work item is (slice, block of 16 groups) on one half-warp;
+//   * two-strand problems: cells of a diagonal are grouped per strand segment
+//     (both ends on strand 1 / crossing the nick / both on strand 2), so the
+//     strand guard of a whole group is ONE interval of valid row positions,
+//     applied when a row element is loaded.
+// The outside pass is the mirror image (enclosing pairs lie on later diagonals
+// d+2+s at positions k-1-u1) and runs through the same code with the same
+// ring, now holding out*factor rows.
+//
+// Everything else of a diagonal step (split sums over finished diagonals, nick
+// sums, unpaired windows, outputs) is shared with mcc_core.h.
+#ifndef RP_MCC_BAND_H
+#define RP_MCC_BAND_H
+
+#include "mcc_core.h"
+
+namespace rp {
+
+constexpr int BR = 8;            // cells per group
+constexpr int BSLOTS = 32;       // ring slots = MAXLOOP + 2
+constexpr int NSLICE = 16;       // row pairs (q, 30-q)
+
+// Shared-memory copy of the small Boltzmann tables (same member names as DevModel, so that
+// ext_stem / ml_stem / special_loop work on either).  With ~225 KB of shared memory carved out the
+// L1 has no room left and every DevModel access would be an L2 round trip on the critical path.
+struct SmallModel {
+  double scale1, mlb1, expMLclosing, expMLintern, expTermAU, inv_expTermAU;
+  double scale_small[10];
+  double expbulge[2], expinternal[6], expninio[2];
+  double expstack[8][8];
+  double mmI[8][5][5], mmH[8][5][5], mmM[8][5][5], mmExt[8][5][5], mm1n[8][5][5], mm23[8][5][5];
+  double dangle5[8][5], dangle3[8][5];
+  const double (*int11)[8][5][5];         // the large tables stay in HBM/L2
+  const double (*int21)[8][5][5][5];
+  const double (*int22)[8][5][5][5][5];
+  int special_hp, pad;
+};
+constexpr int SM_DOUBLES = (int)((sizeof(SmallModel) + 7) / 8);
+
+struct BandShared {
+  int LDB, LD8;   // ring row stride in doubles (multiple of 8) and sub-row length LDB/8
+  int NGP;        // stride of the group-transposed arrays (>= max number of groups of a diagonal)
+  double *TI, *T1, *TA;    // [BSLOTS][LDB] generic / 1xn / bulge class rows
+  double* ipart;           // [NSLICE+1][BR*NGP] partial interior sums, element (r, g) at r*NGP+g; aliases Shared::part
+  double *cI, *c1, *cA;    // [BR*NGP] closing-pair factors of the diagonal whose interior sums are being built
+  double* G;               // generic weights, packed: G[s*(s+1)/2 + t] = g(t, s-t), 0 where (t, s-t) is not generic
+  double *gA, *g1;         // [32] bulge weight g(0,s), 1xn weight g(1,s-1)
+  SmallModel* sm;
+};
+constexpr int GPACK = (MAXLOOP + 1) * (MAXLOOP + 2) / 2;   // 496
+
+RP_HD int band_ldb(int n) { return ((n + 1 + 7) / 8) * 8; }
+RP_HD int band_ngp(int n) { return (n + 7) / 8 + 3; }
+RP_HD size_t band_part_doubles(int n, int T) {
+  const size_t a = (size_t)2 * BAND * T, b = (size_t)(NSLICE + 1) * BR * band_ngp(n);
+  return a > b ? a : b;
+}
+RP_HD size_t band_shared_doubles(int n, int T) {
+  return band_part_doubles(n, T) + 128 /*red*/ + (size_t)3 * BSLOTS * band_ldb(n) + (size_t)3 * BR * band_ngp(n) +
+         GPACK + 64 + SM_DOUBLES + (size_t)(n + 2 + 7) / 8 + 2;
+}
+RP_HD size_t band_shared_bytes(int n, int T) { return band_shared_doubles(n, T) * sizeof(double); }
+
+RP_HD void carve_band(Shared& sh, BandShared& bs, void* base, int n, int T) {
+  sh.T = T;
+  double* p = static_cast<double*>(base);
+  sh.part = p; bs.ipart = p; p += band_part_doubles(n, T);
+  sh.red = p; p += 128;
+  bs.LDB = band_ldb(n); bs.LD8 = bs.LDB / 8; bs.NGP = band_ngp(n);
+  bs.TI = p; p += (size_t)BSLOTS * bs.LDB;
+  bs.T1 = p; p += (size_t)BSLOTS * bs.LDB;
+  bs.TA = p; p += (size_t)BSLOTS * bs.LDB;
+  bs.cI = p; p += (size_t)BR * bs.NGP;
+  bs.c1 = p; p += (size_t)BR * bs.NGP;
+  bs.cA = p; p += (size_t)BR * bs.NGP;
+  bs.G = p; p += GPACK;
+  bs.gA = p; p += 32;
+  bs.g1 = p; p += 32;
+  bs.sm = reinterpret_cast<SmallModel*>(p); p += SM_DOUBLES;
+  sh.S = reinterpret_cast<uint8_t*>(p);
+  sh.grow = nullptr; sh.ghead_b = nullptr; sh.ghead_1 = nullptr;  // the factorised-row tables of the general kernel are not used
+}
+
+RP_HD void load_band_weights(const DevModel& M, const BandShared& bs, int tid, int T) {
+  for (int x = tid; x < (MAXLOOP + 1) * (MAXLOOP + 1); x += T) {
+    const int s = x / (MAXLOOP + 1), t = x % (MAXLOOP + 1);
+    if (t > s) continue;
+    bs.G[s * (s + 1) / 2 + t] = M.gcls[t][s - t] == CLS_GENERIC ? M.gfull[t][s - t] : 0.;
+  }
+  for (int s = tid; s < 32; s += T) {
+    bs.gA[s] = (s >= 2 && s <= MAXLOOP) ? M.gfull[0][s] : 0.;
+    bs.g1[s] = (s >= 4 && s <= MAXLOOP) ? M.gfull[1][s - 1] : 0.;
+  }
+  SmallModel& S = *bs.sm;
+  if (tid == 0) {
+    S.scale1 = M.scale1; S.mlb1 = M.mlb1; S.expMLclosing = M.expMLclosing; S.expMLintern = M.expMLintern;
+    S.expTermAU = M.expTermAU; S.inv_expTermAU = 1.0 / M.expTermAU;
+    for (int k = 0; k < 10; k++) S.scale_small[k] = M.scale_small[k];
+    for (int k = 0; k < 2; k++) { S.expbulge[k] = M.expbulge[k]; S.expninio[k] = M.expninio[k]; }
+    for (int k = 0; k < 6; k++) S.expinternal[k] = M.expinternal[k];
+    S.int11 = M.int11; S.int21 = M.int21; S.int22 = M.int22;
+    S.special_hp = M.special_hp; S.pad = 0;
+  }
+  for (int x = tid; x < 200; x += T) {
+    (&S.mmI[0][0][0])[x] = (&M.mmI[0][0][0])[x];
+    (&S.mmH[0][0][0])[x] = (&M.mmH[0][0][0])[x];
+    (&S.mmM[0][0][0])[x] = (&M.mmM[0][0][0])[x];
+    (&S.mmExt[0][0][0])[x] = (&M.mmExt[0][0][0])[x];
+    (&S.mm1n[0][0][0])[x] = (&M.mm1n[0][0][0])[x];
+    (&S.mm23[0][0][0])[x] = (&M.mm23[0][0][0])[x];
+    if (x < 64) (&S.expstack[0][0])[x] = (&M.expstack[0][0])[x];
+    if (x < 40) {
+      (&S.dangle5[0][0])[x] = (&M.dangle5[0][0])[x];
+      (&S.dangle3[0][0])[x] = (&M.dangle3[0][0])[x];
+    }
+  }
+}
+
+// position p of a ring row
+RP_HD int bidx(const BandShared& bs, int p) { return (p & 7) * bs.LD8 + (p >> 3); }
+RP_HD double* brow(double* band, const BandShared& bs, int d) { return band + (size_t)(d & (BSLOTS - 1)) * bs.LDB; }
+
+// Strand segments of the cells (i, i+d), i = 1..n-d, of one diagonal:
+//   segment 0: i <  b1   (both ends on strand 1)
+//   segment 1: b1 <= i < b2   (the pair crosses the nick)
+//   segment 2: i >= b2   (both ends on strand 2)
+// Groups of BR cells never straddle a segment boundary.  Single strand: one segment.
+struct Segs {
+  int b[4];   // first cell of each segment, b[3] = n-d+1
+  int G[4];   // first group of each segment, G[3] = number of groups
+};
+RP_HD Segs make_segs(int n, int cp, int d) {
+  Segs s;
+  const int C = n - d;
+  s.b[0] = 1; s.b[3] = C + 1;
+  if (cp <= 0) { s.b[1] = C + 1; s.b[2] = C + 1; }
+  else {
+    int b1 = cp - d, b2 = cp;
+    if (b1 < 1) b1 = 1;
+    if (b1 > C + 1) b1 = C + 1;
+    if (b2 > C + 1) b2 = C + 1;
+    if (b2 < b1) b2 = b1;
+    s.b[1] = b1; s.b[2] = b2;
+  }
+  s.G[0] = 0;
+  for (int k = 0; k < 3; k++) s.G[k + 1] = s.G[k] + (s.b[k + 1] - s.b[k] + BR - 1) / BR;
+  return s;
+}
+// element index (r*NGP + g) of cell i in the group-transposed arrays
+RP_HD int seg_slot(const Segs& s, const BandShared& bs, int i) {
+  const int k = (i >= s.b[1]) + (i >= s.b[2]);
+  const int o = i - s.b[k];
+  return (o & (BR - 1)) * bs.NGP + s.G[k] + (o >> 3);
+}
+
+// ---------------------------------------------------------------------------
+// one work item of the interior sums: slice q (rows q and 30-q) of group g.
+// SIGN=+1 inside (rows d-2-s, window starts at i0+1), SIGN=-1 outside (rows
+// d+2+s, window starts at k0-1-s).  Result: the group's BR partial sums, already
+// multiplied by the cells' closing-pair factors.
+// ---------------------------------------------------------------------------
+template <int SIGN>
+RP_HD void interior_item(const BandShared& bs, int n, int cp, int d, const Segs& sg, int q, int g, double* tot) {
+#pragma unroll
+  for (int r = 0; r < BR; r++) tot[r] = 0.;
+  const int k = (g >= sg.G[1]) + (g >= sg.G[2]);
+  const int i0 = sg.b[k] + BR * (g - sg.G[k]);
+  const int smax = SIGN > 0 ? (d - 6 < MAXLOOP ? d - 6 : MAXLOOP) : (n - 3 - d < MAXLOOP ? n - 3 - d : MAXLOOP);
+  const double* fI = bs.cI + g;   // closing factors of cell r at [r*NGP]: loaded where they are used
+  const double* f1 = bs.c1 + g;
+  const double* fA = bs.cA + g;
+  const int NGP = bs.NGP;
+  for (int h = 0; h < 2; h++) {
+    const int s = h == 0 ? q : MAXLOOP - q;
+    if (h == 1 && s == q) break;
+    if (s > smax || s < 2) continue;
+    const int dr = d - SIGN * (2 + s);           // the row's diagonal
+    const int P0 = SIGN > 0 ? i0 + 1 : i0 - 1 - s;  // row position of (cell r = 0, tap t = 0)
+    // valid positions of the row for this group: inside the row, and on the right side of the nick
+    int plo = 1, phi = n - dr;
+    if (cp > 0) {
+      if (SIGN > 0) {
+        if (k == 1) { if (cp - dr > plo) plo = cp - dr; if (cp - 1 < phi) phi = cp - 1; }
+      } else {
+        if (k == 0) { if (cp - 1 - dr < phi) phi = cp - 1 - dr; }
+        else if (k == 2) { if (cp > plo) plo = cp; }
+      }
+    }
+    const unsigned span = phi >= plo ? (unsigned)(phi - plo) : 0u;
+    if (phi < plo) continue;
+    const size_t ro = (size_t)(dr & (BSLOTS - 1)) * bs.LDB;
+    const double* rI = bs.TI + ro;
+    const double* r1 = bs.T1 + ro;
+    const double* rA = bs.TA + ro;
+    const int LD8 = bs.LD8;
+#define RP_BLD(row, p) (((unsigned)((p) - plo) <= span) ? (row)[((p) & 7) * LD8 + ((p) >> 3)] : 0.)
+    {  // bulge ends (0,s) and (s,0); 1xn ends (1,s-1) and (s-1,1)
+      const double wa = bs.gA[s], w1 = bs.g1[s];
+#pragma unroll
+      for (int r = 0; r < BR; r++) {
+        const double a = RP_BLD(rA, P0 + r) + RP_BLD(rA, P0 + r + s);
+        tot[r] += fA[r * NGP] * (wa * a);
+      }
+      if (s >= 4) {
+#pragma unroll
+        for (int r = 0; r < BR; r++) {
+          const double a = RP_BLD(r1, P0 + r + 1) + RP_BLD(r1, P0 + r + s - 1);
+          tot[r] += f1[r * NGP] * (w1 * a);
+        }
+      }
+    }
+    if (s >= 6) {  // generic taps t = 2 .. s-2: tap-major walk with a sliding register window
+      double acc[BR], win[BR];
+#pragma unroll
+      for (int r = 0; r < BR; r++) acc[r] = 0.;
+#pragma unroll
+      for (int r = 0; r < BR - 1; r++) win[r] = RP_BLD(rI, P0 + 2 + r);
+      win[BR - 1] = 0.;
+      const double* gw = bs.G + s * (s + 1) / 2;
+      const int tend = s - 2;
+      int t = 2;
+#pragma unroll 1
+      for (; t + BR - 1 <= tend; t += BR) {
+#pragma unroll
+        for (int u = 0; u < BR; u++) {
+          win[(u + BR - 1) & (BR - 1)] = RP_BLD(rI, P0 + t + u + BR - 1);
+          const double gv = gw[t + u];
+#pragma unroll
+          for (int r = 0; r < BR; r++) acc[r] += gv * win[(u + r) & (BR - 1)];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BR - 1; u++) {
+        if (t + u <= tend) {
+          win[(u + BR - 1) & (BR - 1)] = RP_BLD(rI, P0 + t + u + BR - 1);
+          const double gv = gw[t + u];
+#pragma unroll
+          for (int r = 0; r < BR; r++) acc[r] += gv * win[(u + r) & (BR - 1)];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < BR; r++) tot[r] += fI[r * NGP] * acc[r];
+    }
+#undef RP_BLD
+  }
+}
+
+// (u1,u2) of the nine table-driven shapes as compile-time functions (special_uv's order)
+RP_HD constexpr int sp_u1(int s) { return s == 0 ? 0 : s == 1 ? 1 : s == 2 ? 0 : s == 3 ? 1 : s == 4 ? 1 : s == 5 ? 2 : s == 6 ? 2 : s == 7 ? 2 : 3; }
+RP_HD constexpr int sp_u2(int s) { return s == 0 ? 0 : s == 1 ? 0 : s == 2 ? 1 : s == 3 ? 1 : s == 4 ? 2 : s == 5 ? 1 : s == 6 ? 2 : s == 7 ? 3 : 2; }
+
+// value of qb (inside) / out (outside) recovered from the bulge-class row, which holds
+// x * expTermAU^[type>2]
+RP_HD double band_plain(const BandShared& bs, int d, int p, int type) {
+  const double v = bs.TA[(size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, p)];
+  return type > 2 ? v * bs.sm->inv_expTermAU : v;
+}
+
+// The table-driven small loops of one cell.  Branch-free: all nine shapes are evaluated with
+// clamped indices and masked, so that their (L2-resident) table look-ups overlap instead of
+// queueing one after the other.
+template <class C>
+RP_HD double inside_specials_band(const C& c, const BandShared& bs, int d, int i) {
+  const SmallModel& M = *bs.sm;
+  const int j = i + d;
+  const int type = pair_type(base(c, i), base(c, j));
+  const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
+  if (!type || ddmax < 2) return 0.;
+  const int maxpo = (c.cp > 0 && i < c.cp) ? c.cp - 1 - i : 1000;
+  const int maxu2 = (c.cp > 0 && j >= c.cp) ? j - 1 - c.cp : 1000;
+  const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
+  double v[RP_N_SPECIAL], w[RP_N_SPECIAL];
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) {
+    const int u1 = sp_u1(s), u2 = sp_u2(s), dd = u1 + u2 + 2;
+    const bool ok = dd <= ddmax && u1 + 1 <= maxpo && u2 <= maxu2;
+    const int k = ok ? i + 1 + u1 : i + 1, l = ok ? j - 1 - u2 : j - 1, dr = ok ? d - dd : d - 2;
+    const int t2 = pair_type(base(c, k), base(c, l));
+    v[s] = (ok && t2) ? band_plain(bs, dr, k, t2) : 0.;
+    w[s] = special_loop(M, s, type, rtype(t2), si1, sj1, base(c, k - 1), base(c, l + 1));
+  }
+  double acc = 0.;
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) acc += v[s] * w[s];
+  return acc;
+}
+
+template <class C>
+RP_HD double outside_specials_band(const C& c, const BandShared& bs, int d, int k, double qbv) {
+  const SmallModel& M = *bs.sm;
+  const int n = c.n, l = k + d;
+  const int type = pair_type(base(c, k), base(c, l));
+  const int ddmax = n - 1 - d < MAXLOOP + 2 ? n - 1 - d : MAXLOOP + 2;
+  if (!type || ddmax < 2) return 0.;
+  int maxpo = k - 1, maxu2 = n - l - 1;
+  if (c.cp > 0) {
+    if (k >= c.cp && k - c.cp < maxpo) maxpo = k - c.cp;
+    if (l < c.cp && c.cp - 2 - l < maxu2) maxu2 = c.cp - 2 - l;
+  }
+  if (maxpo < 1 || maxu2 < 0 || qbv == 0.) return 0.;
+  const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
+  double v[RP_N_SPECIAL], w[RP_N_SPECIAL];
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) {
+    const int u1 = sp_u1(s), u2 = sp_u2(s), dd = u1 + u2 + 2;
+    const bool ok = dd <= ddmax && u1 + 1 <= maxpo && u2 <= maxu2;
+    const int i = ok ? k - 1 - u1 : k - 1, j = ok ? l + 1 + u2 : l + 1, dr = ok ? d + dd : d + 2;
+    const int t1 = pair_type(base(c, i), base(c, j));
+    v[s] = (ok && t1) ? band_plain(bs, dr, i, t1) : 0.;
+    w[s] = special_loop(M, s, t1, t2, base(c, i + 1), base(c, j - 1), sp1, sq1);
+  }
+  double acc = 0.;
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) acc += v[s] * w[s];
+  return acc;
+}
+
+// phase A of a diagonal: all interior items.  Half-warp hw serves item hw, hw+nhw, ...;
+// item -> (slice q = item / NB, block b = item % NB), lane hl of the half-warp owns group 16*b+hl.
+// The table-driven small loops (9 per cell) are done one cell per thread by the LAST threads of
+// the CTA (idle or lightly loaded in the item schedule) and form slice NSLICE.
+template <int SIGN, class C>
+RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int T) {
+  const int n = c.n, cells = n - d;
+  const Segs sg = make_segs(n, c.cp, d);
+  const int NG = sg.G[3];
+  const int NB = (NG + 15) / 16;
+  const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
+  const int smax = SIGN > 0 ? d - 6 : n - 3 - d;
+  // small loops first: their table look-ups are in flight while the row items run
+  for (int x = T - 1 - tid; x < cells; x += T) {
+    const int i = 1 + x;
+    double v;
+    if (c.dbg & 8) v = 0.;
+    else if (SIGN > 0) v = inside_specials_band(c, bs, d, i);
+    else v = outside_specials_band(c, bs, d, i, TB(c, T_QB, d, i));
+    bs.ipart[(size_t)NSLICE * BR * bs.NGP + seg_slot(sg, bs, i)] = v;
+  }
+  if (smax >= 2) {
+    for (int item = hw; item < NSLICE * NB; item += nhw) {
+      const int q = item / NB, b = item - q * NB;
+      const int g = 16 * b + hl;
+      if (g >= NG) continue;
+      double tot[BR];
+      if (c.dbg & 1) {
+#pragma unroll
+        for (int r = 0; r < BR; r++) tot[r] = 0.;
+      } else {
+        interior_item<SIGN>(bs, n, c.cp, d, sg, q, g, tot);
+      }
+      double* out = bs.ipart + (size_t)q * BR * bs.NGP + g;
+#pragma unroll
+      for (int r = 0; r < BR; r++) out[r * bs.NGP] = tot[r];
+    }
+  }
+}
+
+// sum of the partials of cell i (fixed order: deterministic)
+template <int SIGN, class C>
+RP_HD double band_interior_sum(const C& c, const BandShared& bs, int d, const Segs& sg, int i) {
+  const int slot = seg_slot(sg, bs, i);
+  const int smax = SIGN > 0 ? d - 6 : c.n - 3 - d;
+  double s = bs.ipart[(size_t)NSLICE * BR * bs.NGP + slot];
+  if (smax >= 2) {
+    double s0 = 0., s1 = 0.;
+#pragma unroll
+    for (int q = 0; q < NSLICE; q += 2) {
+      s0 += bs.ipart[(size_t)q * BR * bs.NGP + slot];
+      s1 += bs.ipart[(size_t)(q + 1) * BR * bs.NGP + slot];
+    }
+    s += s0 + s1;
+  }
+  return s;
+}
+
+// closing-pair factors of the cells of diagonal d (whose interior sums are built next)
+template <class C>
+RP_HD void band_cfac_inside(const C& c, const BandShared& bs, int d, int tid, int T) {
+  const SmallModel& M = *bs.sm;
+  const int cells = c.n - d;
+  if (cells <= 0) return;
+  const Segs sg = make_segs(c.n, c.cp, d);
+  for (int x = tid; x < BR * sg.G[3]; x += T) {  // every slot of every group, cells past a segment end get 0
+    const int g = x / BR, r = x % BR;
+    const int k = (g >= sg.G[1]) + (g >= sg.G[2]);
+    const int i = sg.b[k] + BR * (g - sg.G[k]) + r;
+    double fI = 0., f1 = 0., fA = 0.;
+    if (i < sg.b[k + 1]) {
+      const int j = i + d;
+      const int type = pair_type(base(c, i), base(c, j));
+      if (type) {
+        const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
+        fI = M.mmI[type][si1][sj1];
+        f1 = M.mm1n[type][si1][sj1];
+        fA = type > 2 ? M.expTermAU : 1.0;
+      }
+    }
+    bs.cI[r * bs.NGP + g] = fI;
+    bs.c1[r * bs.NGP + g] = f1;
+    bs.cA[r * bs.NGP + g] = fA;
+  }
+}
+template <class C>
+RP_HD void band_cfac_outside(const C& c, const BandShared& bs, int d, int tid, int T) {
+  const SmallModel& M = *bs.sm;
+  const int n = c.n, cells = n - d;
+  if (cells <= 0 || d <= TURN) return;
+  const Segs sg = make_segs(n, c.cp, d);
+  for (int x = tid; x < BR * sg.G[3]; x += T) {
+    const int g = x / BR, r = x % BR;
+    const int kk = (g >= sg.G[1]) + (g >= sg.G[2]);
+    const int k = sg.b[kk] + BR * (g - sg.G[kk]) + r;
+    double fI = 0., f1 = 0., fA = 0.;
+    if (k < sg.b[kk + 1]) {
+      const int l = k + d;
+      const int type = pair_type(base(c, k), base(c, l));
+      if (type && k > 1 && l < n && TB(c, T_QB, d, k) != 0.) {
+        const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
+        fI = M.mmI[t2][sq1][sp1];
+        f1 = M.mm1n[t2][sq1][sp1];
+        fA = type > 2 ? M.expTermAU : 1.0;
+      }
+    }
+    bs.cI[r * bs.NGP + g] = fI;
+    bs.c1[r * bs.NGP + g] = f1;
+    bs.cA[r * bs.NGP + g] = fA;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// phase B: finish the cells of diagonal d (one thread per cell), write the ring
+// rows, and prepare the closing factors of the next diagonal.  All HBM/L2
+// operands of a cell are loaded up front with clamped addresses (one round
+// trip), then combined.
+// `wide`: also keep the class tables in HBM (the unpaired-window pass of a
+// single-strand problem reads their full history).
+// ---------------------------------------------------------------------------
+template <class C>
+RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
+  const int T = sh.T, n = c.n, cells = n - d;
+  const SmallModel& M = *bs.sm;
+  const Segs sg = make_segs(n, c.cp, d);
+  const int u = d - 1;  // hairpin size
+  const int e = d - band_start_inside(d);
+  const int vprev = (d & 1) ? V_U0 : V_U1, vcur = (d & 1) ? V_U1 : V_U0;
+  for (int x = tid; x < cells; x += T) {
+    const int i = 1 + x, j = i + d;
+    // ---- loads
+    const double sM = TB(c, T_QM2, d, i);
+    double sQ = TB(c, T_QS, d, i);
+    const double qm2c = TB(c, T_QM2, d - 2, i + 1);
+    const double qm1l = TB(c, T_QM1, d - 1, i), qm1r = TB(c, T_QM1, d - 1, i + 1), qql = TB(c, T_QQ, d - 1, i);
+    const double uprev = VEC(c, vprev, i + 1);
+    const double hpw = VEC(c, V_HPW, u), scd = VEC(c, V_SCALE, d + 1);
+    double nq[BAND - 1];
+#pragma unroll
+    for (int a = 0; a < BAND - 1; a++) {
+      const bool ok = a < e && a <= d - TURN - 2;
+      nq[a] = ok ? TB(c, T_QQ, d - 1 - a, i + 1 + a) : 0.;
+    }
+    const bool sp_case = M.special_hp && (u == 3 || u == 4 || u == 6);
+    const double spv = sp_case ? VEC(c, u == 3 ? V_SP3 : (u == 4 ? V_SP4 : V_SP6), i) : -1.;
+    const bool cross = c.cp > 0 && i < c.cp && j >= c.cp;   // !ss(i,j)
+    const double nk1 = (cross && i + 1 <= c.cp - 1) ? TB(c, T_Q, c.cp - 2 - i, i + 1) : 1.0;
+    const double nk2 = (cross && c.cp <= j - 1) ? TB(c, T_Q, j - 1 - c.cp, c.cp) : 1.0;
+    // ---- combine
+    // the terms of the q-split that the band pass could not see yet: q(i, i+a) = scale^(a+1) for a <= TURN
+#pragma unroll
+    for (int a = 0; a < BAND - 1; a++) sQ += M.scale_small[a + 1] * nq[a];
+    const int type = pair_type(base(c, i), base(c, j));
+    const double sI = type ? band_interior_sum<1>(c, bs, d, sg, i) : 0.;
+    const double scale2 = M.scale_small[2];
+    double qb = 0.;
+    if (type) {
+      if (!cross) {
+        double h;
+        if (spv >= 0.) h = spv;
+        else if (sp_case && u == 3) h = type > 2 ? hpw * M.expTermAU : hpw;
+        else h = hpw * M.mmH[type][base(c, i + 1)][base(c, j - 1)];
+        qb += h;
+      }
+      qb += sI;
+      if (ss(c, i, i + 1) && ss(c, j - 1, j))
+        qb += qm2c * M.expMLclosing * ml_stem(M, rtype(type), base(c, j - 1), base(c, i + 1)) * scale2;
+      if (cross) {
+        double t = scale2;
+        t *= nk1;
+        t *= nk2;
+        t *= ext_stem(M, rtype(type), ss(c, j - 1, j) ? base(c, j - 1) : -1, ss(c, i, i + 1) ? base(c, i + 1) : -1);
+        qb += t;
+      }
+    }
+    TB(c, T_QB, d, i) = qb;
+    double fI = 0., f1 = 0., fA = 0.;
+    if (type && qb != 0.) {
+      const int t2 = rtype(type), sq1 = j < n ? base(c, j + 1) : 0, sp1 = i > 1 ? base(c, i - 1) : 0;
+      fI = qb * M.mmI[t2][sq1][sp1];
+      f1 = qb * M.mm1n[t2][sq1][sp1];
+      fA = type > 2 ? qb * M.expTermAU : qb;
+    }
+    {
+      const size_t o = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, i);
+      bs.TI[o] = fI; bs.T1[o] = f1; bs.TA[o] = fA;
+    }
+    if (wide) { TB(c, T_QBI, d, i) = fI; TB(c, T_QB1N, d, i) = f1; TB(c, T_QBAU, d, i) = fA; }
+    double qm1 = ss(c, j - 1, j) ? qm1l * M.mlb1 : 0.;
+    if (type && ss(c, i - 1, i) && ss(c, j, j + 1))
+      qm1 += qb * ml_stem(M, type, i > 1 ? base(c, i - 1) : -1, j < n ? base(c, j + 1) : -1);
+    TB(c, T_QM1, d, i) = qm1;
+    const double U = ss(c, i, i + 1) ? M.mlb1 * (qm1r + uprev) : 0.;
+    VEC(c, vcur, i) = U;
+    TB(c, T_QM, d, i) = qm1 + sM + U;
+    double qq = qql * M.scale1;
+    if (type)
+      qq += qb * ext_stem(M, type, (i > 1 && ss(c, i - 1, i)) ? base(c, i - 1) : -1,
+                          (j < n && ss(c, j, j + 1)) ? base(c, j + 1) : -1);
+    TB(c, T_QQ, d, i) = qq;
+    TB(c, T_Q, d, i) = scd + qq + sQ;
+  }
+  if (d + 1 <= n - 1) band_cfac_inside(c, bs, d + 1, tid, T);
+}
+
+template <class C>
+RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
+  const int T = sh.T, n = c.n, cells = n - d;
+  const SmallModel& M = *bs.sm;
+  const Segs sg = make_segs(n, c.cp, d);
+  for (int x = tid; x < cells; x += T) {
+    const int k = 1 + x, l = k + d;
+    const bool mlr = l < n && ss(c, l, l + 1);
+    const bool mll = k > 1 && ss(c, k - 1, k);
+    // ---- loads
+    const double sP = TB(c, T_PRB, d, k), sL = TB(c, T_MLB, d, k);
+    const double qbv = TB(c, T_QB, d, k);
+    const double plp = mlr ? TB(c, T_PL, d + 1, k) : 0., mcp = mlr ? TB(c, T_MC, d + 1, k) : 0.;
+    const double pmp = mll ? TB(c, T_PMLB, d + 1, k - 1) : 0., prp = mll ? TB(c, T_PR, d + 1, k - 1) : 0.;
+    const double q5 = k > 1 ? TB(c, T_Q, k - 2, 1) : 1.0;
+    const double q3 = l < n ? TB(c, T_Q, n - l - 1, l + 1) : 1.0;
+    double qo = 0., qn = 1.0;
+    if (c.cp > 0) {
+      if (k >= c.cp) {
+        qo = VEC(c, V_QROUT, l);
+        if (k > c.cp) qn = TB(c, T_Q, k - 1 - c.cp, c.cp);
+      } else if (l < c.cp) {
+        qo = VEC(c, V_QLOUT, k);
+        if (l + 1 <= c.cp - 1) qn = TB(c, T_Q, c.cp - 2 - l, l + 1);
+      }
+    }
+    // ---- combine
+    const int type = pair_type(base(c, k), base(c, l));
+    double sI = 0.;
+    if (type && qbv != 0.) sI = band_interior_sum<-1>(c, bs, d, sg, k);
+    const double scale2 = M.scale_small[2];
+    const double PL = mlr ? plp * M.mlb1 + mcp : 0.;
+    const double PR = mlr ? sP : 0.;
+    TB(c, T_PL, d, k) = PL;
+    TB(c, T_PR, d, k) = PR;
+    TB(c, T_PRML, d, k) = PR + PL;
+    const double PMLB = mll ? pmp * M.mlb1 + prp : 0.;
+    TB(c, T_PMLB, d, k) = PMLB;
+    double out = 0.;
+    if (type && qbv != 0.) {
+      out = q5 * q3 * c.invZ * ext_stem(M, type, mll ? base(c, k - 1) : -1, mlr ? base(c, l + 1) : -1);
+      out += sI;
+      if (mlr && mll) out += (PMLB + sL) * ml_stem(M, type, base(c, k - 1), base(c, l + 1)) * scale2;
+      if (c.cp > 0 && qo != 0.) {
+        if (k >= c.cp) out += qo * qn * ext_stem(M, type, k > c.cp ? base(c, k - 1) : -1, base(c, l + 1));
+        else if (l < c.cp) out += qo * qn * ext_stem(M, type, base(c, k - 1), l + 1 < c.cp ? base(c, l + 1) : -1);
+      }
+    }
+    TB(c, T_OUT, d, k) = out;
+    double fI = 0., f1 = 0., fA = 0., mc = 0.;
+    if (out != 0.) {
+      const int si1 = base(c, k + 1), sj1 = base(c, l - 1);
+      fI = out * M.mmI[type][si1][sj1];
+      f1 = out * M.mm1n[type][si1][sj1];
+      fA = type > 2 ? out * M.expTermAU : out;
+      if (ss(c, k, k + 1) && ss(c, l - 1, l)) mc = out * M.expMLclosing * ml_stem(M, rtype(type), sj1, si1);
+    }
+    {
+      const size_t o = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, k);
+      bs.TI[o] = fI; bs.T1[o] = f1; bs.TA[o] = fA;
+    }
+    if (wide) { TB(c, T_OUTI, d, k) = fI; TB(c, T_OUT1N, d, k) = f1; TB(c, T_OUTAU, d, k) = fA; }
+    TB(c, T_MC, d, k) = mc;
+  }
+  if (d - 1 > TURN) band_cfac_outside(c, bs, d - 1, tid, T);
+}
+
+}  // namespace rp
+#endif

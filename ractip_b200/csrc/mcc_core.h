@@ -187,7 +187,9 @@ RP_HD int rtype(int t) { return t == 0 ? 0 : (t == 7 ? 7 : ((t - 1) ^ 1) + 1); }
 template <class C>
 RP_HD bool ss(const C& c, int a, int b) { return c.cp <= 0 || a >= c.cp || b < c.cp; }
 
-RP_HD double ext_stem(const DevModel& M, int type, int s5, int s3) {
+// (MT: DevModel, or the shared-memory copy of its small tables used by the band kernel)
+template <class MT>
+RP_HD double ext_stem(const MT& M, int type, int s5, int s3) {
   double e = 1.0;
   if (s5 >= 0 && s3 >= 0) e = M.mmExt[type][s5][s3];
   else if (s5 >= 0) e = M.dangle5[type][s5];
@@ -195,7 +197,8 @@ RP_HD double ext_stem(const DevModel& M, int type, int s5, int s3) {
   if (type > 2) e *= M.expTermAU;
   return e;
 }
-RP_HD double ml_stem(const DevModel& M, int type, int s5, int s3) {
+template <class MT>
+RP_HD double ml_stem(const MT& M, int type, int s5, int s3) {
   double e = 1.0;
   if (s5 >= 0 && s3 >= 0) e = M.mmM[type][s5][s3];
   else if (s5 >= 0) e = M.dangle5[type][s5];
@@ -220,7 +223,8 @@ RP_HD int special_index(int u1, int u2) {
 }
 // weight (incl. scale) of special shape s: closing pair `type` with neighbours
 // (si1,sj1), inner pair of reversed type t2r with neighbours (sp1,sq1)
-RP_HD double special_loop(const DevModel& M, int s, int type, int t2r, int si1, int sj1, int sp1, int sq1) {
+template <class MT>
+RP_HD double special_loop(const MT& M, int s, int type, int t2r, int si1, int sj1, int sp1, int sq1) {
   switch (s) {
     case 0: return M.expstack[type][t2r] * M.scale_small[2];
     case 1:
@@ -343,6 +347,45 @@ RP_HD void multi_dot(const double* A, int sa, const double* B, int sb, int tb, i
 #pragma unroll
     for (int t = 0; t < 8; t++)
       if (t < nu) acc[t] += a * B[t * tb];
+  }
+}
+
+// The same when the shifts advance along the stream itself (tb == sb):
+//   acc[t] += sum_{x<cnt} A[x*sa] * B[(x+t)*sb],  t < nu <= 8
+// B is walked ONCE with an 8-deep register window (2 loads per 8 FMAs instead of 9).
+// acc[t], t >= nu, receives partial sums that the caller ignores.
+RP_HD void multi_dot_slide(const double* A, int sa, const double* B, int sb, int cnt, int nu, double* acc) {
+  if (cnt <= 0) return;
+  const int last = cnt + nu - 2;  // largest B element any requested term touches
+  double win[8];
+#pragma unroll
+  for (int t = 0; t < 7; t++) win[t] = t <= last ? B[(long)t * sb] : 0.;
+  win[7] = 0.;
+  const double* bp = B + (long)7 * sb;  // next element to enter the window
+  int y = 7;
+  int x = 0;
+#pragma unroll 1
+  for (; x + 8 <= cnt; x += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      win[(u + 7) & 7] = y <= last ? *bp : 0.;
+      bp += sb; y++;
+      const double a = *A;
+      A += sa;
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc[t] += a * win[(u + t) & 7];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 7; u++) {
+    if (x + u < cnt) {
+      win[(u + 7) & 7] = y <= last ? *bp : 0.;
+      bp += sb; y++;
+      const double a = *A;
+      A += sa;
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc[t] += a * win[(u + t) & 7];
+    }
   }
 }
 
@@ -1051,6 +1094,62 @@ RP_HD void unstru_hairpin(C& c, int tid, int T) {
     TB(c, T_DG, d, i) = v;
   }
 }
+// The table-driven shapes (9 small loops, dev_model.h) of the gap sums: item (side, gap size
+// ug <= 3, gap start a, slice) sums the loops of all special shapes with that gap size over
+// every `nsl`-th position of the free pair end and leaves the partial in a scratch row of T_RR
+// (free until unstru_ml_tables): row (side*3+ug-1)*nsl+slice, position a.  unstru_gaps adds the
+// slices up in fixed order.  Branch-free body: cells that cannot pair carry qb = out = 0.
+RP_HD int gap_special_slices(int n) { return n >= 48 ? 4 : 1; }
+template <class C, class MT>
+RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
+  const int n = c.n;
+  if (n < 7) return;   // rows 0..5 of the scratch must exist; shorter sequences have no such loops to speak of (handled below)
+  const int nsl = gap_special_slices(n);
+  const int items = (c.dbg & 4) ? 0 : 2 * 3 * nsl * n;
+  for (int x = tid; x < items; x += T) {
+    const int a = x % n + 1;
+    int y = x / n;
+    const int sl = y % nsl; y /= nsl;
+    const int ug = y % 3 + 1, side = y / 3;
+    const int b = a + ug + 1;
+    double acc = 0.;
+    if (b <= n) {
+      if (side == 0) {
+        const int p = a, k = b, u1 = ug, lmin = k + TURN + 1;
+        const int sp1 = base(c, k - 1), si1 = base(c, p + 1);
+        for (int u2 = 0; u2 <= 3; u2++) {
+          if (c.M->gcls[u1][u2] != CLS_SPECIAL) continue;
+          const int lmax = n - 1 - u2, sidx = special_index(u1, u2);
+#pragma unroll 4
+          for (int l = lmin + sl; l <= lmax; l += nsl) {
+            const int o = l + 1 + u2;
+            const double qb = TB(c, T_QB, l - k, k), ou = TB(c, T_OUT, o - p, p);
+            const double w = special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
+                                          si1, base(c, o - 1), sp1, base(c, l + 1));
+            acc += ou * qb * w;
+          }
+        }
+      } else {
+        const int l = a, o = b, u2 = ug;
+        const int sq1 = base(c, l + 1), sj1 = base(c, o - 1);
+        for (int u1 = 0; u1 <= 3; u1++) {
+          if (c.M->gcls[u1][u2] != CLS_SPECIAL) continue;
+          const int pmax = l - TURN - 2 - u1, sidx = special_index(u1, u2);
+#pragma unroll 4
+          for (int p = 1 + sl; p <= pmax; p += nsl) {
+            const int k = p + 1 + u1;
+            const double ou = TB(c, T_OUT, o - p, p), qb = TB(c, T_QB, l - k, k);
+            const double w = special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
+                                          base(c, p + 1), sj1, base(c, k - 1), sq1);
+            acc += ou * qb * w;
+          }
+        }
+      }
+    }
+    TB(c, T_RR, ((side * 3 + ug - 1) * nsl + sl), a) = acc;
+  }
+}
+
 // U2 (side=0): DG(p,k) += weight of all interior loops closed by some (p,o) with inner pair (k,l): 5' gap (p,k)
 // U3 (side=1): DG(l,o) += the same loops seen from their 3' gap (l,o)
 // One item per gap.  For the factorised classes the sum over the free pair end is a dot
@@ -1085,7 +1184,7 @@ RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
           const double* Q = c.ptr(tabQ[cls], lmin - k, k);           // qbX(k,l), one diagonal per l
           const double* O = c.ptr(tabO[cls], lmin + 1 + u2 - p, p);  // outX(p,l+1+u2), one diagonal per u2
           const int cmain = n - 1 - (u2 + nu - 1) - lmin + 1;        // l range valid for every u2 of the run
-          multi_dot(Q, ds, O, ds, ds, cmain, nu, av);
+          multi_dot_slide(Q, ds, O, ds, cmain, nu, av);
           for (int t = 0; t < nu; t++) {
             // the shorter shifts reach further: l up to n-1-(u2+t)
             const int cnt = n - 1 - (u2 + t) - lmin + 1;
@@ -1094,19 +1193,7 @@ RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
           }
           u2 += nu;
         } else {
-          const int lmax = n - 1 - u2;
-          const int sidx = special_index(u1, u2);
-          const int sp1 = base(c, k - 1), si1 = base(c, p + 1);
-          for (int l = lmin; l <= lmax; l++) {
-            const double qb = TB(c, T_QB, l - k, k);
-            if (qb == 0.) continue;
-            const int o = l + 1 + u2;
-            const double ou = TB(c, T_OUT, o - p, p);
-            if (ou == 0.) continue;
-            acc += ou * qb * special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
-                                          si1, base(c, o - 1), sp1, base(c, l + 1));
-          }
-          u2++;
+          u2++;  // table-driven shapes: summed by unstru_gap_specials into the scratch rows
         }
       }
     } else {
@@ -1121,7 +1208,7 @@ RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
           const double* O = c.ptr(tabO[cls], o - 1, 1);               // outX(p,o): one diagonal down, one cell right per p
           const double* Q = c.ptr(tabQ[cls], l - 2 - u1, 2 + u1);     // qbX(p+1+u1,l); per u1 likewise
           const int cmain = l - TURN - 2 - (u1 + nu - 1);             // p = 1..cmain valid for every u1 of the run
-          multi_dot(O, ps - ds, Q, ps - ds, ps - ds, cmain, nu, av);
+          multi_dot_slide(O, ps - ds, Q, ps - ds, cmain, nu, av);
           for (int t = 0; t < nu; t++) {
             const int cnt = l - TURN - 2 - (u1 + t);
             if (cnt > cmain) av[t] += dot_range(O, ps - ds, Q + (long)t * (ps - ds), ps - ds, cmain, cnt, 0, 1);
@@ -1129,21 +1216,13 @@ RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
           }
           u1 += nu;
         } else {
-          const int pmax = l - TURN - 2 - u1;
-          const int sidx = special_index(u1, u2);
-          const int sq1 = base(c, l + 1), sj1 = base(c, o - 1);
-          for (int p = 1; p <= pmax; p++) {
-            const double ou = TB(c, T_OUT, o - p, p);
-            if (ou == 0.) continue;
-            const int k = p + 1 + u1;
-            const double qb = TB(c, T_QB, l - k, k);
-            if (qb == 0.) continue;
-            acc += ou * qb * special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
-                                          base(c, p + 1), sj1, base(c, k - 1), sq1);
-          }
           u1++;
         }
       }
+    }
+    if (ug <= 3 && n >= 7) {
+      const int nsl = gap_special_slices(n);
+      for (int sl = 0; sl < nsl; sl++) acc += TB(c, T_RR, ((side * 3 + ug - 1) * nsl + sl), a);
     }
     TB(c, T_DG, b - a, a) += acc;
   }

@@ -9,6 +9,7 @@
 #ifndef RP_MCC_DRIVER_H
 #define RP_MCC_DRIVER_H
 
+#include "mcc_band.h"
 #include "mcc_core.h"
 
 namespace rp {
@@ -16,12 +17,13 @@ namespace rp {
 enum {
   PH_STAGE = 0, PH_PROLOGUE, PH_PROLOGUE2, PH_INSIDE_A, PH_INSIDE_B, PH_NICK1, PH_NICK2, PH_OUTSIDE_A, PH_OUTSIDE_B,
   PH_WRITE_BP, PH_UN_HAIRPIN, PH_UN_GAPS0, PH_UN_GAPS1, PH_UN_DOMROWS, PH_UN_DOMCOLS, PH_UN_MLTAB, PH_UN_WINDOWS,
-  PH_WRITE_HP, PH_LOGZ, PH_BAND_A, PH_BAND_B, PH_COUNT
+  PH_WRITE_HP, PH_LOGZ, PH_BAND_A, PH_BAND_B, PH_CFAC, PH_COUNT
 };
 
 // outputs of finished problems; probs[g] is lane g's problem (G = 1 in the general kernel)
-template <class Exec, class Get>
-RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* dense) {
+// `SM`: the model the table-driven gap loops read (DevModel, or the band kernel's shared-memory copy)
+template <class Exec, class Get, class MT>
+RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* dense, const MT& SM) {
   const int nct = ex.nthreads() / G;
   if (probs[0].kind == KIND_LINEAR) {
     ex.phase(PH_WRITE_BP, [&](int tid) {
@@ -33,7 +35,10 @@ RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* d
       if (p.out_bp >= 0) write_bp2(get(tid % G), dense + p.out_bp, tid / G, nct);
     });
     if (probs[0].max_w > 0) {
-      ex.phase(PH_UN_HAIRPIN, [&](int tid) { unstru_hairpin(get(tid % G), tid / G, nct); });
+      ex.phase(PH_UN_HAIRPIN, [&](int tid) {
+        unstru_hairpin(get(tid % G), tid / G, nct);
+        unstru_gap_specials(get(tid % G), SM, tid / G, nct);
+      });
       ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(get(tid % G), 0, tid / G, nct); });
       ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(get(tid % G), 1, tid / G, nct); });
       ex.phase(PH_UN_DOMROWS, [&](int tid) { unstru_dom_rows(get(tid % G), tid / G, nct); });
@@ -123,7 +128,78 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
       ex.phase(PH_OUTSIDE_B, [&](int tid) { outside_B(c, sh, d, i0, C, tid); });
     }
   }
-  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense);
+  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M);
+}
+
+// ---------------------------------------------------------------------------
+// band kernel: one problem per CTA, interior-loop operands in a shared-memory
+// ring of the last 32 diagonals (mcc_band.h); split sums, nick sums, unpaired
+// windows and outputs as in solve_mcc.  `smem` is the CTA's dynamic shared
+// memory (band_shared_bytes(n, T) bytes).
+// ---------------------------------------------------------------------------
+template <class Exec>
+RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* logz, void* smem) {
+  const int T = ex.nthreads();
+  const int n = c.n;
+  Shared sh;
+  BandShared bs;
+  carve_band(sh, bs, smem, n, T);
+  const bool wide = c.kind == KIND_LINEAR && c.max_w > 0;  // the unpaired-window pass reads the class tables' full history
+  {
+    const uint8_t* gS = c.S;
+    ex.phase(PH_STAGE, [&](int tid) {
+      for (int x = tid; x <= n + 1; x += T) sh.S[x] = gS[x];
+      load_band_weights(*c.M, bs, tid, T);
+      prologue_vectors(c, tid, T);
+    });
+    c.S = sh.S;
+  }
+  ex.phase(PH_PROLOGUE2, [&](int tid) {
+    prologue2(c, tid, T);
+    if (TURN + 1 <= n - 1) band_cfac_inside(c, bs, TURN + 1, tid, T);
+  });
+
+  // ---- inside
+  for (int d = TURN + 1; d <= n - 1; d++) {
+    if (d == band_start_inside(d)) {
+      const int rows = n - d;
+      const int chunk = make_split(rows, T).Cp;
+      for (int i0 = 1; i0 <= rows; i0 += chunk) {
+        const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) { inside_band_A(c, sh, d, i0, C, tid); });
+        ex.phase(PH_BAND_B, [&](int tid) { inside_band_B(c, sh, d, i0, C, tid); });
+      }
+    }
+    ex.phase(PH_INSIDE_A, [&](int tid) { band_interior_A<1>(c, bs, d, tid, T); });
+    ex.phase(PH_INSIDE_B, [&](int tid) { band_inside_B(c, sh, bs, d, wide, tid); });
+  }
+  inside_end(c);
+  if (logz) {
+    ex.phase(PH_LOGZ, [&](int tid) {
+      if (tid == 0) logz[(size_t)p.pair * 3 + p.which] = log(TB(c, T_Q, n - 1, 1)) + n * log(c.M->pf_scale);
+    });
+  }
+
+  // ---- outside
+  ex.phase(PH_CFAC, [&](int tid) { band_cfac_outside(c, bs, n - 1, tid, T); });
+  for (int d = n - 1; d >= TURN + 1; d--) {
+    if (c.cp > 0) {
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, sh.red, 1, 32, d, tid, T); });
+      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
+    }
+    if ((n - 1 - d) % BAND == 0) {
+      const int rows = n - d + BAND - 1;
+      const int chunk = make_split(rows, T).Cp;
+      for (int r0 = 0; r0 < rows; r0 += chunk) {
+        const int C = rows - r0 < chunk ? rows - r0 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) { outside_band_A(c, sh, d, r0, C, tid); });
+        ex.phase(PH_BAND_B, [&](int tid) { outside_band_B(c, sh, d, r0, C, tid); });
+      }
+    }
+    ex.phase(PH_OUTSIDE_A, [&](int tid) { band_interior_A<-1>(c, bs, d, tid, T); });
+    ex.phase(PH_OUTSIDE_B, [&](int tid) { band_outside_B(c, sh, bs, d, wide, tid); });
+  }
+  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *bs.sm);
 }
 
 // ---------------------------------------------------------------------------
@@ -167,7 +243,7 @@ RP_HD void solve_lockstep(Exec& ex, Get get, const Problem* probs, const uint8_t
     }
     ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_cells(get(tid % G), sh, d, tid / G, nct); });
   }
-  emit_outputs(ex, get, probs, G, dense);
+  emit_outputs(ex, get, probs, G, dense, *get(0).M);
 }
 
 }  // namespace rp

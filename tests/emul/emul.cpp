@@ -29,9 +29,9 @@ void layout(int n, int max_w, int n1, int n2, size_t& nbp, size_t& nup, size_t& 
 }
 }  // namespace
 
-// general kernel: one problem
-extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
-                            float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
+// one problem; band = 0: general kernel (solve_mcc), band = 1: shared-memory band kernel (solve_band)
+static int run_problem(int band, const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
+                       float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
   int rc = rp::build_dev_model(*m, &g_model);
   if (rc) return rc;
   std::vector<uint8_t> S(n + 16, 0);
@@ -54,12 +54,26 @@ extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, i
   rp::Ctx c;
   rp::bind_ctx(c, &g_model, S.data(), p, ws.data());
   SerialExec ex{T};
-  rp::solve_mcc(ex, c, p, dense.data(), lz, sh);
+  if (band) {
+    std::vector<double> bsm(rp::band_shared_doubles(n, T) + 2, 1e300);  // poison
+    rp::solve_band(ex, c, p, dense.data(), lz, bsm.data());
+  } else {
+    rp::solve_mcc(ex, c, p, dense.data(), lz, sh);
+  }
   if (p.out_bp >= 0) std::memcpy(bp, dense.data(), nbp * sizeof(float));
   if (p.out_up >= 0) std::memcpy(up, dense.data() + nbp, nup * sizeof(float));
   if (p.out_hp >= 0) std::memcpy(hp, dense.data() + nbp + nup, nhp * sizeof(float));
   if (logz) *logz = lz[0];
   return 0;
+}
+
+extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
+                            float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
+  return run_problem(0, m, seq, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
+}
+extern "C" int emul_band_problem(const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
+                                 float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
+  return run_problem(1, m, seq, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
 }
 
 // lockstep kernel: `count` (<= G) same-shape problems; seqs = count*n letters, outputs count blocks

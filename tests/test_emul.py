@@ -70,3 +70,40 @@ def test_emulated_lockstep_two_strand_matches_oracle(emul, oracle, G, T, count):
         for g, (a, b) in enumerate(pairs):
             assert np.abs(hp[g] - oracle.rnaduplex(a, b, 0.0)).max() <= 2e-7, (n1, n2, g)
             assert abs(lz[g] - oracle.fold(a + b, n1 + 1)[2]) < 1e-10
+
+
+# ---- shared-memory band kernel (mcc_band.h): dense register-tiled interior sums, ring of 32 diagonals
+@pytest.mark.parametrize("T", [64, 256, 512])
+def test_emulated_band_linear_matches_oracle(emul, oracle, T):
+    rng = np.random.default_rng(7 + T)
+    for n in [1, 4, 5, 9, 23, 41, 72, 97]:
+        s = rand_seq(rng, n)
+        bp, up, lz = emul.linear(s, 15, T, band=True)
+        obp, oup = oracle.rnafold(s, 15)
+        _, _, olz = oracle.fold(s)
+        assert np.abs(bp - obp).max() <= 2e-7, n
+        assert np.abs(up - oup).max() <= 2e-7, n
+        assert abs(lz - olz) < 1e-10
+
+
+@pytest.mark.parametrize("T", [64, 256])
+def test_emulated_band_two_strand_matches_oracle(emul, oracle, T):
+    rng = np.random.default_rng(300 + T)
+    for n1, n2 in [(1, 1), (3, 9), (12, 9), (35, 35), (30, 52), (9, 70), (61, 8)]:
+        s1, s2 = rand_seq(rng, n1), rand_seq(rng, n2)
+        hp, lz = emul.cofold(s1, s2, 0.0, T, band=True)
+        ohp = oracle.rnaduplex(s1, s2, 0.0)
+        _, _, olz = oracle.fold(s1 + s2, n1 + 1)
+        assert np.abs(hp - ohp).max() <= 2e-7, (n1, n2)
+        assert abs(lz - olz) < 1e-10
+
+
+def test_emulated_band_special_hairpins_and_bundled(emul, oracle, bundled):
+    for s in ["GGGGGACCCC", "CCAACGGG", "ggggaccuuaugc", "GGGTGACTCC", "ACAGUACUGAGCAGUACU", "NNACGUNNACGU"]:
+        bp, up, lz = emul.linear(s, 5, 64, band=True)
+        obp, oup = oracle.rnafold(s, 5)
+        assert np.abs(bp - obp).max() <= 2e-7, s
+        assert np.abs(up - oup).max() <= 2e-7, s
+    s1, s2 = bundled["sequences"]["DIS"], bundled["sequences"]["DIS"]
+    hp, _ = emul.cofold(s1, s2, 0.1, 128, band=True)
+    assert np.array_equal(hp, oracle.rnaduplex(s1, s2, 0.1))
