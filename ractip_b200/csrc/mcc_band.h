@@ -67,6 +67,7 @@ struct BandShared {
   double *cI, *c1, *cA;    // [BR*NGP] closing-pair factors of the diagonal whose interior sums are being built
   double* G;               // generic weights, packed: G[s*(s+1)/2 + t] = g(t, s-t), 0 where (t, s-t) is not generic
   double *gA, *g1;         // [32] bulge weight g(0,s), 1xn weight g(1,s-1)
+  double* sIv;             // [n+2] finished interior sums of the diagonal that is being completed (by cell)
   SmallModel* sm;
 };
 constexpr int GPACK = (MAXLOOP + 1) * (MAXLOOP + 2) / 2;   // 496
@@ -79,7 +80,7 @@ RP_HD size_t band_part_doubles(int n, int T) {
 }
 RP_HD size_t band_shared_doubles(int n, int T) {
   return band_part_doubles(n, T) + 128 /*red*/ + (size_t)3 * BSLOTS * band_ldb(n) + (size_t)3 * BR * band_ngp(n) +
-         GPACK + 64 + SM_DOUBLES + (size_t)(n + 2 + 7) / 8 + 2;
+         GPACK + 64 + (size_t)(n + 2) + SM_DOUBLES + (size_t)(n + 2 + 7) / 8 + 2;
 }
 RP_HD size_t band_shared_bytes(int n, int T) { return band_shared_doubles(n, T) * sizeof(double); }
 
@@ -98,6 +99,7 @@ RP_HD void carve_band(Shared& sh, BandShared& bs, void* base, int n, int T) {
   bs.G = p; p += GPACK;
   bs.gA = p; p += 32;
   bs.g1 = p; p += 32;
+  bs.sIv = p; p += n + 2;
   bs.sm = reinterpret_cast<SmallModel*>(p); p += SM_DOUBLES;
   sh.S = reinterpret_cast<uint8_t*>(p);
   sh.grow = nullptr; sh.ghead_b = nullptr; sh.ghead_1 = nullptr;  // the factorised-row tables of the general kernel are not used
@@ -175,6 +177,27 @@ RP_HD int seg_slot(const Segs& s, const BandShared& bs, int i) {
   return (o & (BR - 1)) * bs.NGP + s.G[k] + (o >> 3);
 }
 
+// Ring element load "valid ? row[ix] : 0" of the item loops.  On the device: one predicated
+// ld.shared (no branch, no address clamp); `x <= span` (unsigned) is the validity test.
+#ifdef __CUDA_ARCH__
+struct RingPtr { unsigned a; };   // shared-window byte address
+__device__ __forceinline__ RingPtr ring_ptr(const double* p) { RingPtr r; r.a = (unsigned)__cvta_generic_to_shared(p); return r; }
+__device__ __forceinline__ double ring_ld(RingPtr base, int ix, unsigned x, unsigned span) {
+  double v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %2, %3;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.shared.f64 %0, [%1];\n\t}"
+               : "=d"(v) : "r"(base.a + (unsigned)(ix * 8)), "r"(x), "r"(span));
+  return v;
+}
+__device__ __forceinline__ void ring_adv(RingPtr& p, int elems) { p.a += (unsigned)(elems * 8); }
+__device__ __forceinline__ void keep_in_reg(int& v) { asm volatile("" : "+r"(v)); }
+#else
+struct RingPtr { const double* a; };
+inline RingPtr ring_ptr(const double* p) { RingPtr r; r.a = p; return r; }
+inline double ring_ld(RingPtr base, int ix, unsigned x, unsigned span) { return x <= span ? base.a[ix] : 0.; }
+inline void ring_adv(RingPtr& p, int elems) { p.a += elems; }
+inline void keep_in_reg(int&) {}
+#endif
+
 // ---------------------------------------------------------------------------
 // one work item of the interior sums: slice q (rows q and 30-q) of group g.
 // SIGN=+1 inside (rows d-2-s, window starts at i0+1), SIGN=-1 outside (rows
@@ -191,7 +214,7 @@ RP_HD void interior_item(const BandShared& bs, int n, int cp, int d, const Segs&
   const double* fI = bs.cI + g;   // closing factors of cell r at [r*NGP]: loaded where they are used
   const double* f1 = bs.c1 + g;
   const double* fA = bs.cA + g;
-  const int NGP = bs.NGP;
+  const int NGP = bs.NGP, LD8 = bs.LD8;
   for (int h = 0; h < 2; h++) {
     const int s = h == 0 ? q : MAXLOOP - q;
     if (h == 1 && s == q) break;
@@ -208,26 +231,36 @@ RP_HD void interior_item(const BandShared& bs, int n, int cp, int d, const Segs&
         else if (k == 2) { if (cp > plo) plo = cp; }
       }
     }
-    const unsigned span = phi >= plo ? (unsigned)(phi - plo) : 0u;
     if (phi < plo) continue;
+    // Window element c stands for row position P0 + c; it is valid iff clo <= c <= clo + span, and
+    // lives at sub-row (b+c)&7, index q0 + ((b+c)>>3) of the (mod-8 transposed) row.
+    const int clo = plo - P0;
+    const unsigned span = (unsigned)(phi - plo);
+    const int b = P0 & 7;
     const size_t ro = (size_t)(dr & (BSLOTS - 1)) * bs.LDB;
-    const double* rI = bs.TI + ro;
-    const double* r1 = bs.T1 + ro;
-    const double* rA = bs.TA + ro;
-    const int LD8 = bs.LD8;
-#define RP_BLD(row, p) (((unsigned)((p) - plo) <= span) ? (row)[((p) & 7) * LD8 + ((p) >> 3)] : 0.)
-    {  // bulge ends (0,s) and (s,0); 1xn ends (1,s-1) and (s-1,1)
+    const RingPtr rI = ring_ptr(bs.TI + ro + (P0 >> 3));   // only dereferenced at valid elements
+    const RingPtr r1 = ring_ptr(bs.T1 + ro + (P0 >> 3));
+    const RingPtr rA = ring_ptr(bs.TA + ro + (P0 >> 3));
+#define RP_IX(e) (((e) & 7) * LD8 + ((e) >> 3))
+    {  // bulge ends (0,s),(s,0): elements r and r+s; 1xn ends (1,s-1),(s-1,1): elements r+1 and r+s-1
+      int ixL[BR + 1], ixR[BR + 1];
+#pragma unroll
+      for (int j = 0; j <= BR; j++) {
+        ixL[j] = RP_IX(b + j);           // element j
+        ixR[j] = RP_IX(b + s - 1 + j);   // element s-1+j
+      }
       const double wa = bs.gA[s], w1 = bs.g1[s];
+      const unsigned xl = (unsigned)(0 - clo), xr = (unsigned)(s - 1 - clo);  // (element) - clo of ixL[0], ixR[0]
 #pragma unroll
       for (int r = 0; r < BR; r++) {
-        const double a = RP_BLD(rA, P0 + r) + RP_BLD(rA, P0 + r + s);
-        tot[r] += fA[r * NGP] * (wa * a);
+        const double x0 = ring_ld(rA, ixL[r], xl + r, span), x1 = ring_ld(rA, ixR[r + 1], xr + r + 1, span);
+        tot[r] += fA[r * NGP] * (wa * (x0 + x1));
       }
       if (s >= 4) {
 #pragma unroll
         for (int r = 0; r < BR; r++) {
-          const double a = RP_BLD(r1, P0 + r + 1) + RP_BLD(r1, P0 + r + s - 1);
-          tot[r] += f1[r * NGP] * (w1 * a);
+          const double x0 = ring_ld(r1, ixL[r + 1], xl + r + 1, span), x1 = ring_ld(r1, ixR[r], xr + r, span);
+          tot[r] += f1[r * NGP] * (w1 * (x0 + x1));
         }
       }
     }
@@ -236,26 +269,34 @@ RP_HD void interior_item(const BandShared& bs, int n, int cp, int d, const Segs&
 #pragma unroll
       for (int r = 0; r < BR; r++) acc[r] = 0.;
 #pragma unroll
-      for (int r = 0; r < BR - 1; r++) win[r] = RP_BLD(rI, P0 + 2 + r);
+      for (int r = 0; r < BR - 1; r++) win[r] = ring_ld(rI, RP_IX(b + 2 + r), (unsigned)(2 + r - clo), span);
       win[BR - 1] = 0.;
-      const double* gw = bs.G + s * (s + 1) / 2;
-      const int tend = s - 2;
-      int t = 2;
+      // step t loads element t+7; within an unrolled block of 8 steps the 8 element offsets are
+      // loop-invariant (the row pointer advances by one per block)
+      int off[BR];
+#pragma unroll
+      for (int u = 0; u < BR; u++) { off[u] = RP_IX(b + 9 + u); keep_in_reg(off[u]); }
+      const double* gw = bs.G + s * (s + 1) / 2 + 2;   // weight of tap 2+x at gw[x]
+      RingPtr pI = rI;
+      unsigned cm = (unsigned)(9 - clo);               // (element of step u) - clo = cm + u
+      const int nst = s - 3;                           // number of steps
+      int x = 0;
 #pragma unroll 1
-      for (; t + BR - 1 <= tend; t += BR) {
+      for (; x + BR <= nst; x += BR) {
 #pragma unroll
         for (int u = 0; u < BR; u++) {
-          win[(u + BR - 1) & (BR - 1)] = RP_BLD(rI, P0 + t + u + BR - 1);
-          const double gv = gw[t + u];
+          win[(u + BR - 1) & (BR - 1)] = ring_ld(pI, off[u], cm + u, span);
+          const double gv = gw[u];
 #pragma unroll
           for (int r = 0; r < BR; r++) acc[r] += gv * win[(u + r) & (BR - 1)];
         }
+        ring_adv(pI, 1); cm += BR; gw += BR;
       }
 #pragma unroll
       for (int u = 0; u < BR - 1; u++) {
-        if (t + u <= tend) {
-          win[(u + BR - 1) & (BR - 1)] = RP_BLD(rI, P0 + t + u + BR - 1);
-          const double gv = gw[t + u];
+        if (x + u < nst) {
+          win[(u + BR - 1) & (BR - 1)] = ring_ld(pI, off[u], cm + u, span);
+          const double gv = gw[u];
 #pragma unroll
           for (int r = 0; r < BR; r++) acc[r] += gv * win[(u + r) & (BR - 1)];
         }
@@ -263,7 +304,7 @@ RP_HD void interior_item(const BandShared& bs, int n, int cp, int d, const Segs&
 #pragma unroll
       for (int r = 0; r < BR; r++) tot[r] += fI[r * NGP] * acc[r];
     }
-#undef RP_BLD
+#undef RP_IX
   }
 }
 
@@ -308,7 +349,7 @@ RP_HD double inside_specials_band(const C& c, const BandShared& bs, int d, int i
 }
 
 template <class C>
-RP_HD double outside_specials_band(const C& c, const BandShared& bs, int d, int k, double qbv) {
+RP_HD double outside_specials_band(const C& c, const BandShared& bs, int d, int k) {
   const SmallModel& M = *bs.sm;
   const int n = c.n, l = k + d;
   const int type = pair_type(base(c, k), base(c, l));
@@ -319,7 +360,7 @@ RP_HD double outside_specials_band(const C& c, const BandShared& bs, int d, int 
     if (k >= c.cp && k - c.cp < maxpo) maxpo = k - c.cp;
     if (l < c.cp && c.cp - 2 - l < maxu2) maxu2 = c.cp - 2 - l;
   }
-  if (maxpo < 1 || maxu2 < 0 || qbv == 0.) return 0.;
+  if (maxpo < 1 || maxu2 < 0) return 0.;
   const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
   double v[RP_N_SPECIAL], w[RP_N_SPECIAL];
 #pragma unroll
@@ -355,7 +396,7 @@ RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int
     double v;
     if (c.dbg & 8) v = 0.;
     else if (SIGN > 0) v = inside_specials_band(c, bs, d, i);
-    else v = outside_specials_band(c, bs, d, i, TB(c, T_QB, d, i));
+    else v = outside_specials_band(c, bs, d, i);
     bs.ipart[(size_t)NSLICE * BR * bs.NGP + seg_slot(sg, bs, i)] = v;
   }
   if (smax >= 2) {
@@ -394,6 +435,12 @@ RP_HD double band_interior_sum(const C& c, const BandShared& bs, int d, const Se
   }
   return s;
 }
+
+// quick phase between two diagonals: collect the partial interior sums of the diagonal whose
+// items have just run (dsum, skipped if < 0) into sIv, and set up the closing factors of the next
+// one (dnext, skipped if < 0).  After it the partial-sum buffer is free again.
+template <int SIGN, class C>
+RP_HD void band_collect(const C& c, const BandShared& bs, int dsum, int dnext, int tid, int T);
 
 // closing-pair factors of the cells of diagonal d (whose interior sums are built next)
 template <class C>
@@ -436,7 +483,7 @@ RP_HD void band_cfac_outside(const C& c, const BandShared& bs, int d, int tid, i
     if (k < sg.b[kk + 1]) {
       const int l = k + d;
       const int type = pair_type(base(c, k), base(c, l));
-      if (type && k > 1 && l < n && TB(c, T_QB, d, k) != 0.) {
+      if (type && k > 1 && l < n) {   // (a pair with qb = 0 gets out = 0 when it is finished, whatever its sums)
         const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
         fI = M.mmI[t2][sq1][sp1];
         f1 = M.mm1n[t2][sq1][sp1];
@@ -461,7 +508,6 @@ template <class C>
 RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
   const int T = sh.T, n = c.n, cells = n - d;
   const SmallModel& M = *bs.sm;
-  const Segs sg = make_segs(n, c.cp, d);
   const int u = d - 1;  // hairpin size
   const int e = d - band_start_inside(d);
   const int vprev = (d & 1) ? V_U0 : V_U1, vcur = (d & 1) ? V_U1 : V_U0;
@@ -490,7 +536,7 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
 #pragma unroll
     for (int a = 0; a < BAND - 1; a++) sQ += M.scale_small[a + 1] * nq[a];
     const int type = pair_type(base(c, i), base(c, j));
-    const double sI = type ? band_interior_sum<1>(c, bs, d, sg, i) : 0.;
+    const double sI = type ? bs.sIv[i] : 0.;
     const double scale2 = M.scale_small[2];
     double qb = 0.;
     if (type) {
@@ -539,14 +585,12 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
     TB(c, T_QQ, d, i) = qq;
     TB(c, T_Q, d, i) = scd + qq + sQ;
   }
-  if (d + 1 <= n - 1) band_cfac_inside(c, bs, d + 1, tid, T);
 }
 
 template <class C>
 RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
   const int T = sh.T, n = c.n, cells = n - d;
   const SmallModel& M = *bs.sm;
-  const Segs sg = make_segs(n, c.cp, d);
   for (int x = tid; x < cells; x += T) {
     const int k = 1 + x, l = k + d;
     const bool mlr = l < n && ss(c, l, l + 1);
@@ -571,7 +615,7 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     // ---- combine
     const int type = pair_type(base(c, k), base(c, l));
     double sI = 0.;
-    if (type && qbv != 0.) sI = band_interior_sum<-1>(c, bs, d, sg, k);
+    if (type && qbv != 0.) sI = bs.sIv[k];
     const double scale2 = M.scale_small[2];
     const double PL = mlr ? plp * M.mlb1 + mcp : 0.;
     const double PR = mlr ? sP : 0.;
@@ -606,7 +650,19 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     if (wide) { TB(c, T_OUTI, d, k) = fI; TB(c, T_OUT1N, d, k) = f1; TB(c, T_OUTAU, d, k) = fA; }
     TB(c, T_MC, d, k) = mc;
   }
-  if (d - 1 > TURN) band_cfac_outside(c, bs, d - 1, tid, T);
+}
+
+template <int SIGN, class C>
+RP_HD void band_collect(const C& c, const BandShared& bs, int dsum, int dnext, int tid, int T) {
+  if (dsum >= 0) {
+    const Segs sg = make_segs(c.n, c.cp, dsum);
+    const int cells = c.n - dsum;
+    for (int x = tid; x < cells; x += T) bs.sIv[1 + x] = band_interior_sum<SIGN>(c, bs, dsum, sg, 1 + x);
+  }
+  if (dnext >= 0) {
+    if (SIGN > 0) band_cfac_inside(c, bs, dnext, tid, T);
+    else band_cfac_outside(c, bs, dnext, tid, T);
+  }
 }
 
 }  // namespace rp

@@ -764,17 +764,18 @@ RP_HD void inside_cells(C& c, const Shared& sh, int d, int ct, int nct) {
 // Step d finalises Qr(d+cp), Qrout(d+cp-1), Ql(cp-1-d), Qlout(cp-d).  Each of the
 // four sums is split over `np` threads (fixed partition => deterministic);
 // partial (job, lane) goes to red[(job*np+lane)*rs].
-template <class C>
-RP_HD double nick_close(const C& c, int p, int r) {
+template <class C, class MT>
+RP_HD double nick_close(const C& c, const MT& M, int p, int r) {
   const int tp = pair_type(base(c, p), base(c, r));
   if (!tp || r - p <= TURN) return 0.;
   const double o = TB(c, T_OUT, r - p, p);
   if (o == 0.) return 0.;
   return o * VEC(c, V_SCALE, 2) *
-         ext_stem(*c.M, rtype(tp), ss(c, r - 1, r) ? base(c, r - 1) : -1, ss(c, p, p + 1) ? base(c, p + 1) : -1);
+         ext_stem(M, rtype(tp), ss(c, r - 1, r) ? base(c, r - 1) : -1, ss(c, p, p + 1) ? base(c, p + 1) : -1);
 }
-template <class C>
-RP_HD void outside_nick1(C& c, double* red, int rs, int np, int d, int ct, int nct) {
+// (M: the model ext_stem reads -- DevModel, or the band kernel's shared-memory copy)
+template <class C, class MT>
+RP_HD void outside_nick1(C& c, const MT& M, double* red, int rs, int np, int d, int ct, int nct) {
   if (c.cp <= 0) return;
   const int n = c.n, cp = c.cp;
   for (int w = ct; w < 4 * np; w += nct) {
@@ -784,14 +785,14 @@ RP_HD void outside_nick1(C& c, double* red, int rs, int np, int d, int ct, int n
       const int r = d + cp;
       if (r >= cp && r <= n)
         for (int p = 1 + lane; p < cp; p += np) {
-          const double v = nick_close(c, p, r);
+          const double v = nick_close(c, M, p, r);
           if (v != 0.) s += v * (p + 1 <= cp - 1 ? TB(c, T_Q, cp - 2 - p, p + 1) : 1.0);
         }
     } else if (job == 1) {   // Ql(p), p = cp-1-d
       const int p = cp - 1 - d;
       if (p >= 1 && p < cp)
         for (int rr = cp + lane; rr <= n; rr += np) {
-          const double v = nick_close(c, p, rr);
+          const double v = nick_close(c, M, p, rr);
           if (v != 0.) s += v * (cp <= rr - 1 ? TB(c, T_Q, rr - 1 - cp, cp) : 1.0);
         }
     } else if (job == 2) {   // part of Qrout(l), l = d+cp-1, that uses Qr(r), r >= l+2 (earlier steps)

@@ -108,7 +108,7 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
   // ---- outside: longest spans first
   for (int d = n - 1; d >= TURN + 1; d--) {
     if (c.cp > 0) {
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, sh.red, 1, 32, d, tid, T); });
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, sh.red, 1, 32, d, tid, T); });
       ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
     }
     if ((n - 1 - d) % BAND == 0) {  // a band of diagonals d, d-1, ..., d-BAND+1 starts here
@@ -154,13 +154,25 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     });
     c.S = sh.S;
   }
-  ex.phase(PH_PROLOGUE2, [&](int tid) {
-    prologue2(c, tid, T);
-    if (TURN + 1 <= n - 1) band_cfac_inside(c, bs, TURN + 1, tid, T);
-  });
+  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, tid, T); });
 
-  // ---- inside
-  for (int d = TURN + 1; d <= n - 1; d++) {
+  // Schedule: the completion ("finish") of diagonal d runs one step late, in the same long phase
+  // as the interior items of the next diagonal, so that its HBM/L2 round trips and the nick sums
+  // hide behind the items' arithmetic.  Per diagonal: one long phase, then one quick phase that
+  // collects the items' partial sums (freeing the partial buffer for the split-sum band phases,
+  // which follow every BAND diagonals) and sets up the next diagonal's closing factors.
+  // ---- inside: diagonals TURN+1 .. n-1
+  ex.phase(PH_CFAC, [&](int tid) { band_collect<1>(c, bs, -1, TURN + 1 <= n - 1 ? TURN + 1 : -1, tid, T); });
+  for (int d = TURN + 1; d <= n; d++) {
+    const int dfin = d - 1 >= TURN + 1 ? d - 1 : -1;   // diagonal to complete in this step
+    const int dnew = d <= n - 1 ? d : -1;              // diagonal whose items run in this step
+    ex.phase(PH_INSIDE_A, [&](int tid) {
+      if (dfin >= 0) band_inside_B(c, sh, bs, dfin, wide, tid);
+      if (dnew >= 0) band_interior_A<1>(c, bs, dnew, tid, T);
+    });
+    if (dnew < 0) break;
+    ex.phase(PH_CFAC, [&](int tid) { band_collect<1>(c, bs, dnew, d + 1 <= n - 1 ? d + 1 : -1, tid, T); });
+    // split sums of diagonals d .. d+BAND-1: every operand lies on a diagonal < d, complete now
     if (d == band_start_inside(d)) {
       const int rows = n - d;
       const int chunk = make_split(rows, T).Cp;
@@ -170,8 +182,6 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
         ex.phase(PH_BAND_B, [&](int tid) { inside_band_B(c, sh, d, i0, C, tid); });
       }
     }
-    ex.phase(PH_INSIDE_A, [&](int tid) { band_interior_A<1>(c, bs, d, tid, T); });
-    ex.phase(PH_INSIDE_B, [&](int tid) { band_inside_B(c, sh, bs, d, wide, tid); });
   }
   inside_end(c);
   if (logz) {
@@ -180,14 +190,17 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     });
   }
 
-  // ---- outside
-  ex.phase(PH_CFAC, [&](int tid) { band_cfac_outside(c, bs, n - 1, tid, T); });
-  for (int d = n - 1; d >= TURN + 1; d--) {
-    if (c.cp > 0) {
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, sh.red, 1, 32, d, tid, T); });
-      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
-    }
-    if ((n - 1 - d) % BAND == 0) {
+  // ---- outside: diagonals n-1 .. TURN+1; step d completes diagonal d+1 and runs the items of d.
+  // Nick sums of diagonal x (outside_nick1/2, they need out of every diagonal > x) ride along one
+  // step late as well: first half in the long phase of step x-1, second half in the quick phase
+  // after it; their results are first read when diagonal x-1 is completed, in step x-2.
+  ex.phase(PH_CFAC, [&](int tid) { band_collect<-1>(c, bs, -1, n - 1 >= TURN + 1 ? n - 1 : -1, tid, T); });
+  for (int d = n - 1; d >= TURN; d--) {
+    const int dfin = d + 1 <= n - 1 ? d + 1 : -1;
+    const int dnew = d >= TURN + 1 ? d : -1;
+    const bool nick = c.cp > 0 && dfin >= 0;
+    // split sums of diagonals d .. d-BAND+1: operands on diagonals >= d+2, complete after the previous step
+    if (dnew >= 0 && (n - 1 - d) % BAND == 0) {
       const int rows = n - d + BAND - 1;
       const int chunk = make_split(rows, T).Cp;
       for (int r0 = 0; r0 < rows; r0 += chunk) {
@@ -196,8 +209,16 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
         ex.phase(PH_BAND_B, [&](int tid) { outside_band_B(c, sh, d, r0, C, tid); });
       }
     }
-    ex.phase(PH_OUTSIDE_A, [&](int tid) { band_interior_A<-1>(c, bs, d, tid, T); });
-    ex.phase(PH_OUTSIDE_B, [&](int tid) { band_outside_B(c, sh, bs, d, wide, tid); });
+    ex.phase(PH_OUTSIDE_A, [&](int tid) {
+      if (dfin >= 0) band_outside_B(c, sh, bs, dfin, wide, tid);
+      if (nick && tid < 128) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
+      if (dnew >= 0) band_interior_A<-1>(c, bs, dnew, tid, T);
+    });
+    if (dnew < 0) break;
+    ex.phase(PH_CFAC, [&](int tid) {
+      band_collect<-1>(c, bs, dnew, d - 1 >= TURN + 1 ? d - 1 : -1, tid, T);
+      if (nick) outside_nick2(c, sh.red, 1, 32, dfin, tid, T);
+    });
   }
   emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *bs.sm);
 }
@@ -238,7 +259,7 @@ RP_HD void solve_lockstep(Exec& ex, Get get, const Problem* probs, const uint8_t
 
   for (int d = n - 1; d >= TURN + 1; d--) {
     if (cp > 0) {
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(get(tid % G), sh.red + (tid % G), G, 1, d, tid / G, nct); });
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(get(tid % G), *get(tid % G).M, sh.red + (tid % G), G, 1, d, tid / G, nct); });
       ex.phase(PH_NICK2, [&](int tid) { outside_nick2(get(tid % G), sh.red + (tid % G), G, 1, d, tid / G, nct); });
     }
     ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_cells(get(tid % G), sh, d, tid / G, nct); });
