@@ -351,36 +351,45 @@ RP_HD void multi_dot(const double* A, int sa, const double* B, int sb, int tb, i
 }
 
 // The same when the shifts advance along the stream itself (tb == sb):
-//   acc[t] += sum_{x<cnt} A[x*sa] * B[(x+t)*sb],  t < nu <= 8
-// B is walked ONCE with an 8-deep register window (2 loads per 8 FMAs instead of 9).
-// acc[t], t >= nu, receives partial sums that the caller ignores.
-RP_HD void multi_dot_slide(const double* A, int sa, const double* B, int sb, int cnt, int nu, double* acc) {
+//   acc[t] += sum_{x<cnt} A[x*sa] * B[(x+t)*sb],  t = 0..7
+// B is walked ONCE with an 8-deep register window (2 loads per 8 FMAs instead of 9), and the 16
+// loads of a block of 8 steps are issued together (one memory round trip per block).
+// Window element z = x+t is read only if zlo <= z <= zhi (else it counts as 0); the caller
+// ignores the acc[t] it did not ask for.  Negative strides walk a stream backwards.
+RP_HD void multi_dot_slide(const double* A, long sa, const double* B, long sb, int cnt, int zlo, int zhi, double* acc) {
   if (cnt <= 0) return;
-  const int last = cnt + nu - 2;  // largest B element any requested term touches
   double win[8];
 #pragma unroll
-  for (int t = 0; t < 7; t++) win[t] = t <= last ? B[(long)t * sb] : 0.;
+  for (int t = 0; t < 7; t++) win[t] = (t >= zlo && t <= zhi) ? B[t * sb] : 0.;
   win[7] = 0.;
-  const double* bp = B + (long)7 * sb;  // next element to enter the window
-  int y = 7;
+  const double* bp = B + 7 * sb;  // next element to enter the window
+  int z = 7;
   int x = 0;
 #pragma unroll 1
   for (; x + 8 <= cnt; x += 8) {
+    double nb[8], na[8];
+    if (z >= zlo && z + 7 <= zhi) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) nb[u] = bp[u * sb];
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; u++) nb[u] = (z + u >= zlo && z + u <= zhi) ? bp[u * sb] : 0.;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) na[u] = A[u * sa];
+    bp += 8 * sb; A += 8 * sa; z += 8;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      win[(u + 7) & 7] = y <= last ? *bp : 0.;
-      bp += sb; y++;
-      const double a = *A;
-      A += sa;
+      win[(u + 7) & 7] = nb[u];
 #pragma unroll
-      for (int t = 0; t < 8; t++) acc[t] += a * win[(u + t) & 7];
+      for (int t = 0; t < 8; t++) acc[t] += na[u] * win[(u + t) & 7];
     }
   }
 #pragma unroll
   for (int u = 0; u < 7; u++) {
     if (x + u < cnt) {
-      win[(u + 7) & 7] = y <= last ? *bp : 0.;
-      bp += sb; y++;
+      win[(u + 7) & 7] = (z >= zlo && z <= zhi) ? *bp : 0.;
+      bp += sb; z++;
       const double a = *A;
       A += sa;
 #pragma unroll
@@ -1095,6 +1104,14 @@ RP_HD void unstru_hairpin(C& c, int tid, int T) {
     TB(c, T_DG, d, i) = v;
   }
 }
+// class of the loop shape (u1,u2), u1+u2 <= MAXLOOP: the rule of build_dev_model (dev_model.cpp), in registers
+RP_HD int loop_class(int u1, int u2) {
+  const int ul = u1 > u2 ? u1 : u2, us = u1 > u2 ? u2 : u1;
+  if (us == 0) return ul >= 2 ? CLS_BULGE : CLS_SPECIAL;
+  if (us == 1) return ul >= 3 ? CLS_1N : CLS_SPECIAL;
+  return (us == 2 && (ul == 2 || ul == 3)) ? CLS_SPECIAL : CLS_GENERIC;
+}
+
 // The table-driven shapes (9 small loops, dev_model.h) of the gap sums: item (side, gap size
 // ug <= 3, gap start a, slice) sums the loops of all special shapes with that gap size over
 // every `nsl`-th position of the free pair end and leaves the partial in a scratch row of T_RR
@@ -1119,7 +1136,7 @@ RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
         const int p = a, k = b, u1 = ug, lmin = k + TURN + 1;
         const int sp1 = base(c, k - 1), si1 = base(c, p + 1);
         for (int u2 = 0; u2 <= 3; u2++) {
-          if (c.M->gcls[u1][u2] != CLS_SPECIAL) continue;
+          if (loop_class(u1, u2) != CLS_SPECIAL) continue;
           const int lmax = n - 1 - u2, sidx = special_index(u1, u2);
 #pragma unroll 4
           for (int l = lmin + sl; l <= lmax; l += nsl) {
@@ -1134,7 +1151,7 @@ RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
         const int l = a, o = b, u2 = ug;
         const int sq1 = base(c, l + 1), sj1 = base(c, o - 1);
         for (int u1 = 0; u1 <= 3; u1++) {
-          if (c.M->gcls[u1][u2] != CLS_SPECIAL) continue;
+          if (loop_class(u1, u2) != CLS_SPECIAL) continue;
           const int pmax = l - TURN - 2 - u1, sidx = special_index(u1, u2);
 #pragma unroll 4
           for (int p = 1 + sl; p <= pmax; p += nsl) {
@@ -1158,9 +1175,9 @@ RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
 //   side 0:  sum_l  outX(p, l+1+u2) * qbX(k, l)          (both advance one diagonal per l)
 //   side 1:  sum_p  outX(p, o)      * qbX(p+1+u1, l)     (both step one diagonal down, one cell right)
 // Runs of up to 8 shifts of one class share the streamed operand (multi_dot).
+// gfull: the weights g(u1,u2) incl. scale, row stride GROW_LD (DevModel::gfull, or a shared-memory copy)
 template <class C>
-RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
-  const DevModel& M = *c.M;
+RP_HD void unstru_gaps(C& c, const double* gfull, int side, int tid, int T) {
   const int n = c.n, ds = c.dstep(), ps = c.pstep();
   const int items = (c.dbg & 4) ? 0 : n * (MAXLOOP + 1);
   const int tabO[3] = {T_OUTI, T_OUT1N, T_OUTAU};
@@ -1176,21 +1193,21 @@ RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
       const int lmin = k + TURN + 1;
       for (int u2 = 0; u1 + u2 <= MAXLOOP;) {
         if (n - 1 - u2 < lmin) break;
-        const int cls = M.gcls[u1][u2];
+        const int cls = loop_class(u1, u2);
         if (cls != CLS_SPECIAL) {
           // run of up to 8 consecutive u2 of the same class
           int nu = 1;
-          while (nu < 8 && u1 + u2 + nu <= MAXLOOP && M.gcls[u1][u2 + nu] == cls && n - 1 - (u2 + nu) >= lmin) nu++;
+          while (nu < 8 && u1 + u2 + nu <= MAXLOOP && loop_class(u1, u2 + nu) == cls && n - 1 - (u2 + nu) >= lmin) nu++;
           double av[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
           const double* Q = c.ptr(tabQ[cls], lmin - k, k);           // qbX(k,l), one diagonal per l
           const double* O = c.ptr(tabO[cls], lmin + 1 + u2 - p, p);  // outX(p,l+1+u2), one diagonal per u2
           const int cmain = n - 1 - (u2 + nu - 1) - lmin + 1;        // l range valid for every u2 of the run
-          multi_dot_slide(Q, ds, O, ds, cmain, nu, av);
+          multi_dot_slide(Q, ds, O, ds, cmain, 0, cmain + nu - 2, av);
           for (int t = 0; t < nu; t++) {
             // the shorter shifts reach further: l up to n-1-(u2+t)
             const int cnt = n - 1 - (u2 + t) - lmin + 1;
             if (cnt > cmain) av[t] += dot_range(Q, ds, O + (long)t * ds, ds, cmain, cnt, 0, 1);
-            acc += M.gfull[u1][u2 + t] * av[t];
+            acc += gfull[u1 * GROW_LD + u2 + t] * av[t];
           }
           u2 += nu;
         } else {
@@ -1201,19 +1218,27 @@ RP_HD void unstru_gaps(C& c, int side, int tid, int T) {
       const int l = a, o = b, u2 = ug;
       for (int u1 = 0; u1 + u2 <= MAXLOOP;) {
         if (l - TURN - 2 - u1 < 1) break;  // k = p+1+u1 <= l-TURN-1 needs p >= 1
-        const int cls = M.gcls[u1][u2];
+        const int cls = loop_class(u1, u2);
         if (cls != CLS_SPECIAL) {
           int nu = 1;
-          while (nu < 8 && u1 + nu + u2 <= MAXLOOP && M.gcls[u1 + nu][u2] == cls && l - TURN - 2 - (u1 + nu) >= 1) nu++;
+          while (nu < 8 && u1 + nu + u2 <= MAXLOOP && loop_class(u1 + nu, u2) == cls && l - TURN - 2 - (u1 + nu) >= 1) nu++;
           double av[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
           const double* O = c.ptr(tabO[cls], o - 1, 1);               // outX(p,o): one diagonal down, one cell right per p
           const double* Q = c.ptr(tabQ[cls], l - 2 - u1, 2 + u1);     // qbX(p+1+u1,l); per u1 likewise
           const int cmain = l - TURN - 2 - (u1 + nu - 1);             // p = 1..cmain valid for every u1 of the run
-          multi_dot_slide(O, ps - ds, Q, ps - ds, cmain, nu, av);
+          // walked from the largest p downwards: then the lanes of a warp (consecutive gaps) read
+          // consecutive addresses.  Reversed window: element z holds Q[cmain+6-z], shift t' = 7-t.
+          if (cmain > 0) {
+            const long st = ps - ds;
+            double rv[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+            multi_dot_slide(O + (long)(cmain - 1) * st, -st, Q + (long)(cmain + 6) * st, -st, cmain, 8 - nu, cmain + 6, rv);
+#pragma unroll
+            for (int t = 0; t < 8; t++) av[t] = rv[7 - t];
+          }
           for (int t = 0; t < nu; t++) {
             const int cnt = l - TURN - 2 - (u1 + t);
             if (cnt > cmain) av[t] += dot_range(O, ps - ds, Q + (long)t * (ps - ds), ps - ds, cmain, cnt, 0, 1);
-            acc += M.gfull[u1 + t][u2] * av[t];
+            acc += gfull[(u1 + t) * GROW_LD + u2] * av[t];
           }
           u1 += nu;
         } else {

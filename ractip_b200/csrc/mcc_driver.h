@@ -21,9 +21,10 @@ enum {
 };
 
 // outputs of finished problems; probs[g] is lane g's problem (G = 1 in the general kernel)
-// `SM`: the model the table-driven gap loops read (DevModel, or the band kernel's shared-memory copy)
+// `SM`: the model the table-driven gap loops read (DevModel, or the band kernel's shared-memory copy);
+// `gfull`: DevModel::gfull or a shared-memory copy of it
 template <class Exec, class Get, class MT>
-RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* dense, const MT& SM) {
+RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* dense, const MT& SM, const double* gfull) {
   const int nct = ex.nthreads() / G;
   if (probs[0].kind == KIND_LINEAR) {
     ex.phase(PH_WRITE_BP, [&](int tid) {
@@ -39,8 +40,8 @@ RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* d
         unstru_hairpin(get(tid % G), tid / G, nct);
         unstru_gap_specials(get(tid % G), SM, tid / G, nct);
       });
-      ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(get(tid % G), 0, tid / G, nct); });
-      ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(get(tid % G), 1, tid / G, nct); });
+      ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(get(tid % G), gfull, 0, tid / G, nct); });
+      ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(get(tid % G), gfull, 1, tid / G, nct); });
       ex.phase(PH_UN_DOMROWS, [&](int tid) { unstru_dom_rows(get(tid % G), tid / G, nct); });
       ex.phase(PH_UN_DOMCOLS, [&](int tid) { unstru_dom_cols(get(tid % G), tid / G, nct); });
       ex.phase(PH_UN_MLTAB, [&](int tid) { unstru_ml_tables(get(tid % G), tid / G, nct); });
@@ -128,7 +129,7 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
       ex.phase(PH_OUTSIDE_B, [&](int tid) { outside_B(c, sh, d, i0, C, tid); });
     }
   }
-  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M);
+  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M, &c.M->gfull[0][0]);
 }
 
 // ---------------------------------------------------------------------------
@@ -220,7 +221,15 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
       if (nick) outside_nick2(c, sh.red, 1, 32, dfin, tid, T);
     });
   }
-  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *bs.sm);
+  // the ring is free now: it takes a copy of the gap-sum weights
+  const double* gfull = &c.M->gfull[0][0];
+  if (wide && (size_t)3 * BSLOTS * bs.LDB >= (size_t)(MAXLOOP + 1) * GROW_LD) {
+    ex.phase(PH_STAGE, [&](int tid) {
+      for (int x = tid; x < (MAXLOOP + 1) * GROW_LD; x += T) bs.TI[x] = (&c.M->gfull[0][0])[x];
+    });
+    gfull = bs.TI;
+  }
+  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *bs.sm, gfull);
 }
 
 // ---------------------------------------------------------------------------
@@ -264,7 +273,7 @@ RP_HD void solve_lockstep(Exec& ex, Get get, const Problem* probs, const uint8_t
     }
     ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_cells(get(tid % G), sh, d, tid / G, nct); });
   }
-  emit_outputs(ex, get, probs, G, dense, *get(0).M);
+  emit_outputs(ex, get, probs, G, dense, *get(0).M, &get(0).M->gfull[0][0]);
 }
 
 }  // namespace rp
