@@ -1202,13 +1202,11 @@ RP_HD void unstru_gaps(C& c, const double* gfull, int side, int tid, int T) {
           const double* Q = c.ptr(tabQ[cls], lmin - k, k);           // qbX(k,l), one diagonal per l
           const double* O = c.ptr(tabO[cls], lmin + 1 + u2 - p, p);  // outX(p,l+1+u2), one diagonal per u2
           const int cmain = n - 1 - (u2 + nu - 1) - lmin + 1;        // l range valid for every u2 of the run
-          multi_dot_slide(Q, ds, O, ds, cmain, 0, cmain + nu - 2, av);
-          for (int t = 0; t < nu; t++) {
-            // the shorter shifts reach further: l up to n-1-(u2+t)
-            const int cnt = n - 1 - (u2 + t) - lmin + 1;
-            if (cnt > cmain) av[t] += dot_range(Q, ds, O + (long)t * ds, ds, cmain, cnt, 0, 1);
-            acc += gfull[u1 * GROW_LD + u2 + t] * av[t];
-          }
+          // the shorter shifts reach further (l up to n-1-(u2+t)): walk to the end of the longest one;
+          // window elements past the last diagonal count as 0
+          const int X = cmain + nu - 1;
+          multi_dot_slide(Q, ds, O, ds, X, 0, X - 1, av);
+          for (int t = 0; t < nu; t++) acc += gfull[u1 * GROW_LD + u2 + t] * av[t];
           u2 += nu;
         } else {
           u2++;  // table-driven shapes: summed by unstru_gap_specials into the scratch rows
@@ -1227,19 +1225,16 @@ RP_HD void unstru_gaps(C& c, const double* gfull, int side, int tid, int T) {
           const double* Q = c.ptr(tabQ[cls], l - 2 - u1, 2 + u1);     // qbX(p+1+u1,l); per u1 likewise
           const int cmain = l - TURN - 2 - (u1 + nu - 1);             // p = 1..cmain valid for every u1 of the run
           // walked from the largest p downwards: then the lanes of a warp (consecutive gaps) read
-          // consecutive addresses.  Reversed window: element z holds Q[cmain+6-z], shift t' = 7-t.
+          // consecutive addresses.  Reversed window: element z holds Q[X+6-z], shift t' = 7-t.
           if (cmain > 0) {
             const long st = ps - ds;
+            const int X = cmain + nu - 1;   // steps of the longest shift (t = 0)
             double rv[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-            multi_dot_slide(O + (long)(cmain - 1) * st, -st, Q + (long)(cmain + 6) * st, -st, cmain, 8 - nu, cmain + 6, rv);
+            multi_dot_slide(O + (long)(X - 1) * st, -st, Q + (long)(X + 6) * st, -st, X, 7, X + 6, rv);
 #pragma unroll
             for (int t = 0; t < 8; t++) av[t] = rv[7 - t];
           }
-          for (int t = 0; t < nu; t++) {
-            const int cnt = l - TURN - 2 - (u1 + t);
-            if (cnt > cmain) av[t] += dot_range(O, ps - ds, Q + (long)t * (ps - ds), ps - ds, cmain, cnt, 0, 1);
-            acc += gfull[(u1 + t) * GROW_LD + u2] * av[t];
-          }
+          for (int t = 0; t < nu; t++) acc += gfull[(u1 + t) * GROW_LD + u2] * av[t];
           u1 += nu;
         } else {
           u1++;
