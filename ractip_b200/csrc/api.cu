@@ -395,6 +395,9 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   *out = nullptr;
   int rc = check_pairs(pairs, n_pairs, opts);
   if (rc) return fail(ctx, rc, "rp_batch_create: bad pairs/opts");
+  for (int p = 0; p < n_pairs; p++)
+    if ((long long)pairs[p].n1 + pairs[p].n2 > rp::RP_MAX_N)
+      return fail(ctx, RP_ERR_TOO_LONG, "rp_batch_create: n1+n2 exceeds the 32-bit workspace indexing limit (12000 nt)");
   CU(cudaSetDevice(ctx->device));
   rp_batch* b = new rp_batch;
   b->ctx = ctx;

@@ -11,6 +11,9 @@
 
 #include "mcc_band.h"
 #include "mcc_core.h"
+#ifdef __CUDACC__
+#include "mcc_band_shfl.cuh"
+#endif
 
 namespace rp {
 
@@ -176,11 +179,26 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     // split sums of diagonals d .. d+BAND-1: every operand lies on a diagonal < d, complete now
     if (d == band_start_inside(d)) {
       const int rows = n - d;
-      const int chunk = make_split(rows, T).Cp;
+      int chunk = make_split(rows, T).Cp;
+#ifdef __CUDA_ARCH__
+      if (chunk > HW * (T / 32)) chunk = HW * (T / 32);   // shuffle variant: 28 rows per warp
+#endif
       for (int i0 = 1; i0 <= rows; i0 += chunk) {
         const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
-        ex.phase(PH_BAND_A, [&](int tid) { inside_band_A(c, sh, d, i0, C, tid); });
-        ex.phase(PH_BAND_B, [&](int tid) { inside_band_B(c, sh, d, i0, C, tid); });
+        ex.phase(PH_BAND_A, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          inside_band_A_shfl(c, sh, d, i0, C, tid);   // same sums, operands passed along the warp
+#else
+          inside_band_A(c, sh, d, i0, C, tid);
+#endif
+        });
+        ex.phase(PH_BAND_B, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          inside_band_B_shfl(c, sh, d, i0, C, tid);
+#else
+          inside_band_B(c, sh, d, i0, C, tid);
+#endif
+        });
       }
     }
   }
@@ -203,11 +221,26 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     // split sums of diagonals d .. d-BAND+1: operands on diagonals >= d+2, complete after the previous step
     if (dnew >= 0 && (n - 1 - d) % BAND == 0) {
       const int rows = n - d + BAND - 1;
-      const int chunk = make_split(rows, T).Cp;
+      int chunk = make_split(rows, T).Cp;
+#ifdef __CUDA_ARCH__
+      if (chunk > HW * (T / 32)) chunk = HW * (T / 32);   // shuffle variant: 28 rows per warp
+#endif
       for (int r0 = 0; r0 < rows; r0 += chunk) {
         const int C = rows - r0 < chunk ? rows - r0 : chunk;
-        ex.phase(PH_BAND_A, [&](int tid) { outside_band_A(c, sh, d, r0, C, tid); });
-        ex.phase(PH_BAND_B, [&](int tid) { outside_band_B(c, sh, d, r0, C, tid); });
+        ex.phase(PH_BAND_A, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          outside_band_A_shfl(c, sh, d, r0, C, tid);
+#else
+          outside_band_A(c, sh, d, r0, C, tid);
+#endif
+        });
+        ex.phase(PH_BAND_B, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          outside_band_B_shfl(c, sh, d, r0, C, tid);
+#else
+          outside_band_B(c, sh, d, r0, C, tid);
+#endif
+        });
       }
     }
     ex.phase(PH_OUTSIDE_A, [&](int tid) {
