@@ -277,7 +277,18 @@ int rp_sparse_plan(const rp_pair* pairs, int n_pairs, const rp_opts* opts, rp_sp
   return RP_OK;
 }
 
+static double alg_flops_mcc_uncached(int n);
 double rp_alg_flops_mcc(int n) {
+  // memoised: the O(n^2) count below used to be recomputed for all 3 problems of every pair of
+  // every one-shot call (tens of milliseconds per 1000-pair batch, more than the copies)
+  static thread_local std::vector<std::pair<int, double>> memo;
+  for (const auto& kv : memo)
+    if (kv.first == n) return kv.second;
+  const double v = alg_flops_mcc_uncached(n);
+  if (memo.size() < 4096) memo.emplace_back(n, v);
+  return v;
+}
+static double alg_flops_mcc_uncached(int n) {
   // F_mcc(n) = 6 I(n) + 2 S_in(n) + 2 S_out(n), TURN=3, MAXLOOP=30
   if (n < 5) return 0.;
   double I = 0, Sin = 0, Sout = 0;
