@@ -387,8 +387,16 @@ RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int
   const int n = c.n, cells = n - d;
   const Segs sg = make_segs(n, c.cp, d);
   const int NG = sg.G[3];
-  const int NB = (NG + 15) / 16;
-  const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
+  // an item block is GB lanes = GB consecutive groups: a half-warp, or a quarter-warp when the whole
+  // diagonal fits in 8 groups (4 slices per warp: half the instructions on the short diagonals)
+  const int GB = NG <= 8 ? 8 : 16;
+  const int NB = (NG + GB - 1) / GB;
+  const int nitems = NSLICE * NB;
+  // Thread roles of the long phase: the first `cells` threads complete the previous diagonal, the
+  // last `cells` do the small loops below; when they fit, the items go to the threads in between,
+  // so that no thread has two jobs.
+  const int Cw = (cells + 1 + 31) & ~31;   // (the previous diagonal has one more cell)
+  const int t0 = (nitems * GB + 2 * Cw <= T) ? Cw : 0;
   const int smax = SIGN > 0 ? d - 6 : n - 3 - d;
   // small loops first: their table look-ups are in flight while the row items run
   for (int x = T - 1 - tid; x < cells; x += T) {
@@ -399,10 +407,11 @@ RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int
     else v = outside_specials_band(c, bs, d, i);
     bs.ipart[(size_t)NSLICE * BR * bs.NGP + seg_slot(sg, bs, i)] = v;
   }
-  if (smax >= 2) {
-    for (int item = hw; item < NSLICE * NB; item += nhw) {
+  if (smax >= 2 && tid >= t0) {
+    const int unit = (tid - t0) / GB, hl = (tid - t0) % GB, nunits = (T - t0) / GB;
+    for (int item = unit; item < nitems; item += nunits) {
       const int q = item / NB, b = item - q * NB;
-      const int g = 16 * b + hl;
+      const int g = GB * b + hl;
       if (g >= NG) continue;
       double tot[BR];
       if (c.dbg & 1) {
@@ -508,6 +517,7 @@ template <class C>
 RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
   const int T = sh.T, n = c.n, cells = n - d;
   const SmallModel& M = *bs.sm;
+  if (c.dbg & 16) return;
   const int u = d - 1;  // hairpin size
   const int e = d - band_start_inside(d);
   const int vprev = (d & 1) ? V_U0 : V_U1, vcur = (d & 1) ? V_U1 : V_U0;
@@ -589,6 +599,7 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
 
 template <class C>
 RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
+  if (c.dbg & 16) return;
   const int T = sh.T, n = c.n, cells = n - d;
   const SmallModel& M = *bs.sm;
   for (int x = tid; x < cells; x += T) {
@@ -654,6 +665,7 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
 
 template <int SIGN, class C>
 RP_HD void band_collect(const C& c, const BandShared& bs, int dsum, int dnext, int tid, int T) {
+  if (c.dbg & 32) return;
   if (dsum >= 0) {
     const Segs sg = make_segs(c.n, c.cp, dsum);
     const int cells = c.n - dsum;

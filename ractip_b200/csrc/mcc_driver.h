@@ -245,7 +245,7 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     }
     ex.phase(PH_OUTSIDE_A, [&](int tid) {
       if (dfin >= 0) band_outside_B(c, sh, bs, dfin, wide, tid);
-      if (nick && tid < 128) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
+      if (nick && tid < 128 && !(c.dbg & 64)) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
       if (dnew >= 0) band_interior_A<-1>(c, bs, dnew, tid, T);
     });
     if (dnew < 0) break;
