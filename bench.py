@@ -331,7 +331,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             except Exception:
                 traffic = None
         roofline = {
-            "bound": "fp64_fma", "kernel": "mcc_persistent", "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
+            "bound": "fp64_fma", "kernel": "mcc_band_kernel (launch shapes <512,1> and <256,2>, timed together)", "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
             "frac": achieved / fp64_tf if fp64_tf else None, "traffic": traffic,
             "alg_flops_per_launch": alg, "launch_ms": launch_ms,
             "peak_source": "live fp64-FMA micro-benchmark on this GPU (rp_measure_peaks); "
@@ -364,8 +364,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "pairs_per_step": total_pairs, "sharding": f"shuffles r::{world}" if world > 1 else "none",
                        "collective": "one all_gather of sparse records" if world > 1 else "none",
-                       "l2": "per-step working set (workspace slots, GBs) exceeds the 126 MB L2; no flush needed",
-                       "threads_per_cta": 512},
+                       "l2": "per-step working set (workspace slots of all resident CTAs, > 1 GB) exceeds the 126 MB L2; no flush needed",
+                       "kernels": "mcc_band_kernel<512,1> (n > ~95) + mcc_band_kernel<256,2> (shorter); general kernel for n > 215"},
             "clocks": clocks,
             "e2e": {"value": e2e_d, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": out_bytes * world, "api": "rp_run_dense (reference layouts, pinned host buffer)"},

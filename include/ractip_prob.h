@@ -249,6 +249,18 @@ int rp_zscore_shuffles(const char* s1, int n1, const char* s2, int n2,
 /* Dense algorithmic flop count F_mcc(n) of SURVEY.md section 8(d). */
 double rp_alg_flops_mcc(int n);
 
+/* Which kernel a McCaskill problem of length n (n1+n2 for the two-strand     */
+/* problem of rnaduplex, src/ractip.cpp:400-458) runs on, given the per-CTA   */
+/* shared-memory limit of the device (bytes; 0 = B200's 232448).  Host        */
+/* arithmetic only.  Returns RP_KERNEL_*; *smem_bytes (may be NULL) receives   */
+/* the dynamic shared memory the band kernel would need for that length.      */
+enum {
+  RP_KERNEL_BAND_1CTA = 0,  /* shared-memory band kernel, 512 threads, 1 CTA/SM */
+  RP_KERNEL_BAND_2CTA = 1,  /* shared-memory band kernel, 256 threads, 2 CTA/SM */
+  RP_KERNEL_GENERAL = 2     /* HBM-table wavefront kernel (any length)          */
+};
+int rp_kernel_plan(int n, size_t smem_limit, size_t* smem_bytes);
+
 const char* rp_version(void);
 
 #ifdef __cplusplus

@@ -93,7 +93,7 @@ EXPORTS = [
     "rp_run_sparse", "rp_batch_create", "rp_batch_run", "rp_batch_sync",
     "rp_batch_fetch_dense", "rp_batch_fetch_sparse", "rp_batch_sparse_device", "rp_batch_fetch_logz",
     "rp_batch_destroy", "rp_last_timing", "rp_measure_peaks", "rp_zscore_shuffles",
-    "rp_alg_flops_mcc", "rp_version",
+    "rp_alg_flops_mcc", "rp_version", "rp_kernel_plan",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load() -> C.CDLL:
         "rp_zscore_shuffles": (i, [C.c_char_p, i, C.c_char_p, i, i, C.c_uint, i, i, C.c_char_p, C.c_char_p]),
         "rp_alg_flops_mcc": (C.c_double, [i]),
         "rp_version": (C.c_char_p, []),
+        "rp_kernel_plan": (i, [i, sz, P(sz)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol

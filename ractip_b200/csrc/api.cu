@@ -194,7 +194,17 @@ int grid_for(const rp_ctx* ctx, int nprob, size_t slot_bytes) {
 
 extern "C" {
 
-const char* rp_version(void) { return "ractip_b200 0.1 (sm_100a)"; }
+const char* rp_version(void) { return "ractip_b200 0.2 (sm_100a)"; }
+
+int rp_kernel_plan(int n, size_t smem_limit, size_t* smem_bytes) {
+  if (smem_limit == 0) smem_limit = 232448;
+  const size_t half_sm = (smem_limit + 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved each
+  if (n < 1) n = 1;
+  const size_t s256 = rp::band_shared_bytes(n, 256), s512 = rp::band_shared_bytes(n, 512);
+  if (s256 <= half_sm) { if (smem_bytes) *smem_bytes = s256; return RP_KERNEL_BAND_2CTA; }
+  if (smem_bytes) *smem_bytes = s512;
+  return s512 <= smem_limit ? RP_KERNEL_BAND_1CTA : RP_KERNEL_GENERAL;
+}
 
 const char* rp_strerror(int code) {
   switch (code) {
@@ -519,12 +529,10 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) { return cost(b->probs[x]) > cost(b->probs[y]); });
   if (ctx->band) {
     // class of a problem: 0 = L (512 threads, ring needs more than half an SM), 1 = S (256 threads, 2 CTAs/SM), -1 = general
-    const size_t half_sm = (ctx->smem_optin + 1024) / 2 - 1024;
     auto cls = [&](const Problem& q) {
       if (q.kind == rp::KIND_DUPLEX) return -1;
-      if (rp::band_shared_bytes(q.n, 256) <= half_sm) return 1;
-      if (rp::band_shared_bytes(q.n, 512) <= ctx->smem_optin) return 0;
-      return -1;
+      const int k = rp_kernel_plan(q.n, ctx->smem_optin, nullptr);
+      return k == RP_KERNEL_GENERAL ? -1 : k;
     };
     std::vector<int> part[3];
     for (int k : b->order) {

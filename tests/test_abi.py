@@ -82,3 +82,23 @@ def test_product_does_not_reference_the_oracle():
         text = p.read_text()
         assert "liboracle" not in text and "rp_oracle" not in text and "from oracle" not in text \
             and "import oracle" not in text and "orc_" not in text, p
+
+
+def test_kernel_plan_routes_lengths_by_shared_memory(lib):
+    """Host-side routing: short problems run two band CTAs per SM, the MicA x ompA two-strand
+    problem (209 nt) must fit the one-CTA band kernel on a B200, long ones fall to the general kernel."""
+    smem = C.c_size_t()
+    assert lib.rp_kernel_plan(72, 0, C.byref(smem)) == 1 and smem.value <= (232448 + 1024) // 2 - 1024
+    assert lib.rp_kernel_plan(137, 0, C.byref(smem)) == 0
+    assert lib.rp_kernel_plan(209, 0, C.byref(smem)) == 0 and smem.value <= 232448
+    assert lib.rp_kernel_plan(215, 0, C.byref(smem)) == 0 and smem.value <= 232448
+    assert lib.rp_kernel_plan(1500, 0, None) == 2
+    # monotone in n, and every band answer respects the limit it was given
+    prev = 1
+    for n in range(1, 400):
+        k = lib.rp_kernel_plan(n, 0, C.byref(smem))
+        assert k in (0, 1, 2) and (k >= prev or (prev == 1 and k == 0)), n
+        if k != 2:
+            assert smem.value <= 232448
+        prev = k
+    assert lib.rp_kernel_plan(72, 48 * 1024, None) == 2   # a device without the opt-in carve-out

@@ -241,3 +241,42 @@ def test_error_paths(stage, lib):
     assert stage.run_dense([], opts) == []
     with pytest.raises(RpError):
         stage.run_dense([("", "ACGU")], opts)
+
+
+@pytest.mark.parametrize("n1,n2", [(95, 1), (96, 3), (60, 40), (150, 65), (107, 108), (108, 108), (215, 1)])
+def test_kernel_class_boundaries(stage, oracle, lib, n1, n2):
+    """Lengths around the routing boundaries of rp_kernel_plan (two band CTAs per SM / one / general
+    kernel): every route gives the oracle's numbers."""
+    from ractip_b200 import default_opts
+    rng = np.random.default_rng(31 * n1 + n2)
+    opts = default_opts()
+    s1, s2 = rand_seq(rng, n1), rand_seq(rng, n2)
+    routes = {lib.rp_kernel_plan(n, 0, None) for n in (n1, n2, n1 + n2)}
+    assert routes <= {0, 1, 2}
+    r = stage.run_dense([(s1, s2)], opts)[0]
+    _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"{n1}x{n2} routes {sorted(routes)}")
+
+
+def test_band_and_general_kernels_agree(model, bundled, monkeypatch):
+    """The shared-memory band kernel and the HBM-table general kernel compute the same matrices
+    (RP_BAND=0 routes everything to the general kernel: A/B aid)."""
+    from ractip_b200 import ProbabilityStage, default_opts, zscore_shuffles
+    s1, s2 = bundled["sequences"]["MicA"], bundled["sequences"]["ompA"]
+    r1, r2 = zscore_shuffles(s1, s2, 6, 1)
+    pairs = list(zip(r1, r2)) + [(bundled["sequences"]["CopA"], bundled["sequences"]["CopT"])]
+    opts = default_opts()
+    st_band = ProbabilityStage(model)
+    a = st_band.run_dense(pairs, opts)
+    st_band.close()
+    monkeypatch.setenv("RP_BAND", "0")
+    st_gen = ProbabilityStage(model)
+    b = st_gen.run_dense(pairs, opts)
+    st_gen.close()
+    for x, y in zip(a, b):
+        for name in ("bp1", "bp2", "up1", "up2"):
+            assert np.abs(getattr(x, name).astype(np.float64) - getattr(y, name)).max() <= TOL, name
+        both = (x.hp != 0) & (y.hp != 0)
+        assert np.abs(x.hp[both].astype(np.float64) - y.hp[both]).max() <= TOL
+        mism = (x.hp != 0) != (y.hp != 0)
+        if mism.any():
+            assert _near_threshold(np.where(x.hp != 0, x.hp, y.hp)[mism], opts.th_hy).all()

@@ -52,6 +52,8 @@ ti = ts = 0
 for r in rows[2:]:
     if len(r) < len(hdr):
         continue
+    if r[ia] == "Address":   # a second kernel's section starts: only the first captured launch is summarised
+        break
     a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
     if base is None:
         base = a
@@ -79,7 +81,7 @@ for ln, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
 # --- per-function totals (line ranges from the source)
 import bisect
 funcs = []
-for fname in ("mcc_core.h", "mcc_driver.h", "kernels.cu"):
+for fname in ("mcc_core.h", "mcc_band.h", "mcc_band_shfl.cuh", "mcc_driver.h", "kernels.cu"):
     f = ROOT / "ractip_b200" / "csrc" / fname
     for no, l in enumerate(f.read_text().split("\n"), start=1):
         m = re.match(r"(?:template.*\n)?(?:RP_HD|__global__|__device__|inline).*?\b(\w+)\(", l)
