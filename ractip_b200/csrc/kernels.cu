@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(T, MINB) mcc_band_kernel(BatchDev b) {
     Ctx c;
     bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)blockIdx.x * b.slot_stride);
     c.dbg = b.dbg;
+    c.prof = b.prof;
     solve_band(ex, c, p, b.dense, b.logz, smem_raw);
   }
 }

@@ -177,6 +177,23 @@ RP_HD int seg_slot(const Segs& s, const BandShared& bs, int i) {
   return (o & (BR - 1)) * bs.NGP + s.G[k] + (o >> 3);
 }
 
+// Global load that is issued WHERE IT IS WRITTEN: at the register cap the compiler otherwise sinks
+// every load of the finish code next to its first use, which turns one L2 round trip into ten.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double ldg_now(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+#else
+inline double ldg_now(const double* p) { return *p; }
+#endif
+// the same for an optional operand: loads a harmless address when !ok and yields `dflt` (no branch)
+RP_HD double ldg_if(bool ok, const double* p, const double* safe, double dflt) {
+  const double v = ldg_now(ok ? p : safe);
+  return ok ? v : dflt;
+}
+
 // Ring element load "valid ? row[ix] : 0" of the item loops.  On the device: one predicated
 // ld.shared (no branch, no address clamp); `x <= span` (unsigned) is the validity test.
 #ifdef __CUDA_ARCH__
@@ -389,8 +406,8 @@ RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int
   const int NG = sg.G[3];
   // an item block is GB lanes = GB consecutive groups: a half-warp, or a quarter-warp when the whole
   // diagonal fits in 8 groups (4 slices per warp: half the instructions on the short diagonals)
-  const int GB = NG <= 8 ? 8 : 16;
-  const int NB = (NG + GB - 1) / GB;
+  const int gsh = NG <= 8 ? 3 : 4, GB = 1 << gsh;   // (shifts: runtime integer divisions cost ~25 dependent instructions each)
+  const int NB = (NG + GB - 1) >> gsh;
   const int nitems = NSLICE * NB;
   // Thread roles of the long phase: the first `cells` threads complete the previous diagonal, the
   // last `cells` do the small loops below; when they fit, the items go to the threads in between,
@@ -408,9 +425,9 @@ RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int
     bs.ipart[(size_t)NSLICE * BR * bs.NGP + seg_slot(sg, bs, i)] = v;
   }
   if (smax >= 2 && tid >= t0) {
-    const int unit = (tid - t0) / GB, hl = (tid - t0) % GB, nunits = (T - t0) / GB;
+    const int unit = (tid - t0) >> gsh, hl = (tid - t0) & (GB - 1), nunits = (T - t0) >> gsh;
     for (int item = unit; item < nitems; item += nunits) {
-      const int q = item / NB, b = item - q * NB;
+      const int q = NB == 1 ? item : (NB == 2 ? item >> 1 : item / NB), b = item - q * NB;
       const int g = GB * b + hl;
       if (g >= NG) continue;
       double tot[BR];
@@ -523,24 +540,41 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
   const int vprev = (d & 1) ? V_U0 : V_U1, vcur = (d & 1) ? V_U1 : V_U0;
   for (int x = tid; x < cells; x += T) {
     const int i = 1 + x, j = i + d;
-    // ---- loads
-    const double sM = TB(c, T_QM2, d, i);
-    double sQ = TB(c, T_QS, d, i);
-    const double qm2c = TB(c, T_QM2, d - 2, i + 1);
-    const double qm1l = TB(c, T_QM1, d - 1, i), qm1r = TB(c, T_QM1, d - 1, i + 1), qql = TB(c, T_QQ, d - 1, i);
-    const double uprev = VEC(c, vprev, i + 1);
-    const double hpw = VEC(c, V_HPW, u), scd = VEC(c, V_SCALE, d + 1);
+    // ---- loads (all issued here, one L2 round trip)
+#ifdef __CUDA_ARCH__
+    long long tp0 = 0;
+    if (c.prof && tid == 0) tp0 = clock64();
+#endif
+    const double* safe = c.ptr(T_Q, 0, 1);
+    const double sM = ldg_now(c.ptr(T_QM2, d, i));
+    double sQ = ldg_now(c.ptr(T_QS, d, i));
+    const double qm2c = ldg_now(c.ptr(T_QM2, d - 2, i + 1));
+    const double qm1l = ldg_now(c.ptr(T_QM1, d - 1, i)), qm1r = ldg_now(c.ptr(T_QM1, d - 1, i + 1));
+    const double qql = ldg_now(c.ptr(T_QQ, d - 1, i));
+    const double uprev = ldg_now(&VEC(c, vprev, i + 1));
+    const double hpw = ldg_now(&VEC(c, V_HPW, u)), scd = ldg_now(&VEC(c, V_SCALE, d + 1));
     double nq[BAND - 1];
 #pragma unroll
     for (int a = 0; a < BAND - 1; a++) {
       const bool ok = a < e && a <= d - TURN - 2;
-      nq[a] = ok ? TB(c, T_QQ, d - 1 - a, i + 1 + a) : 0.;
+      nq[a] = ldg_if(ok, c.ptr(T_QQ, ok ? d - 1 - a : 0, ok ? i + 1 + a : 1), safe, 0.);
     }
     const bool sp_case = M.special_hp && (u == 3 || u == 4 || u == 6);
-    const double spv = sp_case ? VEC(c, u == 3 ? V_SP3 : (u == 4 ? V_SP4 : V_SP6), i) : -1.;
+    const double spv = ldg_if(sp_case, &VEC(c, u == 3 ? V_SP3 : (u == 4 ? V_SP4 : V_SP6), i), safe, -1.);
     const bool cross = c.cp > 0 && i < c.cp && j >= c.cp;   // !ss(i,j)
-    const double nk1 = (cross && i + 1 <= c.cp - 1) ? TB(c, T_Q, c.cp - 2 - i, i + 1) : 1.0;
-    const double nk2 = (cross && c.cp <= j - 1) ? TB(c, T_Q, j - 1 - c.cp, c.cp) : 1.0;
+    const bool has1 = cross && i + 1 <= c.cp - 1, has2 = cross && c.cp <= j - 1;
+    const double nk1 = ldg_if(has1, c.ptr(T_Q, has1 ? c.cp - 2 - i : 0, has1 ? i + 1 : 1), safe, 1.0);
+    const double nk2 = ldg_if(has2, c.ptr(T_Q, has2 ? j - 1 - c.cp : 0, has2 ? c.cp : 1), safe, 1.0);
+#ifdef __CUDA_ARCH__
+    long long tp1 = 0;
+    if (c.prof && tid == 0) {
+      // wait for every load, then stamp
+      const double z = sM + sQ + qm2c + qm1l + qm1r + qql + uprev + hpw + scd + nq[0] + nq[1] + nq[2] + nq[3] + spv + nk1 + nk2;
+      if (z == 1.2345e300) bs.sIv[0] = z;
+      tp1 = clock64();
+    }
+#endif
+    if (c.dbg & 128) { bs.sIv[i] = sM + sQ + qm2c + qm1l + qm1r + qql + uprev + hpw + scd + nq[0] + nq[1] + nq[2] + nq[3] + spv + nk1 + nk2; continue; }
     // ---- combine
     // the terms of the q-split that the band pass could not see yet: q(i, i+a) = scale^(a+1) for a <= TURN
 #pragma unroll
@@ -568,7 +602,7 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
         qb += t;
       }
     }
-    TB(c, T_QB, d, i) = qb;
+    if (!(c.dbg & 256)) RP_ST_STREAM(TB(c, T_QB, d, i), qb);
     double fI = 0., f1 = 0., fA = 0.;
     if (type && qb != 0.) {
       const int t2 = rtype(type), sq1 = j < n ? base(c, j + 1) : 0, sp1 = i > 1 ? base(c, i - 1) : 0;
@@ -580,20 +614,28 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
       const size_t o = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, i);
       bs.TI[o] = fI; bs.T1[o] = f1; bs.TA[o] = fA;
     }
-    if (wide) { TB(c, T_QBI, d, i) = fI; TB(c, T_QB1N, d, i) = f1; TB(c, T_QBAU, d, i) = fA; }
+    if (wide) { RP_ST_STREAM(TB(c, T_QBI, d, i), fI); RP_ST_STREAM(TB(c, T_QB1N, d, i), f1); RP_ST_STREAM(TB(c, T_QBAU, d, i), fA); }
     double qm1 = ss(c, j - 1, j) ? qm1l * M.mlb1 : 0.;
     if (type && ss(c, i - 1, i) && ss(c, j, j + 1))
       qm1 += qb * ml_stem(M, type, i > 1 ? base(c, i - 1) : -1, j < n ? base(c, j + 1) : -1);
-    TB(c, T_QM1, d, i) = qm1;
+    if (!(c.dbg & 256)) TB(c, T_QM1, d, i) = qm1;
     const double U = ss(c, i, i + 1) ? M.mlb1 * (qm1r + uprev) : 0.;
-    VEC(c, vcur, i) = U;
-    TB(c, T_QM, d, i) = qm1 + sM + U;
+    if (!(c.dbg & 256)) { VEC(c, vcur, i) = U; TB(c, T_QM, d, i) = qm1 + sM + U; }
     double qq = qql * M.scale1;
     if (type)
       qq += qb * ext_stem(M, type, (i > 1 && ss(c, i - 1, i)) ? base(c, i - 1) : -1,
                           (j < n && ss(c, j, j + 1)) ? base(c, j + 1) : -1);
-    TB(c, T_QQ, d, i) = qq;
-    TB(c, T_Q, d, i) = scd + qq + sQ;
+    if (!(c.dbg & 256)) { TB(c, T_QQ, d, i) = qq; TB(c, T_Q, d, i) = scd + qq + sQ; }
+    else bs.sIv[i] = qq + qm1 + U;
+#ifdef __CUDA_ARCH__
+    if (c.prof && tid == 0) {
+      const long long tp2 = clock64();
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 24), (unsigned long long)(tp1 - tp0));
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 25), (unsigned long long)(tp2 - tp1));
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 32 + 24), 1ull);
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 32 + 25), 1ull);
+    }
+#endif
   }
 }
 
@@ -606,23 +648,23 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     const int k = 1 + x, l = k + d;
     const bool mlr = l < n && ss(c, l, l + 1);
     const bool mll = k > 1 && ss(c, k - 1, k);
-    // ---- loads
-    const double sP = TB(c, T_PRB, d, k), sL = TB(c, T_MLB, d, k);
-    const double qbv = TB(c, T_QB, d, k);
-    const double plp = mlr ? TB(c, T_PL, d + 1, k) : 0., mcp = mlr ? TB(c, T_MC, d + 1, k) : 0.;
-    const double pmp = mll ? TB(c, T_PMLB, d + 1, k - 1) : 0., prp = mll ? TB(c, T_PR, d + 1, k - 1) : 0.;
-    const double q5 = k > 1 ? TB(c, T_Q, k - 2, 1) : 1.0;
-    const double q3 = l < n ? TB(c, T_Q, n - l - 1, l + 1) : 1.0;
+    // ---- loads (all issued here, one L2 round trip)
+    const double* safe = c.ptr(T_Q, 0, 1);
+    const double sP = ldg_now(c.ptr(T_PRB, d, k)), sL = ldg_now(c.ptr(T_MLB, d, k));
+    const double qbv = ldg_now(c.ptr(T_QB, d, k));
+    const double plp = ldg_if(mlr, c.ptr(T_PL, d + 1, k), safe, 0.), mcp = ldg_if(mlr, c.ptr(T_MC, d + 1, k), safe, 0.);
+    const double pmp = ldg_if(mll, c.ptr(T_PMLB, d + 1, mll ? k - 1 : 1), safe, 0.);
+    const double prp = ldg_if(mll, c.ptr(T_PR, d + 1, mll ? k - 1 : 1), safe, 0.);
+    const double q5 = ldg_if(k > 1, c.ptr(T_Q, k > 1 ? k - 2 : 0, 1), safe, 1.0);
+    const double q3 = ldg_if(l < n, c.ptr(T_Q, l < n ? n - l - 1 : 0, l < n ? l + 1 : 1), safe, 1.0);
     double qo = 0., qn = 1.0;
     if (c.cp > 0) {
-      if (k >= c.cp) {
-        qo = VEC(c, V_QROUT, l);
-        if (k > c.cp) qn = TB(c, T_Q, k - 1 - c.cp, c.cp);
-      } else if (l < c.cp) {
-        qo = VEC(c, V_QLOUT, k);
-        if (l + 1 <= c.cp - 1) qn = TB(c, T_Q, c.cp - 2 - l, l + 1);
-      }
+      const bool s2 = k >= c.cp, s1 = !s2 && l < c.cp;
+      qo = ldg_if(s1 || s2, s2 ? &VEC(c, V_QROUT, l) : &VEC(c, V_QLOUT, k), safe, 0.);
+      const bool hn = s2 ? (k > c.cp) : (s1 && l + 1 <= c.cp - 1);
+      qn = ldg_if(hn, s2 ? c.ptr(T_Q, hn ? k - 1 - c.cp : 0, c.cp) : c.ptr(T_Q, hn ? c.cp - 2 - l : 0, hn ? l + 1 : 1), safe, 1.0);
     }
+    if (c.dbg & 128) { bs.sIv[k] = sP + sL + qbv + plp + mcp + pmp + prp + q5 + q3 + qo + qn; continue; }
     // ---- combine
     const int type = pair_type(base(c, k), base(c, l));
     double sI = 0.;
@@ -645,7 +687,7 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
         else if (l < c.cp) out += qo * qn * ext_stem(M, type, base(c, k - 1), l + 1 < c.cp ? base(c, l + 1) : -1);
       }
     }
-    TB(c, T_OUT, d, k) = out;
+    RP_ST_STREAM(TB(c, T_OUT, d, k), out);
     double fI = 0., f1 = 0., fA = 0., mc = 0.;
     if (out != 0.) {
       const int si1 = base(c, k + 1), sj1 = base(c, l - 1);
@@ -658,7 +700,7 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
       const size_t o = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, k);
       bs.TI[o] = fI; bs.T1[o] = f1; bs.TA[o] = fA;
     }
-    if (wide) { TB(c, T_OUTI, d, k) = fI; TB(c, T_OUT1N, d, k) = f1; TB(c, T_OUTAU, d, k) = fA; }
+    if (wide) { RP_ST_STREAM(TB(c, T_OUTI, d, k), fI); RP_ST_STREAM(TB(c, T_OUT1N, d, k), f1); RP_ST_STREAM(TB(c, T_OUTAU, d, k), fA); }
     TB(c, T_MC, d, k) = mc;
   }
 }

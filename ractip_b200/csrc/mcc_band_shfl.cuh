@@ -22,6 +22,16 @@
 namespace rp {
 
 __device__ __forceinline__ double shfl_down_f64(double v, int delta) { return __shfl_down_sync(0xffffffffu, v, delta); }
+// fine-grained probes (RP_PROFILE): thread 0 accumulates the cycles between two marks into slot k
+#define RP_MARK(k)                                                                                       \
+  do {                                                                                                   \
+    if (c.prof && tid == 0) {                                                                            \
+      const long long now__ = clock64();                                                                 \
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + (k)), (unsigned long long)(now__ - tmark)); \
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 32 + (k)), 1ull);                         \
+      tmark = clock64();                                                                                 \
+    }                                                                                                    \
+  } while (0)
 
 // Work split of the shuffle variants: a warp owns HW = 28 rows; lanes 28..31 shadow the first rows
 // of the next warp and only feed the shuffle chain (a value needs BAND-1 = 4 hops to cross over).
@@ -55,6 +65,7 @@ __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& s
   double m[BAND], q[BAND];
 #pragma unroll
   for (int e = 0; e < BAND; e++) m[e] = q[e] = 0.;
+  long long tmark = (c.prof && tid == 0) ? clock64() : 0;
   if (!(c.dbg & 2)) {
     const int amax = d0 - 1;
     const int lim = d0 - TURN - 2;
@@ -70,6 +81,7 @@ __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& s
           if (e >= emin && e <= a) q[e] += A * B[e * es];
       }
     }
+    RP_MARK(26);
     // main part, TURN < a <= lim: a contiguous run per slice, 4 steps' loads in flight at a time
     const int len = lim - TURN;
     if (len > 0) {
@@ -118,6 +130,7 @@ __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& s
         }
       }
     }
+    RP_MARK(27);
     if (own) {  // tail, lim < a <= amax
       const int a0 = lim + 1 > TURN + 1 ? lim + 1 : TURN + 1;
       for (int a = a0 + slice; a <= amax; a += S) {
@@ -132,6 +145,7 @@ __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& s
       }
     }
   }
+  RP_MARK(28);
   if (!own) return;
 #pragma unroll
   for (int e = 0; e < BAND; e++) {
@@ -168,6 +182,7 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
   double pr[BAND], ml[BAND];
 #pragma unroll
   for (int e = 0; e < BAND; e++) pr[e] = ml[e] = 0.;
+  long long tmark = (c.prof && tid == 0) ? clock64() : 0;
   if (!(c.dbg & 2)) {
     {  // PR, row k; t = j - (k+d0+TURN+3)
       const int k = 1 + r;
@@ -228,15 +243,25 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
         }
       }
     }
+    RP_MARK(29);
     {  // ML-left, column l; cells (k0+e, l), k0 = l-d0; i <= k0+e-TURN-3
       const int l = d0 - BAND + 2 + r, k0 = l - d0;
       unsigned need = 0;
       if (own && l <= n) {
+        // the five qb look-ups in one round trip (a short-circuit chain would serialise them)
+        double qbv[BAND];
+        bool cand[BAND];
+#pragma unroll
         for (int e = 0; e < BAND; e++) {
           const int k = k0 + e, d = d0 - e;
-          if (k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) && TB(c, T_QB, d, k) != 0.) need |= 1u << e;
+          cand[e] = k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) != 0;
+          qbv[e] = cand[e] ? TB(c, T_QB, d, k) : 0.;
         }
+#pragma unroll
+        for (int e = 0; e < BAND; e++)
+          if (cand[e] && qbv[e] != 0.) need |= 1u << e;
       }
+      RP_MARK(30);
       const int imax = k0 + (BAND - 1) - TURN - 3, imain = k0 - TURN - 3;
       // main part: B(e) = qm(i+1, k0+e-1) is the B(0) of the lane e places to the right, same step
       const int imain_hi = __shfl_sync(0xffffffffu, imain, HW - 1);   // largest among the owning lanes
@@ -274,6 +299,7 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
       }
     }
   }
+  RP_MARK(31);
   if (!own) return;
 #pragma unroll
   for (int e = 0; e < BAND; e++) {

@@ -91,9 +91,18 @@ struct Ctx {
   unsigned te, ve;    // elements per table / per vector (a slot is < 2^32 doubles: n <= RP_MAX_N, checked by the host)
   double invZ;        // set after the inside pass
   int dbg;            // tuning aid (RP_DEBUG_SKIP): 1 skip interior rows, 2 skip split sums, 4 skip gap sums
+  long long* prof;    // RP_PROFILE counters (slots 40..: fine-grained probes of thread 0) or null
+  // Tables whose rows are only read while they are recent are RINGS of a few rows (row d at d & mask):
+  // PR/PL/PMLB are read one diagonal after they are written, the band results QS/PRB/MLB within a
+  // band.  A full table would leave every written line behind in L2, where it pushes out the history
+  // tables the split sums stream (the 126 MB L2 holds the history of all resident problems, not more).
+  RP_HD static constexpr unsigned ring_mask(int t) {
+    return (t == T_PR || t == T_PL || t == T_PMLB) ? 1u : (t == T_QS || t == T_PRB || t == T_MLB) ? 7u : 0xffffffffu;
+  }
   // 32-bit element offsets: one IMAD per term instead of 64-bit multiplies (a third of all instructions otherwise)
-  RP_HD double& tb(int t, int d, int i) const { return ws[(unsigned)t * te + (unsigned)d * (unsigned)ld + (unsigned)i]; }
-  RP_HD double* ptr(int t, int d, int i) const { return ws + ((unsigned)t * te + (unsigned)d * (unsigned)ld + (unsigned)i); }
+  RP_HD unsigned off(int t, int d, int i) const { return (unsigned)t * te + ((unsigned)d & ring_mask(t)) * (unsigned)ld + (unsigned)i; }
+  RP_HD double& tb(int t, int d, int i) const { return ws[off(t, d, i)]; }
+  RP_HD double* ptr(int t, int d, int i) const { return ws + off(t, d, i); }
   RP_HD double& v(int vv, int k) const { return ws[(unsigned)T_COUNT * te + (unsigned)vv * ve + (unsigned)k]; }
   RP_HD int dstep() const { return ld; }   // one diagonal up, same position
   RP_HD int pstep() const { return 1; }    // same diagonal, next position
@@ -123,6 +132,7 @@ RP_HD void bind_ctx(Ctx& c, const DevModel* M, const uint8_t* S, const Problem& 
   c.ws = ws; c.te = (unsigned)table_elems(p.n); c.ve = (unsigned)vector_elems(p.n);
   c.invZ = 0;
   c.dbg = 0;
+  c.prof = nullptr;
 }
 template <int G>
 RP_HD void bind_lctx(LCtx<G>& c, const DevModel* M, const uint8_t* S_group, const Problem& p, double* ws_group, int g) {
@@ -133,6 +143,13 @@ RP_HD void bind_lctx(LCtx<G>& c, const DevModel* M, const uint8_t* S_group, cons
 }
 
 #define TB(c, t, d, i) ((c).tb(t, d, i))
+// store of a value that is not read again soon (qb, out, class tables, outputs): evict-first, so that
+// it does not displace the history tables in L2
+#ifdef __CUDA_ARCH__
+#define RP_ST_STREAM(ref, v) __stcs(&(ref), (v))
+#else
+#define RP_ST_STREAM(ref, v) ((ref) = (v))
+#endif
 #define VEC(c, vec_id, k) ((c).v(vec_id, k))
 
 // Per-diagonal compaction of the cells that can pair (static per sequence; general kernel):
@@ -1318,7 +1335,7 @@ RP_HD void unstru_windows(C& c, float* up, int tid, int T) {
         v += (m1 + m2 + m3 * VEC(c, V_MLB, dd + 1)) * VEC(c, V_SCALE, 2);
       }
     }
-    up[x] = (float)v;
+    RP_ST_STREAM(up[x], (float)v);
   }
 }
 
@@ -1330,7 +1347,7 @@ template <class C>
 RP_HD void write_bp(const C& c, float* bp, int tid, int T) {
   const int L = c.n;
   const size_t total = (size_t)(L + 1) * (L + 2) / 2;
-  for (size_t x = tid; x < total; x += T) bp[x] = 0.f;
+  for (size_t x = tid; x < total; x += T) RP_ST_STREAM(bp[x], 0.f);
 }
 template <class C>
 RP_HD void write_bp2(const C& c, float* bp, int tid, int T) {
@@ -1340,7 +1357,7 @@ RP_HD void write_bp2(const C& c, float* bp, int tid, int T) {
     const int d = (int)(x / c.ld), i = (int)(x % c.ld);
     if (i < 1 || i + d > L || d < 1) continue;
     const double p = d > TURN ? TB(c, T_OUT, d, i) * TB(c, T_QB, d, i) : 0.;
-    bp[(size_t)i * (2 * L + 1 - i) / 2 + (i + d)] = (float)p;
+    RP_ST_STREAM(bp[(size_t)i * (2 * L + 1 - i) / 2 + (i + d)], (float)p);
   }
 }
 // hp[i][j-cp+1] = p if i<cp<=j and p>th_hy (float compare)   (src/ractip.cpp:404-405,447-453)
@@ -1359,7 +1376,7 @@ RP_HD void write_hp(const C& c, float* hp, int n1, int n2, float th_hy, int tid,
         if (p >= (double)th_hy && pf > th_hy) v = pf;
       }
     }
-    hp[x] = v;
+    RP_ST_STREAM(hp[x], v);
   }
 }
 

@@ -210,7 +210,9 @@ def test_full_batch_size_independent_properties(stage, bundled):
     opts = default_opts()
     b = stage.batch(list(zip(r1, r2)), opts)
     b.run()
-    flat = b.fetch_dense()
+    flat = b.fetch_dense().copy()
+    b.run()
+    assert np.array_equal(flat, b.fetch_dense()), "the 3000-problem batch is not bitwise repeatable (a race?)"
     res = b.split_dense(flat)
     b.close()
     assert np.isfinite(flat).all()
