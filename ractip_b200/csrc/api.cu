@@ -45,6 +45,8 @@ struct rp_ctx {
   int threads = RP_MCC_THREADS;  // CTA width of the wavefront kernel (RP_MCC_THREADS env var narrows it: tuning aid)
   rp::DevModel* d_model = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t side_stream = nullptr;   // the second band launch shape runs here, so that its CTAs fill the SMs the first one leaves
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   double* ws = nullptr;       // workspace slots (grow-only)
@@ -342,6 +344,10 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   ctx->stream = ctx->own_stream;
+  if ((e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMalloc(&ctx->d_model, sizeof(rp::DevModel))) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
@@ -374,6 +380,9 @@ int rp_destroy(rp_ctx* ctx) {
   if (ctx->d_model) cudaFree(ctx->d_model);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return RP_OK;
@@ -481,7 +490,14 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   // Same-shape problems go to the lockstep kernel in groups of RP_LS_G: the shuffles of a z-score
   // batch all share the lengths of the original pair.  Everything else (ragged batches, leftovers
   // of a shape with fewer than RP_LS_G problems, --duplex) goes to the general kernel.
-  auto cost = [&](const Problem& q) { return q.kind == rp::KIND_DUPLEX ? 0.0 : (double)q.n * q.n * (q.n + 1500.0); };
+  // LPT cost.  Band-kernel lengths (measured, profiles/r01b_phase_ablation.txt): ~30 k cycles per unit of
+  // length for the two wavefronts (fixed cost per diagonal) + ~160 n^2 for the unpaired-window pass.
+  auto cost = [&](const Problem& q) {
+    if (q.kind == rp::KIND_DUPLEX) return 0.0;
+    if (ctx->band && rp_kernel_plan(q.n, ctx->smem_optin, nullptr) != RP_KERNEL_GENERAL)
+      return 3.0e4 * q.n + ((q.kind == rp::KIND_LINEAR && q.max_w > 0) ? 160.0 * q.n * q.n : 0.0);
+    return (double)q.n * q.n * (q.n + 1500.0);
+  };
   std::vector<char> in_group(b->probs.size(), 0);
   std::vector<uint8_t> gseq;
   if (ctx->lockstep && ctx->ls_ctas_per_sm > 0) {
@@ -660,13 +676,23 @@ int rp_batch_run(rp_batch* b) {
   {
     size_t ws_off = gen_bytes / sizeof(double);
     int ord_off = 0;
+    if (b->n_band[0] && b->n_band[1]) CU(cudaEventRecord(ctx->ev_fork, st));   // inputs and counters are ready here
     for (int k = 0; k < 2; k++) {
       if (b->n_band[k]) {
         rp::BatchDev db = d;
         db.order = b->d_order + ord_off; db.nprob = b->n_band[k];
         db.counter = b->d_counter + 1 + k;
         db.ws = ctx->ws + ws_off; db.slot_stride = band_slot[k]; db.nslots = b->band_grid[k];
-        CU(rp::launch_band(db, b->band_grid[k], band_threads[k], band_smem[k], st));
+        cudaStream_t ls = st;
+        if (k == 1 && b->n_band[0]) {   // the short class runs on the side stream (forked before the first launch)
+          CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+          ls = ctx->side_stream;
+        }
+        CU(rp::launch_band(db, b->band_grid[k], band_threads[k], band_smem[k], ls));
+        if (ls != st) {                 // join before anything else of the batch runs
+          CU(cudaEventRecord(ctx->ev_join, ls));
+          CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        }
         launches++;
       }
       ws_off += (size_t)b->band_grid[k] * band_slot[k];
