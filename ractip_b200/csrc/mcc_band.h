@@ -530,6 +530,29 @@ RP_HD void band_cfac_outside(const C& c, const BandShared& bs, int d, int tid, i
 // `wide`: also keep the class tables in HBM (the unpaired-window pass of a
 // single-strand problem reads their full history).
 // ---------------------------------------------------------------------------
+// branch-free stem factors (all three candidates are loaded with clamped indices, then selected):
+// same values as ext_stem / ml_stem of mcc_core.h
+template <class MT>
+RP_HD double ext_stem_bf(const MT& M, int type, int s5, int s3) {
+  const int a = s5 >= 0 ? s5 : 0, b = s3 >= 0 ? s3 : 0;
+  const double both = M.mmExt[type][a][b], d5 = M.dangle5[type][a], d3 = M.dangle3[type][b];
+  const double e = (s5 >= 0 && s3 >= 0) ? both : (s5 >= 0 ? d5 : (s3 >= 0 ? d3 : 1.0));
+  return type > 2 ? e * M.expTermAU : e;
+}
+template <class MT>
+RP_HD double ml_stem_bf(const MT& M, int type, int s5, int s3) {
+  const int a = s5 >= 0 ? s5 : 0, b = s3 >= 0 ? s3 : 0;
+  const double both = M.mmM[type][a][b], d5 = M.dangle5[type][a], d3 = M.dangle3[type][b];
+  double e = (s5 >= 0 && s3 >= 0) ? both : (s5 >= 0 ? d5 : (s3 >= 0 ? d3 : 1.0));
+  if (type > 2) e *= M.expTermAU;
+  return e * M.expMLintern;
+}
+
+// Finish of a cell, written for latency: (1) every HBM/L2 operand is requested first; (2) while the
+// requests are in flight, everything that depends on the sequence alone (pair type, stem and mismatch
+// factors: shared-memory look-ups) is evaluated WITHOUT branches; (3) only then the loaded values are
+// combined, in half a dozen dependent fp operations, and stored.  (A consumer of a loaded value
+// stalls the warp's whole in-order stream, and a branch keeps the compiler from filling the wait.)
 template <class C>
 RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
   const int T = sh.T, n = c.n, cells = n - d;
@@ -540,7 +563,7 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
   const int vprev = (d & 1) ? V_U0 : V_U1, vcur = (d & 1) ? V_U1 : V_U0;
   for (int x = tid; x < cells; x += T) {
     const int i = 1 + x, j = i + d;
-    // ---- loads (all issued here, one L2 round trip)
+    // ---- (1) loads
 #ifdef __CUDA_ARCH__
     long long tp0 = 0;
     if (c.prof && tid == 0) tp0 = clock64();
@@ -565,68 +588,53 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
     const bool has1 = cross && i + 1 <= c.cp - 1, has2 = cross && c.cp <= j - 1;
     const double nk1 = ldg_if(has1, c.ptr(T_Q, has1 ? c.cp - 2 - i : 0, has1 ? i + 1 : 1), safe, 1.0);
     const double nk2 = ldg_if(has2, c.ptr(T_Q, has2 ? j - 1 - c.cp : 0, has2 ? c.cp : 1), safe, 1.0);
+    // ---- (2) sequence-only factors
+    const int type = pair_type(base(c, i), base(c, j));
+    const bool tz = type != 0;
+    const int rt = rtype(type);
+    const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
+    const int sim = i > 1 ? base(c, i - 1) : -1, sjp = j < n ? base(c, j + 1) : -1;
+    const bool ssl = ss(c, i, i + 1), ssr = ss(c, j - 1, j), ssi = ss(c, i - 1, i), ssj = ss(c, j, j + 1);
+    const double au = type > 2 ? M.expTermAU : 1.0;
+    const double scale2 = M.scale_small[2];
+    const double hfac = (sp_case && u == 3) ? au : M.mmH[type][si1][sj1];                      // hairpin: hpw * hfac
+    const double k1 = (tz && ssl && ssr) ? M.expMLclosing * ml_stem_bf(M, rt, sj1, si1) * scale2 : 0.;   // closes a multiloop
+    const double k2 = (tz && cross) ? scale2 * ext_stem_bf(M, rt, ssr ? sj1 : -1, ssl ? si1 : -1) : 0.;  // closes the nicked loop
+    const double k3 = (tz && ssi && ssj) ? ml_stem_bf(M, type, sim, sjp) : 0.;                 // stem in a multiloop
+    const double k4 = tz ? ext_stem_bf(M, type, ssi ? sim : -1, ssj ? sjp : -1) : 0.;          // stem in the exterior loop
+    const double gI = tz ? M.mmI[rt][sjp < 0 ? 0 : sjp][sim < 0 ? 0 : sim] : 0.;               // seen as an inner pair
+    const double g1 = tz ? M.mm1n[rt][sjp < 0 ? 0 : sjp][sim < 0 ? 0 : sim] : 0.;
+    const double gA = tz ? au : 0.;
+    const double m1 = ssr ? M.mlb1 : 0., mU = ssl ? M.mlb1 : 0.;
+    const double sI = tz ? bs.sIv[i] : 0.;
+    const size_t ro = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, i);
 #ifdef __CUDA_ARCH__
     long long tp1 = 0;
-    if (c.prof && tid == 0) {
-      // wait for every load, then stamp
-      const double z = sM + sQ + qm2c + qm1l + qm1r + qql + uprev + hpw + scd + nq[0] + nq[1] + nq[2] + nq[3] + spv + nk1 + nk2;
-      if (z == 1.2345e300) bs.sIv[0] = z;
-      tp1 = clock64();
-    }
+    if (c.prof && tid == 0) tp1 = clock64();
 #endif
     if (c.dbg & 128) { bs.sIv[i] = sM + sQ + qm2c + qm1l + qm1r + qql + uprev + hpw + scd + nq[0] + nq[1] + nq[2] + nq[3] + spv + nk1 + nk2; continue; }
-    // ---- combine
-    // the terms of the q-split that the band pass could not see yet: q(i, i+a) = scale^(a+1) for a <= TURN
+    // ---- (3) combine
 #pragma unroll
-    for (int a = 0; a < BAND - 1; a++) sQ += M.scale_small[a + 1] * nq[a];
-    const int type = pair_type(base(c, i), base(c, j));
-    const double sI = type ? bs.sIv[i] : 0.;
-    const double scale2 = M.scale_small[2];
-    double qb = 0.;
-    if (type) {
-      if (!cross) {
-        double h;
-        if (spv >= 0.) h = spv;
-        else if (sp_case && u == 3) h = type > 2 ? hpw * M.expTermAU : hpw;
-        else h = hpw * M.mmH[type][base(c, i + 1)][base(c, j - 1)];
-        qb += h;
-      }
-      qb += sI;
-      if (ss(c, i, i + 1) && ss(c, j - 1, j))
-        qb += qm2c * M.expMLclosing * ml_stem(M, rtype(type), base(c, j - 1), base(c, i + 1)) * scale2;
-      if (cross) {
-        double t = scale2;
-        t *= nk1;
-        t *= nk2;
-        t *= ext_stem(M, rtype(type), ss(c, j - 1, j) ? base(c, j - 1) : -1, ss(c, i, i + 1) ? base(c, i + 1) : -1);
-        qb += t;
-      }
-    }
+    for (int a = 0; a < BAND - 1; a++) sQ += M.scale_small[a + 1] * nq[a];   // q(i,i+a) = scale^(a+1), a <= TURN
+    const double h = spv >= 0. ? spv : hpw * hfac;
+    double qb = (tz && !cross) ? h : 0.;
+    qb += sI;
+    qb += qm2c * k1;
+    qb += k2 * nk1 * nk2;
     if (!(c.dbg & 256)) RP_ST_STREAM(TB(c, T_QB, d, i), qb);
-    double fI = 0., f1 = 0., fA = 0.;
-    if (type && qb != 0.) {
-      const int t2 = rtype(type), sq1 = j < n ? base(c, j + 1) : 0, sp1 = i > 1 ? base(c, i - 1) : 0;
-      fI = qb * M.mmI[t2][sq1][sp1];
-      f1 = qb * M.mm1n[t2][sq1][sp1];
-      fA = type > 2 ? qb * M.expTermAU : qb;
-    }
-    {
-      const size_t o = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, i);
-      bs.TI[o] = fI; bs.T1[o] = f1; bs.TA[o] = fA;
-    }
+    const double fI = qb * gI, f1 = qb * g1, fA = qb * gA;
+    bs.TI[ro] = fI; bs.T1[ro] = f1; bs.TA[ro] = fA;
     if (wide) { RP_ST_STREAM(TB(c, T_QBI, d, i), fI); RP_ST_STREAM(TB(c, T_QB1N, d, i), f1); RP_ST_STREAM(TB(c, T_QBAU, d, i), fA); }
-    double qm1 = ss(c, j - 1, j) ? qm1l * M.mlb1 : 0.;
-    if (type && ss(c, i - 1, i) && ss(c, j, j + 1))
-      qm1 += qb * ml_stem(M, type, i > 1 ? base(c, i - 1) : -1, j < n ? base(c, j + 1) : -1);
-    if (!(c.dbg & 256)) TB(c, T_QM1, d, i) = qm1;
-    const double U = ss(c, i, i + 1) ? M.mlb1 * (qm1r + uprev) : 0.;
-    if (!(c.dbg & 256)) { VEC(c, vcur, i) = U; TB(c, T_QM, d, i) = qm1 + sM + U; }
-    double qq = qql * M.scale1;
-    if (type)
-      qq += qb * ext_stem(M, type, (i > 1 && ss(c, i - 1, i)) ? base(c, i - 1) : -1,
-                          (j < n && ss(c, j, j + 1)) ? base(c, j + 1) : -1);
-    if (!(c.dbg & 256)) { TB(c, T_QQ, d, i) = qq; TB(c, T_Q, d, i) = scd + qq + sQ; }
-    else bs.sIv[i] = qq + qm1 + U;
+    const double qm1 = qm1l * m1 + qb * k3;
+    const double U = mU * (qm1r + uprev);
+    const double qq = qql * M.scale1 + qb * k4;
+    if (!(c.dbg & 256)) {
+      TB(c, T_QM1, d, i) = qm1;
+      VEC(c, vcur, i) = U;
+      TB(c, T_QM, d, i) = qm1 + sM + U;
+      TB(c, T_QQ, d, i) = qq;
+      TB(c, T_Q, d, i) = scd + qq + sQ;
+    } else bs.sIv[i] = qq + qm1 + U;
 #ifdef __CUDA_ARCH__
     if (c.prof && tid == 0) {
       const long long tp2 = clock64();
@@ -648,7 +656,7 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     const int k = 1 + x, l = k + d;
     const bool mlr = l < n && ss(c, l, l + 1);
     const bool mll = k > 1 && ss(c, k - 1, k);
-    // ---- loads (all issued here, one L2 round trip)
+    // ---- (1) loads
     const double* safe = c.ptr(T_Q, 0, 1);
     const double sP = ldg_now(c.ptr(T_PRB, d, k)), sL = ldg_now(c.ptr(T_MLB, d, k));
     const double qbv = ldg_now(c.ptr(T_QB, d, k));
@@ -658,50 +666,47 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     const double q5 = ldg_if(k > 1, c.ptr(T_Q, k > 1 ? k - 2 : 0, 1), safe, 1.0);
     const double q3 = ldg_if(l < n, c.ptr(T_Q, l < n ? n - l - 1 : 0, l < n ? l + 1 : 1), safe, 1.0);
     double qo = 0., qn = 1.0;
+    const bool s2 = c.cp > 0 && k >= c.cp, s1 = c.cp > 0 && !s2 && l < c.cp;
     if (c.cp > 0) {
-      const bool s2 = k >= c.cp, s1 = !s2 && l < c.cp;
       qo = ldg_if(s1 || s2, s2 ? &VEC(c, V_QROUT, l) : &VEC(c, V_QLOUT, k), safe, 0.);
       const bool hn = s2 ? (k > c.cp) : (s1 && l + 1 <= c.cp - 1);
       qn = ldg_if(hn, s2 ? c.ptr(T_Q, hn ? k - 1 - c.cp : 0, c.cp) : c.ptr(T_Q, hn ? c.cp - 2 - l : 0, hn ? l + 1 : 1), safe, 1.0);
     }
-    if (c.dbg & 128) { bs.sIv[k] = sP + sL + qbv + plp + mcp + pmp + prp + q5 + q3 + qo + qn; continue; }
-    // ---- combine
+    // ---- (2) sequence-only factors
     const int type = pair_type(base(c, k), base(c, l));
-    double sI = 0.;
-    if (type && qbv != 0.) sI = bs.sIv[k];
+    const bool tz = type != 0;
+    const int rt = rtype(type);
+    const int skm = base(c, k - 1), slp = base(c, l + 1), si1 = base(c, k + 1), sj1 = base(c, l - 1);
+    const double au = type > 2 ? M.expTermAU : 1.0;
     const double scale2 = M.scale_small[2];
+    const double kx = ext_stem_bf(M, type, mll ? skm : -1, mlr ? slp : -1);                     // stem in the exterior loop
+    const double km = (mlr && mll) ? ml_stem_bf(M, type, skm, slp) * scale2 : 0.;              // stem in a multiloop
+    // stem in the nicked loop: strand 2 (5' neighbour missing when k == cp), strand 1 (3' neighbour missing when l+1 == cp)
+    const double kn = s2 ? ext_stem_bf(M, type, k > c.cp ? skm : -1, slp) : (s1 ? ext_stem_bf(M, type, skm, l + 1 < c.cp ? slp : -1) : 0.);
+    const double gI = tz ? M.mmI[type][si1][sj1] : 0., g1 = tz ? M.mm1n[type][si1][sj1] : 0., gA = tz ? au : 0.;
+    const double gM = (tz && ss(c, k, k + 1) && ss(c, l - 1, l)) ? M.expMLclosing * ml_stem_bf(M, rt, sj1, si1) : 0.;
+    const double sIraw = bs.sIv[k];
+    const size_t ro = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, k);
+    if (c.dbg & 128) { bs.sIv[k] = sP + sL + qbv + plp + mcp + pmp + prp + q5 + q3 + qo + qn; continue; }
+    // ---- (3) combine
+    const bool live = tz && qbv != 0.;
     const double PL = mlr ? plp * M.mlb1 + mcp : 0.;
     const double PR = mlr ? sP : 0.;
+    const double PMLB = mll ? pmp * M.mlb1 + prp : 0.;
+    double out = q5 * q3 * c.invZ * kx;
+    out += sIraw;
+    out += (PMLB + sL) * km;
+    out += qo * qn * kn;
+    out = live ? out : 0.;
     TB(c, T_PL, d, k) = PL;
     TB(c, T_PR, d, k) = PR;
     TB(c, T_PRML, d, k) = PR + PL;
-    const double PMLB = mll ? pmp * M.mlb1 + prp : 0.;
     TB(c, T_PMLB, d, k) = PMLB;
-    double out = 0.;
-    if (type && qbv != 0.) {
-      out = q5 * q3 * c.invZ * ext_stem(M, type, mll ? base(c, k - 1) : -1, mlr ? base(c, l + 1) : -1);
-      out += sI;
-      if (mlr && mll) out += (PMLB + sL) * ml_stem(M, type, base(c, k - 1), base(c, l + 1)) * scale2;
-      if (c.cp > 0 && qo != 0.) {
-        if (k >= c.cp) out += qo * qn * ext_stem(M, type, k > c.cp ? base(c, k - 1) : -1, base(c, l + 1));
-        else if (l < c.cp) out += qo * qn * ext_stem(M, type, base(c, k - 1), l + 1 < c.cp ? base(c, l + 1) : -1);
-      }
-    }
     RP_ST_STREAM(TB(c, T_OUT, d, k), out);
-    double fI = 0., f1 = 0., fA = 0., mc = 0.;
-    if (out != 0.) {
-      const int si1 = base(c, k + 1), sj1 = base(c, l - 1);
-      fI = out * M.mmI[type][si1][sj1];
-      f1 = out * M.mm1n[type][si1][sj1];
-      fA = type > 2 ? out * M.expTermAU : out;
-      if (ss(c, k, k + 1) && ss(c, l - 1, l)) mc = out * M.expMLclosing * ml_stem(M, rtype(type), sj1, si1);
-    }
-    {
-      const size_t o = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, k);
-      bs.TI[o] = fI; bs.T1[o] = f1; bs.TA[o] = fA;
-    }
+    const double fI = out * gI, f1 = out * g1, fA = out * gA;
+    bs.TI[ro] = fI; bs.T1[ro] = f1; bs.TA[ro] = fA;
     if (wide) { RP_ST_STREAM(TB(c, T_OUTI, d, k), fI); RP_ST_STREAM(TB(c, T_OUT1N, d, k), f1); RP_ST_STREAM(TB(c, T_OUTAU, d, k), fA); }
-    TB(c, T_MC, d, k) = mc;
+    TB(c, T_MC, d, k) = out * gM;
   }
 }
 
