@@ -713,14 +713,18 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
 template <int SIGN, class C>
 RP_HD void band_collect(const C& c, const BandShared& bs, int dsum, int dnext, int tid, int T) {
   if (c.dbg & 32) return;
-  if (dsum >= 0) {
-    const Segs sg = make_segs(c.n, c.cp, dsum);
-    const int cells = c.n - dsum;
-    for (int x = tid; x < cells; x += T) bs.sIv[1 + x] = band_interior_sum<SIGN>(c, bs, dsum, sg, 1 + x);
-  }
-  if (dnext >= 0) {
-    if (SIGN > 0) band_cfac_inside(c, bs, dnext, tid, T);
-    else band_cfac_outside(c, bs, dnext, tid, T);
+  const int reps = (c.dbg & 512) ? 2 : 1;   // tuning aid: the same code twice tells cold-code cost from work
+#pragma unroll 1
+  for (int rep = 0; rep < reps; rep++) {
+    if (dsum >= 0) {
+      const Segs sg = make_segs(c.n, c.cp, dsum);
+      const int cells = c.n - dsum;
+      for (int x = tid; x < cells; x += T) bs.sIv[1 + x] = band_interior_sum<SIGN>(c, bs, dsum, sg, 1 + x);
+    }
+    if (dnext >= 0) {
+      if (SIGN > 0) band_cfac_inside(c, bs, dnext, tid, T);
+      else band_cfac_outside(c, bs, dnext, tid, T);
+    }
   }
 }
 

@@ -1225,7 +1225,8 @@ RP_HD void unstru_gaps(C& c, const double* gfull, int side, int tid, int T) {
           // the shorter shifts reach further (l up to n-1-(u2+t)): walk to the end of the longest one;
           // window elements past the last diagonal count as 0
           const int X = cmain + nu - 1;
-          multi_dot_slide(Q, ds, O, ds, X, 0, X - 1, av);
+          if (nu == 1) av[0] = dot_range(Q, ds, O, ds, 0, X, 0, 1);   // a lone shift (the bulge / 1xn heads): plain dot product
+          else multi_dot_slide(Q, ds, O, ds, X, 0, X - 1, av);
           for (int t = 0; t < nu; t++) acc += gfull[u1 * GROW_LD + u2 + t] * av[t];
           u2 += nu;
         } else {
@@ -1249,10 +1250,14 @@ RP_HD void unstru_gaps(C& c, const double* gfull, int side, int tid, int T) {
           if (cmain > 0) {
             const long st = ps - ds;
             const int X = cmain + nu - 1;   // steps of the longest shift (t = 0)
-            double rv[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-            multi_dot_slide(O + (long)(X - 1) * st, -st, Q + (long)(X + 6) * st, -st, X, 7, X + 6, rv);
+            if (nu == 1) {
+              av[0] = dot_range(O + (long)(X - 1) * st, (int)-st, Q + (long)(X - 1) * st, (int)-st, 0, X, 0, 1);
+            } else {
+              double rv[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+              multi_dot_slide(O + (long)(X - 1) * st, -st, Q + (long)(X + 6) * st, -st, X, 7, X + 6, rv);
 #pragma unroll
-            for (int t = 0; t < 8; t++) av[t] = rv[7 - t];
+              for (int t = 0; t < 8; t++) av[t] = rv[7 - t];
+            }
           }
           for (int t = 0; t < nu; t++) acc += gfull[(u1 + t) * GROW_LD + u2] * av[t];
           u1 += nu;
