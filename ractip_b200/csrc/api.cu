@@ -29,7 +29,9 @@ using rp::Problem;
 struct rp_ctx {
   int device = 0;
   int sm_count = 0;
-  int ctas_per_sm = 0;
+  int ctas_per_sm = 0;       // general kernel, 64-register build (two CTAs per SM)
+  int ctas_per_sm1 = 0;      // general kernel, 128-register build (one CTA per SM: long problems)
+  int mcc_long_n = 400;      // problems at least this long run the 128-register build (RP_MCC_LONG_N)
   int ls_threads = RP_LS_THREADS;
   int ls_ctas_per_sm = 0;
   // The batch-lockstep schedule is OFF by default: measured on B200 (1000 MicA x ompA shuffles) it
@@ -79,6 +81,7 @@ struct rp_batch {
   int* d_order = nullptr;
   // lockstep groups (same-shape problems, RP_LS_G per CTA)
   std::vector<rp::GroupDev> groups;
+  int mcc_minb = 2;           // register budget of the general kernel for this batch (kernels.h)
   int grid_cached = -1, ls_grid_cached = -1;  // launch shapes, fixed at the first run (cudaMemGetInfo is slow)
   int n_general = 0;          // problems left to the general kernel + duplex (entries of order after the band classes)
   // band classes: order = [class L | class S | general]
@@ -176,8 +179,8 @@ void pool_release(rp_ctx* ctx, void* p) {
 }
 
 // number of CTAs (= workspace slots) for a batch
-int grid_for(const rp_ctx* ctx, int nprob, size_t slot_bytes) {
-  int g = ctx->sm_count * std::max(1, ctx->ctas_per_sm);
+int grid_for(const rp_ctx* ctx, int nprob, size_t slot_bytes, int minb) {
+  int g = ctx->sm_count * std::max(1, minb >= 2 ? ctx->ctas_per_sm : ctx->ctas_per_sm1);
   g = std::min(g, std::max(1, nprob));
   if (const char* e = std::getenv("RP_GRID")) {  // tuning aid
     int v = std::atoi(e);
@@ -357,7 +360,9 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
     int t = std::atoi(e) / 32 * 32;
     if (t >= 64 && t <= RP_MCC_THREADS) ctx->threads = t;
   }
-  ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads);
+  ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads, 2);
+  ctx->ctas_per_sm1 = rp::mcc_max_ctas_per_sm(ctx->threads, 1);
+  if (const char* e = std::getenv("RP_MCC_LONG_N")) ctx->mcc_long_n = std::atoi(e);
   if (const char* e = std::getenv("RP_LS_THREADS")) {
     int t = std::atoi(e) / 32 * 32;
     if (t >= 32 && t <= RP_LS_THREADS) ctx->ls_threads = t;
@@ -569,6 +574,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   }
   b->n_mcc = gen_mcc;
   b->slot_doubles = std::max(gen_mcc ? rp::slot_doubles(gen_maxn) : (size_t)0, ws_need);
+  b->mcc_minb = (gen_maxn >= ctx->mcc_long_n && ctx->ctas_per_sm1 > 0) ? 1 : 2;
 
   auto bail = [&](cudaError_t e, const char* what) {
     rp_batch_destroy(b);
@@ -610,7 +616,7 @@ int rp_batch_run(rp_batch* b) {
   ctx->timing.alg_flops = b->alg_flops;
   if (nprob == 0) { ctx->timing_pending = false; return RP_OK; }
   const size_t slot_bytes = b->slot_doubles * sizeof(double);
-  if (b->grid_cached < 0) b->grid_cached = b->n_general > 0 ? grid_for(ctx, b->n_general, std::max<size_t>(slot_bytes, 8)) : 0;
+  if (b->grid_cached < 0) b->grid_cached = b->n_general > 0 ? grid_for(ctx, b->n_general, std::max<size_t>(slot_bytes, 8), b->mcc_minb) : 0;
   const int grid = b->grid_cached;
   // lockstep: one CTA slot holds RP_LS_G problem workspaces
   const int ngroups = (int)b->groups.size();
@@ -704,7 +710,7 @@ int rp_batch_run(rp_batch* b) {
     launches++;
   }
   if (b->n_mcc > 0) {
-    CU(rp::launch_mcc(d, grid, ctx->threads, st));
+    CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, st));
     launches++;
   }
   if (b->n_duplex > 0) {

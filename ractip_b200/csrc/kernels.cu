@@ -34,7 +34,12 @@ struct CtaExec {
 
 }  // namespace
 
-__global__ void __launch_bounds__(RP_MCC_THREADS, RP_MCC_MIN_CTAS) mcc_persistent(BatchDev b) {
+// Instantiated for two register budgets: <2> two CTAs per SM at 64 registers (many short problems
+// in flight) and <1> one CTA per SM at 128 registers (long problems: the split-sum band phases keep
+// their accumulators, operand windows and four steps' loads in registers without spilling, and half
+// as many problem histories compete for the L2).
+template <int MINB>
+__global__ void __launch_bounds__(RP_MCC_THREADS, MINB) mcc_persistent(BatchDev b) {
   extern __shared__ double smem_raw[];
   __shared__ int s_next;
   CtaExec ex;
@@ -373,17 +378,19 @@ __global__ void __launch_bounds__(256) peak_smem_kernel(double* out, int iters) 
 // ---------------------------------------------------------------------------
 // host-callable launchers
 // ---------------------------------------------------------------------------
-int mcc_max_ctas_per_sm(int threads) {
+int mcc_max_ctas_per_sm(int threads, int minb) {
   int n = 0;
   size_t smem = shared_bytes(threads);
-  cudaFuncSetAttribute(mcc_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mcc_persistent, threads, smem) != cudaSuccess) return 0;
-  return n;
+  auto k = minb >= 2 ? mcc_persistent<RP_MCC_MIN_CTAS> : mcc_persistent<1>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem) != cudaSuccess) return 0;
+  return minb >= 2 ? n : (n > 1 ? 1 : n);
 }
 
-cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, cudaStream_t st) {
+cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, cudaStream_t st) {
   size_t smem = shared_bytes(threads);
-  mcc_persistent<<<grid, threads, smem, st>>>(b);
+  if (minb >= 2) mcc_persistent<RP_MCC_MIN_CTAS><<<grid, threads, smem, st>>>(b);
+  else mcc_persistent<1><<<grid, threads, smem, st>>>(b);
   return cudaGetLastError();
 }
 

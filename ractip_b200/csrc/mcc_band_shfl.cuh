@@ -309,6 +309,7 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
 }
 __device__ __forceinline__ void outside_band_B_shfl(Ctx& c, const Shared& sh, int d0, int r0, int C, int tid) {
   const int T = sh.T, n = c.n;
+  const bool keep = c.kind == KIND_LINEAR && c.max_w > 0;
   const SplitW sp = make_split_w(C, T);
   for (int x = tid; x < BAND * C; x += T) {
     const int e = x / C, cell = x % C, r = r0 + cell, d = d0 - e;
@@ -319,7 +320,10 @@ __device__ __forceinline__ void outside_band_B_shfl(Ctx& c, const Shared& sh, in
       b += sh.part[((size_t)(BAND + e) * sp.S + s) * sp.CP + cell];
     }
     const int k = 1 + r;
-    if (k + d <= n) TB(c, T_PRB, d, k) = a;
+    if (k + d <= n) {
+      TB(c, T_PRB, d, k) = a;
+      if (keep) RP_ST_STREAM(TB(c, T_XX, d, k), a);   // the unpaired-window pass reads PR again (unstru_windows)
+    }
     const int l = d0 - BAND + 2 + r, k2 = l - d;
     if (l <= n && k2 >= 1) TB(c, T_MLB, d, k2) = b;
   }

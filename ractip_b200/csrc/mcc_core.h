@@ -1052,6 +1052,7 @@ RP_HD void outside_band_A(const Ctx& c, const Shared& sh, int d0, int r0, int C,
 }
 RP_HD void outside_band_B(Ctx& c, const Shared& sh, int d0, int r0, int C, int tid) {
   const int T = sh.T, n = c.n;
+  const bool keep = c.kind == KIND_LINEAR && c.max_w > 0;
   const Split sp = make_split(C, T);
   for (int x = tid; x < BAND * C; x += T) {
     const int e = x / C, cell = x % C, r = r0 + cell, d = d0 - e;
@@ -1062,7 +1063,10 @@ RP_HD void outside_band_B(Ctx& c, const Shared& sh, int d0, int r0, int C, int t
       b += sh.part[(size_t)(BAND + e) * T + s * sp.Cp + cell];
     }
     const int k = 1 + r;                       // PR cell (k, k+d)
-    if (k + d <= n) TB(c, T_PRB, d, k) = a;
+    if (k + d <= n) {
+      TB(c, T_PRB, d, k) = a;
+      if (keep) RP_ST_STREAM(TB(c, T_XX, d, k), a);   // the unpaired-window pass reads PR again (unstru_windows)
+    }
     const int l = d0 - BAND + 2 + r, k2 = l - d;  // MLL cell (l-d, l)
     if (l <= n && k2 >= 1) TB(c, T_MLB, d, k2) = b;
   }
@@ -1101,6 +1105,7 @@ RP_HD void outside_cells(C& c, const Shared& sh, int d, int ct, int nct) {
     const double sI = type ? outside_interior(c, sh, d, k, 0, 1) : 0.;
     double sP, sL;
     outside_splits(c, d, k, type != 0, 0, 1, sP, sL);
+    if (c.kind == KIND_LINEAR && c.max_w > 0) TB(c, T_XX, d, k) = sP;
     outside_finish(c, d, k, type, sI, sP, sL);
   }
 }
@@ -1296,35 +1301,54 @@ RP_HD void unstru_dom_cols(C& c, int tid, int T) {
     }
   }
 }
-// U5: RR(p,j) = sum_{o>=j+2} Mc(p,o) QM2(j+1,o-1)
-//     LL(i,o) = sum_{p<=i-2} Mc(p,o) QM2(p+1,i-1)
-//     XX(i,o) = sum_{p<=i-2} Mc(p,o) qm (p+1,i-1)
+// U5/U6: the multiloop part of the unpaired-window probabilities.  The window [i..j] (dd = j-i) lies in
+// the loop closed by (p,o), p < i, j < o, next to the closing pair's unpaired run or between stems:
+//   m1 = sum_{p<i} mlb^(j-p)  sum_{o>=j+2} Mc(p,o) QM2(j+1,o-1)           window in the 5' run, >= 2 stems follow
+//   m2 = sum_{o>j} mlb^(o-i)  sum_{p<=i-2} Mc(p,o) QM2(p+1,i-1)           window in the 3' run, >= 2 stems before
+//   m3 = mlb^(dd+1) sum_{p,o} qm(p+1,i-1) Mc(p,o) qm(j+1,o-1)             stems on both sides
+// Summed in this order the inner sums are O(n) per CELL (O(n^3) in all, as in ViennaRNA's pf_unstru).
+// Exchanging the sums leaves O(n) per WINDOW (n*max_w windows):
+//   m1 = mlb^dd     sum_o QM2(j+1,o-1) K(i,o),     K(i,o)  = sum_{p<i} Mc(p,o) mlb^(i-p)     column scan of Mc
+//   m2 = mlb^(dd+1) sum_p QM2(p+1,i-1) PLf(p,j),   PLf(p,j) = sum_{o>j} Mc(p,o) mlb^(o-j-1)  row scan of Mc
+//   m3 = mlb^(dd+1) sum_p qm(p+1,i-1)  PR(p,j),    PR(p,j)  = sum_o Mc(p,o) qm(j+1,o-1)
+// and PR is the outside pass's own right-hand multiloop sum, which the band phases leave in T_XX for
+// single-strand problems with windows.  Tables: K -> T_RR, PLf -> T_LL.
 template <class C>
 RP_HD void unstru_ml_tables(C& c, int tid, int T) {
   const int n = c.n;
-  const size_t total = (size_t)n * c.ld;
-  for (size_t x = tid; x < total; x += T) {
-    const int e = (int)(x / c.ld), i = (int)(x % c.ld);
-    if (i < 1 || i + e > n) continue;
-    const int o = i + e;  // cell (i,o); also (p,j) for RR
-    double r = 0., l2 = 0., l1 = 0.;
-    for (int b = 2 * TURN + 3; b <= n - o - 2; b++) r += TB(c, T_MC, e + 2 + b, i) * TB(c, T_QM2, b, o + 1);
-    for (int cc = TURN + 1; cc <= i - 3; cc++) {
-      const double m = TB(c, T_MC, e + 2 + cc, i - 2 - cc);
-      l2 += m * TB(c, T_QM2, cc, i - 1 - cc);
-      l1 += m * TB(c, T_QM, cc, i - 1 - cc);
+  const double mlb1 = c.M->mlb1;
+  // both scans walk the diagonals downwards, every thread on the same diagonal at the same step, so
+  // that the threads of a warp touch consecutive elements
+  for (int p0 = 1; p0 < n; p0 += T) {          // row p: PLf(p,j), j = n .. p+1
+    const int p = p0 + tid;
+    double s = 0.;
+#pragma unroll 8
+    for (int d = n - p0; d >= 1; d--) {
+      if (d > n - p) continue;
+      const double mc = TB(c, T_MC, d, p);
+      TB(c, T_LL, d, p) = s;
+      s = s * mlb1 + mc;
     }
-    TB(c, T_RR, e, i) = r;
-    TB(c, T_LL, e, i) = l2;
-    TB(c, T_XX, e, i) = l1;
+  }
+  for (int o0 = 2; o0 <= n; o0 += T) {         // column o: K(i,o), i = 1 .. o-1
+    const int o = o0 + tid, top = (o0 + T - 1 < n ? o0 + T - 1 : n) - 1;
+    double s = 0.;
+#pragma unroll 8
+    for (int d = top; d >= 1; d--) {
+      if (o > n || d > o - 1) continue;
+      const double mc = TB(c, T_MC, d, o - d);
+      TB(c, T_RR, d, o - d) = s;
+      s = mlb1 * (s + mc);
+    }
   }
 }
-// U6: assemble; writes fp32 in the reference layout up[(i-1)*max_w + d]
+// U6: assemble; writes fp32 in the reference layout up[(i-1)*max_w + d].  Consecutive threads take
+// consecutive i of the same window length: every operand stream is unit-stride across the warp.
 template <class C>
 RP_HD void unstru_windows(C& c, float* up, int tid, int T) {
   const int n = c.n, w = c.max_w;
   for (int x = tid; x < n * w; x += T) {
-    const int i = x / w + 1, dd = x % w, j = i + dd;
+    const int dd = x / n, i = x % n + 1, j = i + dd;
     double v = 0.;
     if (j <= n) {
       const double q5 = i > 1 ? TB(c, T_Q, i - 2, 1) : 1.0;
@@ -1333,14 +1357,30 @@ RP_HD void unstru_windows(C& c, float* up, int tid, int T) {
       if (i > 1 && j < n) {
         v += TB(c, T_DG, j - i + 2, i - 1);
         double m1 = 0., m2 = 0., m3 = 0.;
-        for (int p = 1; p < i; p++) m1 += VEC(c, V_MLB, j - p) * TB(c, T_RR, j - p, p);
-        for (int o = j + 1; o <= n; o++) m2 += VEC(c, V_MLB, o - i) * TB(c, T_LL, o - i, i);
-        for (int o = j + 2 + TURN + 1; o <= n; o++) m3 += TB(c, T_QM, o - j - 2, j + 1) * TB(c, T_XX, o - i, i);
+        {
+          const double* A = c.ptr(T_QM2, 2 * TURN + 3, j + 1);
+          const double* B = c.ptr(T_RR, dd + 2 * TURN + 5, i);
+          const int cnt = n - j - 2 - (2 * TURN + 3) + 1, ds = c.dstep();
+#pragma unroll 4
+          for (int t = 0; t < cnt; t++) m1 += A[(long)t * ds] * B[(long)t * ds];
+        }
+        {
+          const int cnt = i - 3 - TURN, st = c.dstep() - c.pstep();   // cc = TURN+1+t: one diagonal up, one cell left
+          const double* A2 = c.ptr(T_QM2, TURN + 1, i - 2 - TURN);
+          const double* A1 = c.ptr(T_QM, TURN + 1, i - 2 - TURN);
+          const double* BL = c.ptr(T_LL, dd + TURN + 3, i - 3 - TURN);
+          const double* BR = c.ptr(T_XX, dd + TURN + 3, i - 3 - TURN);
+#pragma unroll 4
+          for (int t = 0; t < cnt; t++) {
+            m2 += A2[(long)t * st] * BL[(long)t * st];
+            m3 += A1[(long)t * st] * BR[(long)t * st];
+          }
+        }
         // Mc carries no scale factor for the closing pair's two bases: apply it here
-        v += (m1 + m2 + m3 * VEC(c, V_MLB, dd + 1)) * VEC(c, V_SCALE, 2);
+        v += (m1 * VEC(c, V_MLB, dd) + (m2 + m3) * VEC(c, V_MLB, dd + 1)) * VEC(c, V_SCALE, 2);
       }
     }
-    RP_ST_STREAM(up[x], (float)v);
+    RP_ST_STREAM(up[(size_t)(i - 1) * w + dd], (float)v);
   }
 }
 

@@ -87,11 +87,26 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
   for (int d = TURN + 1; d <= n - 1; d++) {
     if (d == band_start_inside(d)) {
       const int rows = n - d;
-      const int chunk = make_split(rows, T).Cp;
+      int chunk = make_split(rows, T).Cp;
+#ifdef __CUDA_ARCH__
+      if (chunk > HW * (T / 32)) chunk = HW * (T / 32);   // shuffle variant: 28 rows per warp
+#endif
       for (int i0 = 1; i0 <= rows; i0 += chunk) {
         const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
-        ex.phase(PH_BAND_A, [&](int tid) { inside_band_A(c, sh, d, i0, C, tid); });
-        ex.phase(PH_BAND_B, [&](int tid) { inside_band_B(c, sh, d, i0, C, tid); });
+        ex.phase(PH_BAND_A, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          inside_band_A_shfl(c, sh, d, i0, C, tid);   // same sums, operands passed along the warp
+#else
+          inside_band_A(c, sh, d, i0, C, tid);
+#endif
+        });
+        ex.phase(PH_BAND_B, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          inside_band_B_shfl(c, sh, d, i0, C, tid);
+#else
+          inside_band_B(c, sh, d, i0, C, tid);
+#endif
+        });
       }
     }
     const int cells = n - d;
@@ -117,11 +132,26 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
     }
     if ((n - 1 - d) % BAND == 0) {  // a band of diagonals d, d-1, ..., d-BAND+1 starts here
       const int rows = n - d + BAND - 1;
-      const int chunk = make_split(rows, T).Cp;
+      int chunk = make_split(rows, T).Cp;
+#ifdef __CUDA_ARCH__
+      if (chunk > HW * (T / 32)) chunk = HW * (T / 32);
+#endif
       for (int r0 = 0; r0 < rows; r0 += chunk) {
         const int C = rows - r0 < chunk ? rows - r0 : chunk;
-        ex.phase(PH_BAND_A, [&](int tid) { outside_band_A(c, sh, d, r0, C, tid); });
-        ex.phase(PH_BAND_B, [&](int tid) { outside_band_B(c, sh, d, r0, C, tid); });
+        ex.phase(PH_BAND_A, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          outside_band_A_shfl(c, sh, d, r0, C, tid);
+#else
+          outside_band_A(c, sh, d, r0, C, tid);
+#endif
+        });
+        ex.phase(PH_BAND_B, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          outside_band_B_shfl(c, sh, d, r0, C, tid);
+#else
+          outside_band_B(c, sh, d, r0, C, tid);
+#endif
+        });
       }
     }
     const int cells = n - d;
