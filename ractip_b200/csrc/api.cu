@@ -31,7 +31,8 @@ struct rp_ctx {
   int sm_count = 0;
   int ctas_per_sm = 0;       // general kernel, 64-register build (two CTAs per SM)
   int ctas_per_sm1 = 0;      // general kernel, 128-register build (one CTA per SM: long problems)
-  int mcc_long_n = 400;      // problems at least this long run the 128-register build (RP_MCC_LONG_N)
+  int mcc_long_n = 900;      // problems at least this long run the 128-register build (RP_MCC_LONG_N)
+  int mcc_wide = 10;         // ... with split-sum bands of this many diagonals (RP_MCC_WIDE: 5, 10, 15)
   int ls_threads = RP_LS_THREADS;
   int ls_ctas_per_sm = 0;
   // The batch-lockstep schedule is OFF by default: measured on B200 (1000 MicA x ompA shuffles) it
@@ -360,9 +361,10 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
     int t = std::atoi(e) / 32 * 32;
     if (t >= 64 && t <= RP_MCC_THREADS) ctx->threads = t;
   }
-  ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads, 2);
-  ctx->ctas_per_sm1 = rp::mcc_max_ctas_per_sm(ctx->threads, 1);
   if (const char* e = std::getenv("RP_MCC_LONG_N")) ctx->mcc_long_n = std::atoi(e);
+  if (const char* e = std::getenv("RP_MCC_WIDE")) ctx->mcc_wide = std::atoi(e);
+  ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads, 2, ctx->mcc_wide);
+  ctx->ctas_per_sm1 = rp::mcc_max_ctas_per_sm(ctx->threads, 1, ctx->mcc_wide);
   if (const char* e = std::getenv("RP_LS_THREADS")) {
     int t = std::atoi(e) / 32 * 32;
     if (t >= 32 && t <= RP_LS_THREADS) ctx->ls_threads = t;
@@ -710,7 +712,7 @@ int rp_batch_run(rp_batch* b) {
     launches++;
   }
   if (b->n_mcc > 0) {
-    CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, st));
+    CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, ctx->mcc_wide, st));
     launches++;
   }
   if (b->n_duplex > 0) {

@@ -16,7 +16,10 @@ namespace rp {
 
 namespace {
 
-struct CtaExec {
+template <int NB = 4, int W = BAND>
+struct CtaExecT {
+  static constexpr int kBatch = NB;   // load-batch depth of the split-sum band phases (mcc_band_shfl.cuh)
+  static constexpr int kWide = W;     // diagonals per split-sum band of the general kernel (solve_mcc_wide when > BAND)
   long long* prof;  // optional per-phase cycle counters (RP_PROFILE=1), else null
   __device__ __forceinline__ int nthreads() const { return blockDim.x; }
   template <class F>
@@ -32,20 +35,24 @@ struct CtaExec {
   }
 };
 
+using CtaExec = CtaExecT<4>;
+
 }  // namespace
 
 // Instantiated for two register budgets: <2> two CTAs per SM at 64 registers (many short problems
 // in flight) and <1> one CTA per SM at 128 registers (long problems: the split-sum band phases keep
 // their accumulators, operand windows and four steps' loads in registers without spilling, and half
 // as many problem histories compete for the L2).
-template <int MINB>
+// <1, W> with W > BAND sums the split sums in wide bands (solve_mcc_wide): W-fold reuse of every element
+// streamed from HBM.
+template <int MINB, int W>
 __global__ void __launch_bounds__(RP_MCC_THREADS, MINB) mcc_persistent(BatchDev b) {
   extern __shared__ double smem_raw[];
   __shared__ int s_next;
-  CtaExec ex;
+  CtaExecT<(MINB >= 2 ? 2 : 4), W> ex;
   ex.prof = b.prof;
   Shared sh;
-  carve_shared(sh, smem_raw, blockDim.x);
+  carve_shared(sh, smem_raw, blockDim.x, W);
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(b.counter, 1);
     __syncthreads();
@@ -57,7 +64,8 @@ __global__ void __launch_bounds__(RP_MCC_THREADS, MINB) mcc_persistent(BatchDev 
     Ctx c;
     bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)blockIdx.x * b.slot_stride);
     c.dbg = b.dbg;
-    solve_mcc(ex, c, p, b.dense, b.logz, sh);
+    if (W > BAND) solve_mcc_wide(ex, c, p, b.dense, b.logz, sh);
+    else solve_mcc(ex, c, p, b.dense, b.logz, sh);
   }
 }
 
@@ -378,19 +386,33 @@ __global__ void __launch_bounds__(256) peak_smem_kernel(double* out, int iters) 
 // ---------------------------------------------------------------------------
 // host-callable launchers
 // ---------------------------------------------------------------------------
-int mcc_max_ctas_per_sm(int threads, int minb) {
-  int n = 0;
-  size_t smem = shared_bytes(threads);
-  auto k = minb >= 2 ? mcc_persistent<RP_MCC_MIN_CTAS> : mcc_persistent<1>;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+namespace {
+using MccKernel = void (*)(BatchDev);
+// minb = 2: 64-register build, BAND-wide sums; minb = 1: 128 registers, bands of `wide` diagonals (5, 10 or 15)
+MccKernel mcc_kernel(int minb, int wide, int* w_out) {
+  if (minb >= 2) { *w_out = BAND; return mcc_persistent<RP_MCC_MIN_CTAS, BAND>; }
+  if (wide >= 15) { *w_out = 15; return mcc_persistent<1, 15>; }
+  if (wide >= 10) { *w_out = 10; return mcc_persistent<1, 10>; }
+  *w_out = BAND;
+  return mcc_persistent<1, BAND>;
+}
+}  // namespace
+
+int mcc_max_ctas_per_sm(int threads, int minb, int wide) {
+  int n = 0, w = BAND;
+  MccKernel k = mcc_kernel(minb, wide, &w);
+  size_t smem = shared_bytes(threads, w);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem) != cudaSuccess) return 0;
   return minb >= 2 ? n : (n > 1 ? 1 : n);
 }
 
-cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, cudaStream_t st) {
-  size_t smem = shared_bytes(threads);
-  if (minb >= 2) mcc_persistent<RP_MCC_MIN_CTAS><<<grid, threads, smem, st>>>(b);
-  else mcc_persistent<1><<<grid, threads, smem, st>>>(b);
+cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, int wide, cudaStream_t st) {
+  int w = BAND;
+  MccKernel k = mcc_kernel(minb, wide, &w);
+  size_t smem = shared_bytes(threads, w);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<grid, threads, smem, st>>>(b);
   return cudaGetLastError();
 }
 

@@ -75,8 +75,9 @@ struct SparseDev {
   float th_ss, th_hy;
 };
 
-int mcc_max_ctas_per_sm(int threads, int minb);   // minb = 2: 64-register build, two CTAs per SM; 1: 128 registers, one CTA per SM
-cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, cudaStream_t st);
+// minb = 2: 64-register build, two CTAs per SM; 1: 128 registers, one CTA per SM, split sums in bands of `wide` diagonals
+int mcc_max_ctas_per_sm(int threads, int minb, int wide);
+cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, int wide, cudaStream_t st);
 int band_max_ctas_per_sm(int threads, size_t smem);   // threads = 512 or 256
 cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, cudaStream_t st);
 int lockstep_max_ctas_per_sm(int threads);

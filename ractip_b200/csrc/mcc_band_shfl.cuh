@@ -51,6 +51,8 @@ __device__ __forceinline__ SplitW make_split_w(int C, int T) {
 }
 // partial (sum w, diagonal e, slice sl, row cell) at part[((w*BAND+e)*S + sl)*CP + cell]
 
+// NB: steps whose loads are issued together (4 with 128 registers per thread, 2 in the 64-register build)
+template <int NB = 4>
 __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& sh, int d0, int i0, int C, int tid) {
   const int T = sh.T;
   const SplitW sp = make_split_w(C, T);
@@ -100,10 +102,10 @@ __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& s
       }
       bool first = true;
 #pragma unroll 1
-      for (int a = a_lo; a <= a_hi; a += 4) {
-        double Am[4], Aq[4], b0m[4], b0q[4];
+      for (int a = a_lo; a <= a_hi; a += NB) {
+        double Am[NB], Aq[NB], b0m[NB], b0q[NB];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < NB; u++) {
           const int au = a + u;
           const bool on = au <= a_hi;
           Am[u] = (on && own && au != askip) ? TB(c, T_QM, au, i) : 0.;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& s
           b0q[u] = (on && rowok) ? TB(c, T_QQ, d0 - 1 - au, i + 1 + au) : 0.;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < NB; u++) {
           if (a + u <= a_hi) {
             if (!first) {
 #pragma unroll
@@ -169,6 +171,7 @@ __device__ __forceinline__ void inside_band_B_shfl(Ctx& c, const Shared& sh, int
   }
 }
 
+template <int NB = 4>
 __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& sh, int d0, int r0, int C, int tid) {
   const int T = sh.T;
   const SplitW sp = make_split_w(C, T);
@@ -217,17 +220,17 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
         }
         bool first = true;
 #pragma unroll 1
-        for (int t = t_lo; t <= t_hi; t += 4) {
-          double A[4], b4[4];
+        for (int t = t_lo; t <= t_hi; t += NB) {
+          double A[NB], b4[NB];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
+          for (int u = 0; u < NB; u++) {
             const int tu = t + u;
             const bool on = tu <= t_hi && tu <= tmax;
             A[u] = (on && own) ? TB(c, T_MC, d0 + TURN + 3 + tu, k) : 0.;
             b4[u] = on ? *(c.ptr(T_QM, TURN + 1 + tu, k + d0 + 1) + (BAND - 1) * es) : 0.;
           }
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
+          for (int u = 0; u < NB; u++) {
             if (t + u <= t_hi) {
               if (!first) {
 #pragma unroll
@@ -266,17 +269,17 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
       // main part: B(e) = qm(i+1, k0+e-1) is the B(0) of the lane e places to the right, same step
       const int imain_hi = __shfl_sync(0xffffffffu, imain, HW - 1);   // largest among the owning lanes
 #pragma unroll 1
-      for (int i = 1 + slice; i <= imain_hi; i += 4 * S) {
-        double A[4], b0[4];
+      for (int i = 1 + slice; i <= imain_hi; i += NB * S) {
+        double A[NB], b0[NB];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < NB; u++) {
           const int iu = i + u * S;
           const int row0 = k0 - 2 - iu;   // diagonal of B(0)
           A[u] = (need != 0 && iu <= imain) ? TB(c, T_PRML, l - iu, iu) : 0.;
           b0[u] = (iu <= imain_hi && row0 >= 0 && k0 - 1 <= n) ? *(c.ptr(T_QM, 0, iu + 1) + (long)row0 * ds) : 0.;   // qm(iu+1, k0-1)
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < NB; u++) {
           double bv[BAND];
           bv[0] = b0[u];
 #pragma unroll

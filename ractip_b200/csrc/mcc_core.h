@@ -97,7 +97,7 @@ struct Ctx {
   // band.  A full table would leave every written line behind in L2, where it pushes out the history
   // tables the split sums stream (the 126 MB L2 holds the history of all resident problems, not more).
   RP_HD static constexpr unsigned ring_mask(int t) {
-    return (t == T_PR || t == T_PL || t == T_PMLB) ? 1u : (t == T_QS || t == T_PRB || t == T_MLB) ? 7u : 0xffffffffu;
+    return (t == T_PR || t == T_PL || t == T_PMLB) ? 1u : (t == T_QS || t == T_PRB || t == T_MLB) ? 15u : 0xffffffffu;
   }
   // 32-bit element offsets: one IMAD per term instead of 64-bit multiplies (a third of all instructions otherwise)
   RP_HD unsigned off(int t, int d, int i) const { return (unsigned)t * te + ((unsigned)d & ring_mask(t)) * (unsigned)ld + (unsigned)i; }
@@ -162,25 +162,28 @@ RP_HD uint16_t* posp(const Ctx& c) { return reinterpret_cast<uint16_t*>(c.ptr(T_
 // band starts: qm, qm1 and qq vanish on diagonals <= TURN, so the terms of diagonal d reach back at
 // least TURN+2 diagonals.
 constexpr int BAND = TURN + 2;
+// The general kernel can sum WIDE bands (wide_* functions): a far pass every W <= WIDE_MAX diagonals covers the
+// terms whose operands are final by then, the few remaining (near) terms are added when a cell is finished.
+constexpr int WIDE_MAX = 15;
 
 // CTA-shared scratch (CUDA shared memory; a heap block in the host emulation)
 constexpr int RP_SMEM_SEQ = 4096;  // sequence bytes staged in shared memory (n+2 general, (n+2)*G lockstep)
 struct Shared {
   int T;
-  double* part;     // [2*BAND][T] partial sums of the current phase (general kernel)
+  double* part;     // [2*W][T] partial sums of the current phase (general kernel; W = width of its bands)
   double* grow;     // [MAXLOOP+1][GROW_LD] run weights of the factorised interior loops (DevModel::grow)
   double* ghead_b;  // [GROW_LD]
   double* ghead_1;  // [GROW_LD]
   double* red;      // [128] small reductions (nick sums)
   uint8_t* S;       // [RP_SMEM_SEQ + 8] staged sequence(s)
 };
-RP_HD size_t shared_bytes(int T) {
-  return sizeof(double) * (2 * BAND * (size_t)T + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
+RP_HD size_t shared_bytes(int T, int W = BAND) {
+  return sizeof(double) * (2 * W * (size_t)T + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
 }
-RP_HD void carve_shared(Shared& sh, void* base, int T) {
+RP_HD void carve_shared(Shared& sh, void* base, int T, int W = BAND) {
   sh.T = T;
   double* p = static_cast<double*>(base);
-  sh.part = p; p += 2 * BAND * (size_t)T;
+  sh.part = p; p += 2 * W * (size_t)T;
   sh.grow = p; p += (MAXLOOP + 1) * GROW_LD;
   sh.ghead_b = p; p += GROW_LD;
   sh.ghead_1 = p; p += GROW_LD;
@@ -1108,6 +1111,192 @@ RP_HD void outside_cells(C& c, const Shared& sh, int d, int ct, int nct) {
     if (c.kind == KIND_LINEAR && c.max_w > 0) TB(c, T_XX, d, k) = sP;
     outside_finish(c, d, k, type, sI, sP, sL);
   }
+}
+
+// ---------------------------------------------------------------------------
+// Wide bands (general kernel, long problems).  With BAND = TURN+2 diagonals per pass every operand of
+// the split sums is final when the pass runs, but each pass streams the whole history of the tables
+// for 5 FMAs per loaded element -- for long problems that stream comes from HBM.  A band of W > BAND
+// diagonals reuses every loaded element W times.  The price: for the later diagonals of the band some
+// operands lie on diagonals of the band itself.  The far pass (wide_*_A/B, below) leaves those terms
+// out; inside_near / outside_near add them when the cell is finished (at most 2(W-BAND) per sum).
+//   inside, band D0 .. D0+W-1, cell (i, i+D0+e):  term a (operands qm[a][i], qm1[D0+e-1-a][i+1+a]) is
+//     far iff a <= D0-1 (first operand final) and a >= e (second operand final)
+//   outside, band d0 .. d0-W+1, cell of diagonal d0-e: term b (operand Mc or PRML on diagonal d+2+b)
+//     is far iff b >= e (diagonals >= d0+2 are final when the pass runs)
+// ---------------------------------------------------------------------------
+template <int W>
+RP_HD int wide_start_inside(int d) { return TURN + 1 + (d - TURN - 1) / W * W; }
+template <int W>
+RP_HD int wide_start_outside(int n, int d) { return n - 1 - (n - 1 - d) / W * W; }
+
+// host / reference form of the far pass (the CUDA build runs the shuffle variants of mcc_band_shfl.cuh)
+template <int W>
+RP_HD void wide_inside_A(const Ctx& c, const Shared& sh, int d0, int i0, int C, int tid) {
+  const int T = sh.T;
+  const Split sp = make_split(C, T);
+  const int cell = tid % sp.Cp, slice = tid / sp.Cp, S = sp.S;
+  if (slice >= S || cell >= C) return;
+  const int i = i0 + cell;
+  const long es = c.dstep();
+  double m[W], q[W];
+  for (int e = 0; e < W; e++) m[e] = q[e] = 0.;
+  if (!(c.dbg & 2)) {
+    const int amax = d0 - 1, lim = d0 - TURN - 2;
+    const int askip = c.cp > 0 ? c.cp - 1 - i : -1;
+    for (int a = slice; a <= amax; a += S) {
+      const double Aq = TB(c, T_Q, a, i);
+      const double Am = (a > TURN && a != askip) ? TB(c, T_QM, a, i) : 0.;
+      const double* Bm = c.ptr(T_QM1, d0 - 1 - a, i + 1 + a);
+      const double* Bq = c.ptr(T_QQ, d0 - 1 - a, i + 1 + a);
+      for (int e = 0; e < W; e++)
+        if (e >= a - lim && e <= a && i + d0 + e <= c.n) { m[e] += Am * Bm[e * es]; q[e] += Aq * Bq[e * es]; }
+    }
+  }
+  for (int e = 0; e < W; e++) {
+    sh.part[(size_t)e * T + tid] = m[e];
+    sh.part[(size_t)(W + e) * T + tid] = q[e];
+  }
+}
+template <int W>
+RP_HD void wide_inside_B(Ctx& c, const Shared& sh, int d0, int i0, int C, int tid) {
+  const int T = sh.T;
+  const Split sp = make_split(C, T);
+  for (int x = tid; x < W * C; x += T) {
+    const int e = x / C, cell = x % C, i = i0 + cell;
+    if (i + d0 + e > c.n) continue;
+    double m = 0., q = 0.;
+    for (int s = 0; s < sp.S; s++) {
+      m += sh.part[(size_t)e * T + s * sp.Cp + cell];
+      q += sh.part[(size_t)(W + e) * T + s * sp.Cp + cell];
+    }
+    TB(c, T_QM2, d0 + e, i) = m;
+    TB(c, T_QS, d0 + e, i) = q;
+  }
+}
+// the terms of cell (i, i+d) the far pass of its band could not see
+template <int W>
+RP_HD void inside_near(const Ctx& c, int d, int i, double& sM, double& sQ) {
+  const int d0 = wide_start_inside<W>(d), e = d - d0, hi = d - TURN - 2;
+  const int askip = c.cp > 0 ? c.cp - 1 - i : -1;
+  for (int a = 0; a < e && a <= hi; a++) {             // second operand on a diagonal of the band
+    sQ += TB(c, T_Q, a, i) * TB(c, T_QQ, d - 1 - a, i + 1 + a);
+    if (a > TURN && a != askip) sM += TB(c, T_QM, a, i) * TB(c, T_QM1, d - 1 - a, i + 1 + a);
+  }
+  for (int a = (d0 > e ? d0 : e); a <= hi; a++) {      // first operand on a diagonal of the band
+    sQ += TB(c, T_Q, a, i) * TB(c, T_QQ, d - 1 - a, i + 1 + a);
+    if (a != askip) sM += TB(c, T_QM, a, i) * TB(c, T_QM1, d - 1 - a, i + 1 + a);
+  }
+}
+
+template <int W>
+RP_HD void wide_outside_A(const Ctx& c, const Shared& sh, int d0, int r0, int C, int tid) {
+  const int T = sh.T;
+  const Split sp = make_split(C, T);
+  const int cell = tid % sp.Cp, slice = tid / sp.Cp, S = sp.S;
+  if (slice >= S || cell >= C) return;
+  const int r = r0 + cell, n = c.n, ds = c.dstep(), ps = c.pstep();
+  double pr[W], ml[W];
+  for (int e = 0; e < W; e++) pr[e] = ml[e] = 0.;
+  if (!(c.dbg & 2)) {
+    {  // PR, row k; t = b - (TURN+1) - e: Mc on diagonal d0+TURN+3+t (final iff t >= -(TURN+1)), qm on diagonal TURN+1+t+e
+      const int k = 1 + r;
+      const int tmax = n - k - d0 - (TURN + 3);
+      const long es = ds - ps;
+      for (int t = -(TURN + 1) + slice; t <= tmax; t += S) {
+        const double A = TB(c, T_MC, d0 + TURN + 3 + t, k);
+        const double* B = c.ptr(T_QM, TURN + 1 + t, k + d0 + 1);
+        for (int e = 0; e < W; e++)
+          if (e >= -t && k + d0 - e <= n && d0 - e >= 1) pr[e] += A * B[e * es];
+      }
+    }
+    {  // ML-left, column l; cells (k0+e, l), k0 = l-d0; term i: PRML(i,l) on diagonal l-i (final iff i <= k0-2)
+      const int l = d0 - W + 2 + r, k0 = l - d0;
+      if (l <= n) {
+        unsigned need = 0;
+        for (int e = 0; e < W; e++) {
+          const int k = k0 + e, d = d0 - e;
+          if (k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) && TB(c, T_QB, d, k) != 0.) need |= 1u << e;
+        }
+        if (need) {
+          const int ifar = k0 - 2;
+          for (int i = 1 + slice; i <= ifar; i += S) {
+            const double A = TB(c, T_PRML, l - i, i);
+            const double* B = c.ptr(T_QM, 0, i + 1) + (long)(k0 - 2 - i) * ds;   // qm(i+1, k0-1); per e one diagonal up
+            const int emin = i - k0 + TURN + 3;
+            for (int e = 0; e < W; e++)
+              if (e >= emin && ((need >> e) & 1)) ml[e] += A * B[(long)e * ds];
+          }
+        }
+      }
+    }
+  }
+  for (int e = 0; e < W; e++) {
+    sh.part[(size_t)e * T + tid] = pr[e];
+    sh.part[(size_t)(W + e) * T + tid] = ml[e];
+  }
+}
+template <int W>
+RP_HD void wide_outside_B(Ctx& c, const Shared& sh, int d0, int r0, int C, int tid) {
+  const int T = sh.T, n = c.n;
+  const Split sp = make_split(C, T);
+  for (int x = tid; x < W * C; x += T) {
+    const int e = x / C, cell = x % C, r = r0 + cell, d = d0 - e;
+    if (d < 1) continue;
+    double a = 0., b = 0.;
+    for (int s = 0; s < sp.S; s++) {
+      a += sh.part[(size_t)e * T + s * sp.Cp + cell];
+      b += sh.part[(size_t)(W + e) * T + s * sp.Cp + cell];
+    }
+    const int k = 1 + r;                        // PR cell (k, k+d)
+    if (k + d <= n) TB(c, T_PRB, d, k) = a;
+    const int l = d0 - W + 2 + r, k2 = l - d;   // MLL cell (l-d, l)
+    if (l <= n && k2 >= 1) TB(c, T_MLB, d, k2) = b;
+  }
+}
+// per diagonal, phase B of the wide schedule: as inside_B, plus the near terms
+template <int W>
+RP_HD void wide_inside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if (tid >= C) return;
+  const int i = i0 + tid;
+  double sI = 0.;
+  double sM = TB(c, T_QM2, d, i), sQ = TB(c, T_QS, d, i);
+  inside_near<W>(c, d, i, sM, sQ);
+  const int type = pair_type(base(c, i), base(c, i + d));
+  if (type && d - (TURN + 1) >= 2) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = (int)posp(c)[(size_t)d * c.ld + i] - is.lo;
+    for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+  }
+  TB(c, T_QM2, d, i) = sM;   // complete now: the closing sum of (i-1,i+d+1) and the unpaired-window pass read it
+  inside_finish(c, d, i, type, sI, sM, sQ);
+}
+// near terms of cell (k, k+d): Mc / PRML on diagonals d+2+b < d0+2, i.e. b < e = d0-d
+template <int W>
+RP_HD void outside_near(const Ctx& c, int d, int k, bool pairs, double& sP, double& sL) {
+  const int n = c.n, l = k + d, d0 = wide_start_outside<W>(n, d), e = d0 - d;
+  for (int b = TURN + 1; b < e && b <= n - l - 2; b++) sP += TB(c, T_MC, d + 2 + b, k) * TB(c, T_QM, b, l + 1);
+  if (pairs)
+    for (int cc = TURN + 1; cc < e && cc <= k - 3; cc++) sL += TB(c, T_PRML, d + 2 + cc, k - 2 - cc) * TB(c, T_QM, cc, k - 1 - cc);
+}
+template <int W>
+RP_HD void wide_outside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if (tid >= C) return;
+  const int k = i0 + tid, l = k + d;
+  double sI = 0.;
+  double sP = TB(c, T_PRB, d, k), sL = TB(c, T_MLB, d, k);
+  const int type = pair_type(base(c, k), base(c, l));
+  const bool pairs = type && TB(c, T_QB, d, k) != 0.;
+  outside_near<W>(c, d, k, pairs && k > 2 && l < c.n, sP, sL);
+  if (pairs && c.n - 1 - d >= 2) {
+    const ISplit is = make_isplit(c, d, i0, C, T);
+    const int r = (int)posp(c)[(size_t)d * c.ld + k] - is.lo;
+    for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+  }
+  if (c.kind == KIND_LINEAR && c.max_w > 0) RP_ST_STREAM(TB(c, T_XX, d, k), sP);   // PR for the unpaired-window pass
+  outside_finish(c, d, k, type, sI, sP, sL);
 }
 
 // ---------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 #include "mcc_core.h"
 #ifdef __CUDACC__
 #include "mcc_band_shfl.cuh"
+#include "mcc_wide_shfl.cuh"
 #endif
 
 namespace rp {
@@ -95,7 +96,7 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
         const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
         ex.phase(PH_BAND_A, [&](int tid) {
 #ifdef __CUDA_ARCH__
-          inside_band_A_shfl(c, sh, d, i0, C, tid);   // same sums, operands passed along the warp
+          inside_band_A_shfl<Exec::kBatch>(c, sh, d, i0, C, tid);   // same sums, operands passed along the warp
 #else
           inside_band_A(c, sh, d, i0, C, tid);
 #endif
@@ -140,7 +141,7 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
         const int C = rows - r0 < chunk ? rows - r0 : chunk;
         ex.phase(PH_BAND_A, [&](int tid) {
 #ifdef __CUDA_ARCH__
-          outside_band_A_shfl(c, sh, d, r0, C, tid);
+          outside_band_A_shfl<Exec::kBatch>(c, sh, d, r0, C, tid);
 #else
           outside_band_A(c, sh, d, r0, C, tid);
 #endif
@@ -160,6 +161,110 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
       const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
       ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
       ex.phase(PH_OUTSIDE_B, [&](int tid) { outside_B(c, sh, d, i0, C, tid); });
+    }
+  }
+  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M, &c.M->gfull[0][0]);
+}
+
+// ---------------------------------------------------------------------------
+// general kernel, wide-band schedule (long problems): as solve_mcc, but the split sums are computed
+// W = Exec::kWide diagonals at a time (far pass, "Wide bands" in mcc_core.h) and the finishing phase
+// of a diagonal adds the few terms the far pass could not see.  `sh` must be carved with W.
+// ---------------------------------------------------------------------------
+template <class Exec>
+RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, double* logz, const Shared& sh) {
+  constexpr int W = Exec::kWide;
+  const int T = sh.T;
+  const int n = c.n;
+  if (n + 2 <= RP_SMEM_SEQ) {
+    const uint8_t* gS = c.S;
+    ex.phase(PH_STAGE, [&](int tid) {
+      for (int x = tid; x <= n + 1; x += T) sh.S[x] = gS[x];
+    });
+    c.S = sh.S;
+  }
+  ex.phase(PH_PROLOGUE, [&](int tid) {
+    load_shared_model(*c.M, sh, tid);
+    prologue_vectors(c, tid, T);
+    prologue_lists(c, tid, T);
+  });
+  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, tid, T); });
+
+  for (int d = TURN + 1; d <= n - 1; d++) {
+    if (d == wide_start_inside<W>(d)) {
+      const int rows = n - d;
+      int chunk = make_split(rows, T).Cp;
+#ifdef __CUDA_ARCH__
+      if (chunk > wide_chunk<W>(T)) chunk = wide_chunk<W>(T);
+#endif
+      for (int i0 = 1; i0 <= rows; i0 += chunk) {
+        const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          wide_inside_A_shfl<W, Exec::kBatch>(c, sh, d, i0, C, tid);
+#else
+          wide_inside_A<W>(c, sh, d, i0, C, tid);
+#endif
+        });
+        ex.phase(PH_BAND_B, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          wide_inside_B_shfl<W>(c, sh, d, i0, C, tid);
+#else
+          wide_inside_B<W>(c, sh, d, i0, C, tid);
+#endif
+        });
+      }
+    }
+    const int cells = n - d;
+    const int chunk = cells < T ? cells : T;
+    for (int i0 = 1; i0 <= cells; i0 += chunk) {
+      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
+      ex.phase(PH_INSIDE_A, [&](int tid) { inside_A(c, sh, d, i0, C, tid); });
+      ex.phase(PH_INSIDE_B, [&](int tid) { wide_inside_finish<W>(c, sh, d, i0, C, tid); });
+    }
+  }
+  inside_end(c);
+  if (logz) {
+    ex.phase(PH_LOGZ, [&](int tid) {
+      if (tid == 0) logz[(size_t)p.pair * 3 + p.which] = log(TB(c, T_Q, n - 1, 1)) + n * log(c.M->pf_scale);
+    });
+  }
+
+  for (int d = n - 1; d >= TURN + 1; d--) {
+    if (c.cp > 0) {
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, sh.red, 1, 32, d, tid, T); });
+      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
+    }
+    if (d == wide_start_outside<W>(n, d)) {
+      const int rows = n - d + W - 1;
+      int chunk = make_split(rows, T).Cp;
+#ifdef __CUDA_ARCH__
+      if (chunk > wide_chunk<W>(T)) chunk = wide_chunk<W>(T);
+#endif
+      for (int r0 = 0; r0 < rows; r0 += chunk) {
+        const int C = rows - r0 < chunk ? rows - r0 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          wide_outside_A_shfl<W, Exec::kBatch>(c, sh, d, r0, C, tid);
+#else
+          wide_outside_A<W>(c, sh, d, r0, C, tid);
+#endif
+        });
+        ex.phase(PH_BAND_B, [&](int tid) {
+#ifdef __CUDA_ARCH__
+          wide_outside_B_shfl<W>(c, sh, d, r0, C, tid);
+#else
+          wide_outside_B<W>(c, sh, d, r0, C, tid);
+#endif
+        });
+      }
+    }
+    const int cells = n - d;
+    const int chunk = cells < T ? cells : T;
+    for (int i0 = 1; i0 <= cells; i0 += chunk) {
+      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
+      ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
+      ex.phase(PH_OUTSIDE_B, [&](int tid) { wide_outside_finish<W>(c, sh, d, i0, C, tid); });
     }
   }
   emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M, &c.M->gfull[0][0]);

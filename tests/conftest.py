@@ -58,27 +58,36 @@ def emul(model):
     em.emul_problem.restype = C.c_int
     em.emul_band_problem.argtypes = em.emul_problem.argtypes
     em.emul_band_problem.restype = C.c_int
+    em.emul_wide_problem.argtypes = [C.c_int] + em.emul_problem.argtypes
+    em.emul_wide_problem.restype = C.c_int
     em.emul_lockstep.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     em.emul_lockstep.restype = C.c_int
 
     class Emul:
-        def linear(self, s, w, T=64, band=False):
+        @staticmethod
+        def _fn(band, wide):
+            """band: shared-memory band schedule; wide=W: general schedule with W-diagonal split-sum bands"""
+            if wide:
+                return lambda *a: em.emul_wide_problem(wide, *a)
+            return em.emul_band_problem if band else em.emul_problem
+
+        def linear(self, s, w, T=64, band=False, wide=0):
             n = len(s)
             bp = np.zeros((n + 1) * (n + 2) // 2, dtype=np.float32)
             up = np.zeros((n, w), dtype=np.float32)
             lz = C.c_double()
-            fn = em.emul_band_problem if band else em.emul_problem
+            fn = self._fn(band, wide)
             rc = fn(C.addressof(model), s.encode(), n, 0, 0, w, 0, 0, 0.0, T, bp.ctypes.data,
                                  up.ctypes.data, None, C.byref(lz))
             assert rc == 0
             return bp, up, lz.value
 
-        def cofold(self, s1, s2, th=0.1, T=64, band=False):
+        def cofold(self, s1, s2, th=0.1, T=64, band=False, wide=0):
             n1, n2 = len(s1), len(s2)
             hp = np.zeros((n1 + 1, n2 + 1), dtype=np.float32)
             lz = C.c_double()
-            fn = em.emul_band_problem if band else em.emul_problem
+            fn = self._fn(band, wide)
             rc = fn(C.addressof(model), (s1 + s2).encode(), n1 + n2, n1 + 1, 1, 0, n1, n2, th, T,
                                  None, None, hp.ctypes.data, C.byref(lz))
             assert rc == 0

@@ -11,7 +11,9 @@
 #include "seq_encode.h"
 
 namespace {
-struct SerialExec {
+template <int W>
+struct SerialExecT {
+  static constexpr int kWide = W;   // width of the wide split-sum bands (solve_mcc_wide)
   int T;
   int nthreads() const { return T; }
   template <class F>
@@ -19,6 +21,7 @@ struct SerialExec {
     for (int t = 0; t < T; t++) f(t);
   }
 };
+using SerialExec = SerialExecT<rp::BAND>;
 
 rp::DevModel g_model;  // large
 
@@ -29,7 +32,8 @@ void layout(int n, int max_w, int n1, int n2, size_t& nbp, size_t& nup, size_t& 
 }
 }  // namespace
 
-// one problem; band = 0: general kernel (solve_mcc), band = 1: shared-memory band kernel (solve_band)
+// one problem; band = 0: general kernel (solve_mcc), band = 1: shared-memory band kernel (solve_band),
+// band = 5..15: general kernel with wide split-sum bands of that width (solve_mcc_wide)
 static int run_problem(int band, const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
                        float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
   int rc = rp::build_dev_model(*m, &g_model);
@@ -47,14 +51,24 @@ static int run_problem(int band, const rp_model* m, const char* seq, int n, int 
   p.out_up = (kind == rp::KIND_LINEAR && up && max_w > 0) ? (long long)nbp : -1;
   p.out_hp = (kind == rp::KIND_COFOLD && hp) ? (long long)(nbp + nup) : -1;
   std::vector<double> ws(rp::slot_doubles(n), 1e300);  // poison: stale data must never be read
-  std::vector<double> smem(rp::shared_bytes(T) / sizeof(double) + 2, 0.0);
+  const int W = band >= rp::BAND ? band : rp::BAND;
+  std::vector<double> smem(rp::shared_bytes(T, W) / sizeof(double) + 2, 0.0);
   rp::Shared sh;
-  rp::carve_shared(sh, smem.data(), T);
+  rp::carve_shared(sh, smem.data(), T, W);
   double lz[3] = {0, 0, 0};
   rp::Ctx c;
   rp::bind_ctx(c, &g_model, S.data(), p, ws.data());
   SerialExec ex{T};
-  if (band) {
+  if (band == 5) {
+    SerialExecT<5> wx{T};
+    rp::solve_mcc_wide(wx, c, p, dense.data(), lz, sh);
+  } else if (band == 10) {
+    SerialExecT<10> wx{T};
+    rp::solve_mcc_wide(wx, c, p, dense.data(), lz, sh);
+  } else if (band == 15) {
+    SerialExecT<15> wx{T};
+    rp::solve_mcc_wide(wx, c, p, dense.data(), lz, sh);
+  } else if (band) {
     std::vector<double> bsm(rp::band_shared_doubles(n, T) + 2, 1e300);  // poison
     rp::solve_band(ex, c, p, dense.data(), lz, bsm.data());
   } else {
@@ -70,6 +84,11 @@ static int run_problem(int band, const rp_model* m, const char* seq, int n, int 
 extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
                             float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
   return run_problem(0, m, seq, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
+}
+extern "C" int emul_wide_problem(int W, const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1,
+                                 int n2, float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
+  if (W != 5 && W != 10 && W != 15) return -1;
+  return run_problem(W, m, seq, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
 }
 extern "C" int emul_band_problem(const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
                                  float th_hy, int T, float* bp, float* up, float* hp, double* logz) {

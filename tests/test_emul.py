@@ -107,3 +107,24 @@ def test_emulated_band_special_hairpins_and_bundled(emul, oracle, bundled):
     s1, s2 = bundled["sequences"]["DIS"], bundled["sequences"]["DIS"]
     hp, _ = emul.cofold(s1, s2, 0.1, 128, band=True)
     assert np.array_equal(hp, oracle.rnaduplex(s1, s2, 0.1))
+
+
+@pytest.mark.parametrize("W", [5, 10, 15])
+def test_emulated_wide_bands_match_oracle(emul, oracle, W):
+    """General schedule with W-diagonal split-sum bands (far pass + near terms at the finish, long problems)."""
+    rng = np.random.default_rng(7000 + W)
+    for n, T in [(1, 64), (5, 64), (9, 33), (16, 64), (23, 64), (41, 32), (58, 64), (72, 256)]:
+        s = rand_seq(rng, n)
+        bp, up, lz = emul.linear(s, 15, T, wide=W)
+        obp, oup = oracle.rnafold(s, 15)
+        _, _, olz = oracle.fold(s)
+        assert np.array_equal(bp, obp), n
+        assert np.abs(up - oup).max() <= 2e-7, n
+        assert abs(lz - olz) < 1e-10
+    for n1, n2, T in [(1, 1, 64), (3, 9, 64), (12, 9, 33), (35, 35, 64), (30, 52, 128)]:
+        s1, s2 = rand_seq(rng, n1), rand_seq(rng, n2)
+        hp, lz = emul.cofold(s1, s2, 0.0, T, wide=W)
+        ohp = oracle.rnaduplex(s1, s2, 0.0)
+        _, _, olz = oracle.fold(s1 + s2, n1 + 1)
+        assert np.abs(hp - ohp).max() <= 2e-7, (n1, n2)
+        assert abs(lz - olz) < 1e-10
