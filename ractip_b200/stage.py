@@ -218,16 +218,29 @@ class ProbabilityStage:
     def batch(self, pairs: Sequence[Tuple[str, str]], opts: Optional[RpOpts] = None) -> DeviceBatch:
         return DeviceBatch(self, pairs, opts if opts is not None else default_opts())
 
-    def run_dense(self, pairs: Sequence[Tuple[str, str]], opts: Optional[RpOpts] = None) -> List[PairProbabilities]:
-        """rp_run_dense: host buffers in, host buffers out."""
+    def run_dense(self, pairs: Sequence[Tuple[str, str]], opts: Optional[RpOpts] = None,
+                  pinned: bool = False) -> List[PairProbabilities]:
+        """rp_run_dense: host buffers in, host buffers out.  pinned=True hands the library a page-locked
+        buffer (rp_host_alloc), which the kernels write directly instead of a staged device-to-host copy."""
         opts = opts if opts is not None else default_opts()
         arr, keep = _make_pairs(pairs)
         n = len(pairs)
         layout = (RpDenseLayout * max(n, 1))()
         tot = C.c_size_t()
         self._check(self.lib.rp_dense_plan(arr, n, C.byref(opts), layout, C.byref(tot)))
-        flat = np.empty(max(tot.value, 1), dtype=np.float32)
-        self._check(self.lib.rp_run_dense(self.ctx, arr, n, C.byref(opts), flat.ctypes.data, flat.size))
+        if pinned:
+            nfl = max(tot.value, 1)
+            ptr = self.lib.rp_host_alloc(nfl * 4)
+            if not ptr:
+                raise MemoryError("rp_host_alloc failed")
+            try:
+                self._check(self.lib.rp_run_dense(self.ctx, arr, n, C.byref(opts), C.c_void_p(ptr), nfl))
+                flat = np.ctypeslib.as_array((C.c_float * nfl).from_address(ptr)).copy()
+            finally:
+                self.lib.rp_host_free(C.c_void_p(ptr))
+        else:
+            flat = np.empty(max(tot.value, 1), dtype=np.float32)
+            self._check(self.lib.rp_run_dense(self.ctx, arr, n, C.byref(opts), flat.ctypes.data, flat.size))
         w = max(opts.max_w, 0)
         out = []
         for k, (s1, s2) in enumerate(pairs):

@@ -282,3 +282,60 @@ def test_band_and_general_kernels_agree(model, bundled, monkeypatch):
         mism = (x.hp != 0) != (y.hp != 0)
         if mism.any():
             assert _near_threshold(np.where(x.hp != 0, x.hp, y.hp)[mism], opts.th_hy).all()
+
+
+@pytest.mark.parametrize("wide", [10, 15])
+def test_wide_split_sum_bands(model, oracle, monkeypatch, wide):
+    """Long-problem schedule of the general kernel (128-register build, split sums in bands of `wide`
+    diagonals: far pass + near terms at the finish), forced onto mid-size problems the oracle does quickly."""
+    from ractip_b200 import ProbabilityStage, default_opts
+    monkeypatch.setenv("RP_MCC_LONG_N", "216")
+    monkeypatch.setenv("RP_MCC_WIDE", str(wide))
+    rng = np.random.default_rng(4100 + wide)
+    opts = default_opts()
+    pairs = [(rand_seq(rng, 300), rand_seq(rng, 130)), (rand_seq(rng, 217), rand_seq(rng, 260))]
+    st = ProbabilityStage(model)
+    try:
+        for (s1, s2), r in zip(pairs, st.run_dense(pairs, opts)):
+            _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"wide={wide} {len(s1)}x{len(s2)}")
+    finally:
+        st.close()
+
+
+def test_long_pair_default_routing(stage, oracle):
+    """620 x 300 nt: the two-strand problem (920 nt) takes the wide-band build by default, the single
+    strands the 64-register build."""
+    from ractip_b200 import default_opts
+    rng = np.random.default_rng(920)
+    s1, s2 = rand_seq(rng, 620), rand_seq(rng, 300)
+    opts = default_opts()
+    r = stage.run_dense([(s1, s2)], opts)[0]
+    _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, "620x300")
+
+
+def test_pinned_host_buffer_is_written_in_place(stage, bundled, monkeypatch):
+    """rp_run_dense into a page-locked buffer written by the kernels directly (RP_ZERO_COPY=1, opt-in)
+    and into pageable memory (staged copy) give the same bytes."""
+    from ractip_b200 import default_opts
+    monkeypatch.setenv("RP_ZERO_COPY", "1")
+    seqs = bundled["sequences"]
+    pairs = [(seqs["DIS"], seqs["DIS"]), (seqs["MicA"], seqs["ompA"]), (seqs["CopA"], seqs["CopT"])]
+    for duplex in (0, 1):
+        opts = default_opts()
+        opts.use_pf_duplex = duplex
+        a = stage.run_dense(pairs, opts)
+        b = stage.run_dense(pairs, opts, pinned=True)
+        for x, y in zip(a, b):
+            for name in ("bp1", "bp2", "up1", "up2", "hp"):
+                assert np.array_equal(getattr(x, name), getattr(y, name)), (duplex, name)
+
+
+def test_configs4_size_pair_matches_oracle(stage, oracle):
+    """One pair of BASELINE configs[4]'s size (1000 x 500 nt, two-strand problem of 1500 nt) against the oracle."""
+    from ractip_b200 import default_opts
+    rng = np.random.default_rng(20261018)
+    s1 = "".join("ACGU"[x] for x in rng.integers(0, 4, 1000))
+    s2 = "".join("ACGU"[x] for x in rng.integers(0, 4, 500))
+    opts = default_opts()
+    r = stage.run_dense([(s1, s2)], opts, pinned=True)[0]
+    _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, "1000x500")
