@@ -331,7 +331,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             except Exception:
                 traffic = None
         roofline = {
-            "bound": "fp64_fma", "kernel": "mcc_band_kernel (launch shapes <512,1> and <256,2>, timed together)", "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
+            "bound": "fp64_fma", "kernel": KERNELS[args.workload][0], "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
             "frac": achieved / fp64_tf if fp64_tf else None, "traffic": traffic,
             "alg_flops_per_launch": alg, "launch_ms": launch_ms,
             "peak_source": "live fp64-FMA micro-benchmark on this GPU (rp_measure_peaks); "
@@ -365,7 +365,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "config": {"workload": desc, "pairs_per_step": total_pairs, "sharding": f"shuffles r::{world}" if world > 1 else "none",
                        "collective": "one all_gather of sparse records" if world > 1 else "none",
                        "l2": "per-step working set (workspace slots of all resident CTAs, > 1 GB) exceeds the 126 MB L2; no flush needed",
-                       "kernels": "mcc_band_kernel<512,1> (n > ~95) + mcc_band_kernel<256,2> (shorter); general kernel for n > 215"},
+                       "kernels": KERNELS[args.workload][1]},
             "clocks": clocks,
             "e2e": {"value": e2e_d, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": out_bytes * world, "api": "rp_run_dense (reference layouts, pinned host buffer)"},
@@ -387,6 +387,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# dominant kernel (roofline) and routing of each workload (rp_kernel_plan / rp_batch_create)
+KERNELS = {
+    "mica_ompa": ("mcc_band_kernel (launch shapes <512,1> and <256,2>, timed together)",
+                  "mcc_band_kernel<512,1> (n > ~95) + mcc_band_kernel<256,2> (shorter); general kernel for n > 215"),
+    "synthetic": ("mcc_persistent<1,10> (general kernel, HBM tables, 128 registers, split sums in bands of 10 diagonals)",
+                  "mcc_persistent<1,10>: one CTA per problem and per SM, 1500 / 1000 / 500-nt problems from one cost-ordered queue"),
+}
 
 
 def main():

@@ -1174,18 +1174,35 @@ RP_HD void wide_inside_B(Ctx& c, const Shared& sh, int d0, int i0, int C, int ti
     TB(c, T_QS, d0 + e, i) = q;
   }
 }
-// the terms of cell (i, i+d) the far pass of its band could not see
+// the terms of cell (i, i+d) the far pass of its band could not see: a < e (second operand on a
+// diagonal of the band) and a >= max(d0, e) (first operand on one).  All operands are loaded before
+// the first product is formed: the loop is short (<= 2(W-BAND)+BAND terms) but every load is an L2 or
+// HBM round trip, and this runs in the one-thread-per-cell finishing phase.
 template <int W>
 RP_HD void inside_near(const Ctx& c, int d, int i, double& sM, double& sQ) {
   const int d0 = wide_start_inside<W>(d), e = d - d0, hi = d - TURN - 2;
   const int askip = c.cp > 0 ? c.cp - 1 - i : -1;
-  for (int a = 0; a < e && a <= hi; a++) {             // second operand on a diagonal of the band
-    sQ += TB(c, T_Q, a, i) * TB(c, T_QQ, d - 1 - a, i + 1 + a);
-    if (a > TURN && a != askip) sM += TB(c, T_QM, a, i) * TB(c, T_QM1, d - 1 - a, i + 1 + a);
-  }
-  for (int a = (d0 > e ? d0 : e); a <= hi; a++) {      // first operand on a diagonal of the band
-    sQ += TB(c, T_Q, a, i) * TB(c, T_QQ, d - 1 - a, i + 1 + a);
-    if (a != askip) sM += TB(c, T_QM, a, i) * TB(c, T_QM1, d - 1 - a, i + 1 + a);
+  int n1 = (e - 1 < hi ? e - 1 : hi) + 1;                  // terms a = 0 .. n1-1
+  if (n1 < 0) n1 = 0;
+  const int a2 = d0 > e ? d0 : e;                          // terms a = a2 .. hi
+  const int total = n1 + (hi >= a2 ? hi - a2 + 1 : 0);
+  constexpr int CH = 5;   // operands of CH terms per round trip (4*CH doubles in registers)
+#pragma unroll 1
+  for (int x0 = 0; x0 < total; x0 += CH) {
+    double aq[CH], bq[CH], am[CH], bm[CH];
+#pragma unroll
+    for (int u = 0; u < CH; u++) {
+      const int x = x0 + u;
+      const bool on = x < total;
+      const int a = x < n1 ? x : a2 + (x - n1);
+      const bool onm = on && a > TURN && a != askip;
+      aq[u] = on ? TB(c, T_Q, a, i) : 0.;
+      bq[u] = on ? TB(c, T_QQ, d - 1 - a, i + 1 + a) : 0.;
+      am[u] = onm ? TB(c, T_QM, a, i) : 0.;
+      bm[u] = onm ? TB(c, T_QM1, d - 1 - a, i + 1 + a) : 0.;
+    }
+#pragma unroll
+    for (int u = 0; u < CH; u++) { sQ += aq[u] * bq[u]; sM += am[u] * bm[u]; }
   }
 }
 

@@ -232,8 +232,11 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
 
   for (int d = n - 1; d >= TURN + 1; d--) {
     if (c.cp > 0) {
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, sh.red, 1, 32, d, tid, T); });
-      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
+      // long strands: each of the four nick sums over T/4 threads (partials in the partial-sum buffer, idle here)
+      const int np = T >= 128 ? T / 4 : 32;
+      double* red = T >= 128 ? sh.part : sh.red;
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, red, 1, np, d, tid, T); });
+      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, red, 1, np, d, tid, T); });
     }
     if (d == wide_start_outside<W>(n, d)) {
       const int rows = n - d + W - 1;

@@ -3,6 +3,9 @@
 
     python tools/ncu_lines.py gpurun_out/prof.ncu-rep [kernel_substring] [top]
 
+kernel_substring selects the SASS section by its MANGLED name: give enough of it to single out one template
+instance (mcc_band_kernelILi512ELi1, mcc_persistentILi1ELi10), or the line map of another instance is used.
+
 Uses `ncu --page source --csv` for the per-SASS-instruction counters and
 `nvdisasm -g` on the cubin extracted from the built library for the SASS->line map.
 """
@@ -81,7 +84,7 @@ for ln, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
 # --- per-function totals (line ranges from the source)
 import bisect
 funcs = []
-for fname in ("mcc_core.h", "mcc_band.h", "mcc_band_shfl.cuh", "mcc_driver.h", "kernels.cu"):
+for fname in ("mcc_core.h", "mcc_band.h", "mcc_band_shfl.cuh", "mcc_wide_shfl.cuh", "mcc_driver.h", "kernels.cu"):
     f = ROOT / "ractip_b200" / "csrc" / fname
     for no, l in enumerate(f.read_text().split("\n"), start=1):
         m = re.match(r"(?:template.*\n)?(?:RP_HD|__global__|__device__|inline).*?\b(\w+)\(", l)
