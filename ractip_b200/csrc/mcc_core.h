@@ -119,6 +119,7 @@ struct LCtx {
   size_t te, ve;
   double invZ;
   int dbg;
+  long long* prof;
   RP_HD double& tb(int t, int d, int i) const { return ws[((size_t)t * te + (size_t)d * ld + i) * G]; }
   RP_HD double* ptr(int t, int d, int i) const { return ws + ((size_t)t * te + (size_t)d * ld + i) * G; }
   RP_HD double& v(int vv, int k) const { return ws[((size_t)T_COUNT * te + (size_t)vv * ve + k) * G]; }
@@ -140,6 +141,7 @@ RP_HD void bind_lctx(LCtx<G>& c, const DevModel* M, const uint8_t* S_group, cons
   c.ws = ws_group + g; c.te = table_elems(p.n); c.ve = vector_elems(p.n);
   c.invZ = 0;
   c.dbg = 0;
+  c.prof = nullptr;
 }
 
 #define TB(c, t, d, i) ((c).tb(t, d, i))
@@ -1323,9 +1325,9 @@ RP_HD void wide_outside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, i
 template <class C>
 RP_HD void unstru_hairpin(C& c, int tid, int T) {
   const int n = c.n;
-  const size_t total = (size_t)n * c.ld;
-  for (size_t x = tid; x < total; x += T) {
-    const int d = (int)(x / c.ld), i = (int)(x % c.ld);
+  const unsigned total = (unsigned)n * (unsigned)c.ld, ld = (unsigned)c.ld;   // n <= RP_MAX_N: 32-bit index arithmetic
+  for (unsigned x = tid; x < total; x += T) {
+    const int d = (int)(x / ld), i = (int)(x - (unsigned)d * ld);
     if (i < 1 || i + d > n) continue;
     double v = 0.;
     if (d > TURN) {
@@ -1369,13 +1371,25 @@ RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
         for (int u2 = 0; u2 <= 3; u2++) {
           if (loop_class(u1, u2) != CLS_SPECIAL) continue;
           const int lmax = n - 1 - u2, sidx = special_index(u1, u2);
-#pragma unroll 4
-          for (int l = lmin + sl; l <= lmax; l += nsl) {
-            const int o = l + 1 + u2;
-            const double qb = TB(c, T_QB, l - k, k), ou = TB(c, T_OUT, o - p, p);
-            const double w = special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
-                                          si1, base(c, o - 1), sp1, base(c, l + 1));
-            acc += ou * qb * w;
+          // four positions per round trip: the eight table loads go out before the first weight is looked up
+          for (int l0 = lmin + sl; l0 <= lmax; l0 += 4 * nsl) {
+            double qb[4], ou[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int l = l0 + u * nsl;
+              const bool on = l <= lmax;
+              qb[u] = on ? TB(c, T_QB, l - k, k) : 0.;
+              ou[u] = on ? TB(c, T_OUT, l + 1 + u2 - p, p) : 0.;
+            }
+            double w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {   // branch-free: the four weight look-ups (L2) are in flight together
+              const int l = l0 + u * nsl <= lmax ? l0 + u * nsl : lmax, o = l + 1 + u2;
+              w[u] = special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
+                                  si1, base(c, o - 1), sp1, base(c, l + 1));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc += ou[u] * qb[u] * w[u];
           }
         }
       } else {
@@ -1384,13 +1398,24 @@ RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
         for (int u1 = 0; u1 <= 3; u1++) {
           if (loop_class(u1, u2) != CLS_SPECIAL) continue;
           const int pmax = l - TURN - 2 - u1, sidx = special_index(u1, u2);
-#pragma unroll 4
-          for (int p = 1 + sl; p <= pmax; p += nsl) {
-            const int k = p + 1 + u1;
-            const double ou = TB(c, T_OUT, o - p, p), qb = TB(c, T_QB, l - k, k);
-            const double w = special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
-                                          base(c, p + 1), sj1, base(c, k - 1), sq1);
-            acc += ou * qb * w;
+          for (int p0 = 1 + sl; p0 <= pmax; p0 += 4 * nsl) {
+            double qb[4], ou[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int p = p0 + u * nsl;
+              const bool on = p <= pmax;
+              ou[u] = on ? TB(c, T_OUT, o - p, p) : 0.;
+              qb[u] = on ? TB(c, T_QB, l - (p + 1 + u1), p + 1 + u1) : 0.;
+            }
+            double w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int p = p0 + u * nsl <= pmax ? p0 + u * nsl : pmax, k = p + 1 + u1;
+              w[u] = special_loop(M, sidx, pair_type(base(c, p), base(c, o)), rtype(pair_type(base(c, k), base(c, l))),
+                                  base(c, p + 1), sj1, base(c, k - 1), sq1);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc += ou[u] * qb[u] * w[u];
           }
         }
       }
@@ -1603,9 +1628,9 @@ RP_HD void write_bp(const C& c, float* bp, int tid, int T) {
 template <class C>
 RP_HD void write_bp2(const C& c, float* bp, int tid, int T) {
   const int L = c.n;
-  const size_t total = (size_t)L * c.ld;
-  for (size_t x = tid; x < total; x += T) {
-    const int d = (int)(x / c.ld), i = (int)(x % c.ld);
+  const unsigned total = (unsigned)L * (unsigned)c.ld, ld = (unsigned)c.ld;
+  for (unsigned x = tid; x < total; x += T) {
+    const int d = (int)(x / ld), i = (int)(x - (unsigned)d * ld);
     if (i < 1 || i + d > L || d < 1) continue;
     const double p = d > TURN ? TB(c, T_OUT, d, i) * TB(c, T_QB, d, i) : 0.;
     RP_ST_STREAM(bp[(size_t)i * (2 * L + 1 - i) / 2 + (i + d)], (float)p);

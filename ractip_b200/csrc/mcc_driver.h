@@ -41,8 +41,23 @@ RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* d
     });
     if (probs[0].max_w > 0) {
       ex.phase(PH_UN_HAIRPIN, [&](int tid) {
+#ifdef __CUDA_ARCH__
+        long long* prof = get(tid % G).prof;
+        const long long t0 = (prof && tid == 0) ? clock64() : 0;
+#endif
         unstru_hairpin(get(tid % G), tid / G, nct);
+#ifdef __CUDA_ARCH__
+        const long long t1 = (prof && tid == 0) ? clock64() : 0;
+#endif
         unstru_gap_specials(get(tid % G), SM, tid / G, nct);
+#ifdef __CUDA_ARCH__
+        if (prof && tid == 0) {   // RP_PROFILE probes of thread 0: the two halves of the phase
+          atomicAdd(reinterpret_cast<unsigned long long*>(prof + 22), (unsigned long long)(t1 - t0));
+          atomicAdd(reinterpret_cast<unsigned long long*>(prof + 32 + 22), 1ull);
+          atomicAdd(reinterpret_cast<unsigned long long*>(prof + 23), (unsigned long long)(clock64() - t1));
+          atomicAdd(reinterpret_cast<unsigned long long*>(prof + 32 + 23), 1ull);
+        }
+#endif
       });
       ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(get(tid % G), gfull, 0, tid / G, nct); });
       ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(get(tid % G), gfull, 1, tid / G, nct); });

@@ -20,6 +20,11 @@
 
 namespace rp {
 
+// The far passes stream tens of MB per call that will not be touched again before the next pass of the
+// same problem, by which time 147 other problems have streamed theirs: evict-first loads keep them from
+// pushing the recent diagonals (the interior-loop operands, re-read for 32 diagonals) out of the L2.
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+
 template <int W>
 struct WideSplit {
   static constexpr int HWW = 32 - (W - 1);   // rows a warp owns
@@ -78,8 +83,8 @@ __device__ __forceinline__ void wide_inside_A_shfl(const Ctx& c, const Shared& s
         for (int u = 0; u < NB; u++) {
           const int au = a + u;
           const bool on = au <= a_hi;
-          A[u] = (on && own && (sum || au != askip)) ? TB(c, tA, au, i) : 0.;
-          b0[u] = (on && rowok) ? TB(c, tB, d0 - 1 - au, i + 1 + au) : 0.;
+          A[u] = (on && own && (sum || au != askip)) ? ld_stream(c.ptr(tA, au, i)) : 0.;
+          b0[u] = (on && rowok) ? ld_stream(c.ptr(tB, d0 - 1 - au, i + 1 + au)) : 0.;
         }
 #pragma unroll
         for (int u = 0; u < NB; u++) {
@@ -158,8 +163,8 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
         for (int u = 0; u < NB; u++) {
           const int tu = t + u;
           const bool on = tu <= t_hi && tu <= tmax;
-          A[u] = (on && own) ? TB(c, T_MC, d0 + TURN + 3 + tu, k) : 0.;
-          bn[u] = (on && k + d0 + 2 - W >= 1) ? *(c.ptr(T_QM, TURN + 1 + tu, k + d0 + 1) + (W - 1) * es) : 0.;
+          A[u] = (on && own) ? ld_stream(c.ptr(T_MC, d0 + TURN + 3 + tu, k)) : 0.;
+          bn[u] = (on && k + d0 + 2 - W >= 1) ? ld_stream(c.ptr(T_QM, TURN + 1 + tu, k + d0 + 1) + (W - 1) * es) : 0.;
         }
 #pragma unroll
         for (int u = 0; u < NB; u++) {
@@ -211,8 +216,8 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
         for (int u = 0; u < NB; u++) {
           const int iu = i + u * S;
           const int row0 = k0 - 2 - iu;   // diagonal of this lane's e = 0 element
-          A[u] = (need != 0 && iu <= ifar) ? TB(c, T_PRML, l - iu, iu) : 0.;
-          b0[u] = (iu <= ifar_hi && row0 >= 0 && k0 - 1 <= n) ? *(c.ptr(T_QM, 0, iu + 1) + (long)row0 * ds) : 0.;   // qm(iu+1, k0-1)
+          A[u] = (need != 0 && iu <= ifar) ? ld_stream(c.ptr(T_PRML, l - iu, iu)) : 0.;
+          b0[u] = (iu <= ifar_hi && row0 >= 0 && k0 - 1 <= n) ? ld_stream(c.ptr(T_QM, 0, iu + 1) + (long)row0 * ds) : 0.;   // qm(iu+1, k0-1)
         }
 #pragma unroll
         for (int u = 0; u < NB; u++) {
