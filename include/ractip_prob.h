@@ -257,7 +257,11 @@ double rp_alg_flops_mcc(int n);
 enum {
   RP_KERNEL_BAND_1CTA = 0,  /* shared-memory band kernel, 512 threads, 1 CTA/SM */
   RP_KERNEL_BAND_2CTA = 1,  /* shared-memory band kernel, 256 threads, 2 CTA/SM */
-  RP_KERNEL_GENERAL = 2     /* HBM-table wavefront kernel (any length)          */
+  RP_KERNEL_GENERAL = 2,    /* HBM-table wavefront kernel (any length), 2 CTA/SM */
+  RP_KERNEL_GENERAL_WIDE = 3 /* the same with 128 registers, 1 CTA/SM and split  */
+                            /* sums in bands of 10 diagonals: n >= 900.  A batch */
+                            /* runs ALL its general-kernel problems in this build */
+                            /* when its longest one qualifies.                    */
 };
 int rp_kernel_plan(int n, size_t smem_limit, size_t* smem_bytes);
 

@@ -210,7 +210,8 @@ int rp_kernel_plan(int n, size_t smem_limit, size_t* smem_bytes) {
   const size_t s256 = rp::band_shared_bytes(n, 256), s512 = rp::band_shared_bytes(n, 512);
   if (s256 <= half_sm) { if (smem_bytes) *smem_bytes = s256; return RP_KERNEL_BAND_2CTA; }
   if (smem_bytes) *smem_bytes = s512;
-  return s512 <= smem_limit ? RP_KERNEL_BAND_1CTA : RP_KERNEL_GENERAL;
+  if (s512 <= smem_limit) return RP_KERNEL_BAND_1CTA;
+  return n >= 900 ? RP_KERNEL_GENERAL_WIDE : RP_KERNEL_GENERAL;   // rp_ctx::mcc_long_n default
 }
 
 const char* rp_strerror(int code) {
