@@ -503,7 +503,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   // length for the two wavefronts (fixed cost per diagonal) + ~160 n^2 for the unpaired-window pass.
   auto cost = [&](const Problem& q) {
     if (q.kind == rp::KIND_DUPLEX) return 0.0;
-    if (ctx->band && rp_kernel_plan(q.n, ctx->smem_optin, nullptr) != RP_KERNEL_GENERAL)
+    if (ctx->band && rp_kernel_plan(q.n, ctx->smem_optin, nullptr) < RP_KERNEL_GENERAL)
       return 3.0e4 * q.n + ((q.kind == rp::KIND_LINEAR && q.max_w > 0) ? 160.0 * q.n * q.n : 0.0);
     return (double)q.n * q.n * (q.n + 1500.0);
   };
@@ -557,7 +557,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     auto cls = [&](const Problem& q) {
       if (q.kind == rp::KIND_DUPLEX) return -1;
       const int k = rp_kernel_plan(q.n, ctx->smem_optin, nullptr);
-      return k == RP_KERNEL_GENERAL ? -1 : k;
+      return k >= RP_KERNEL_GENERAL ? -1 : k;   // RP_KERNEL_GENERAL / RP_KERNEL_GENERAL_WIDE: the general queue
     };
     std::vector<int> part[3];
     for (int k : b->order) {

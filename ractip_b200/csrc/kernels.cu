@@ -416,28 +416,26 @@ cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, int w
   return cudaGetLastError();
 }
 
+namespace {
+// launch shapes of the band kernel: 256 threads x 2 CTAs/SM (short problems), 512 threads x 1 CTA/SM.
+// (Wider CTAs were measured: <640,1> at 96 registers and <768,1> at 80 compile with 32 / 256 bytes of
+// spills and run the 100..137-nt class 6 % / 14 % SLOWER -- the phases have no parallelism left for the
+// extra warps.)
+MccKernel band_kernel(int threads) { return threads == 256 ? mcc_band_kernel<256, 2> : mcc_band_kernel<512, 1>; }
+}  // namespace
+
 int band_max_ctas_per_sm(int threads, size_t smem) {
   int n = 0;
-  cudaError_t e;
-  if (threads == 512) {
-    if (cudaFuncSetAttribute(mcc_band_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mcc_band_kernel<512, 1>, 512, smem);
-  } else {
-    if (cudaFuncSetAttribute(mcc_band_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mcc_band_kernel<256, 2>, 256, smem);
-  }
-  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  MccKernel k = band_kernel(threads);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 
 cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, cudaStream_t st) {
-  if (threads == 512) {
-    cudaFuncSetAttribute(mcc_band_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mcc_band_kernel<512, 1><<<grid, 512, smem, st>>>(b);
-  } else {
-    cudaFuncSetAttribute(mcc_band_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mcc_band_kernel<256, 2><<<grid, 256, smem, st>>>(b);
-  }
+  MccKernel k = band_kernel(threads);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<grid, threads, smem, st>>>(b);
   return cudaGetLastError();
 }
 
