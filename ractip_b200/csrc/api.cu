@@ -50,6 +50,8 @@ struct rp_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t side_stream = nullptr;   // the second band launch shape runs here, so that its CTAs fill the SMs the first one leaves
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t copy_stream = nullptr;   // rp_batch_fetch_dense: outputs of the long band class leave while the short class still runs
+  cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   double* ws = nullptr;       // workspace slots (grow-only)
@@ -95,6 +97,12 @@ struct rp_batch {
   int* d_gcounter = nullptr;
   int* d_counter = nullptr;
   float* d_dense = nullptr;
+  // Split fetch (uniform batches whose problems fall into both band classes, nothing else launched): sections of a
+  // pair's dense block written by the long class / by the short class, as (offset, length) in floats within pair 0's
+  // block; every pair has the same block layout, `pair_stride` floats apart.
+  bool split_fetch = false;
+  size_t pair_stride = 0;
+  std::vector<std::pair<size_t, size_t>> sect_long, sect_short;
   float* dense_out = nullptr;   // set by rp_run_dense: the caller's pinned host buffer, written by the kernels directly
   double* d_logz = nullptr;
   // sparse
@@ -354,6 +362,9 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
     return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMalloc(&ctx->d_model, sizeof(rp::DevModel))) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
@@ -390,6 +401,9 @@ int rp_destroy(rp_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -579,6 +593,31 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   b->n_mcc = gen_mcc;
   b->slot_doubles = std::max(gen_mcc ? rp::slot_doubles(gen_maxn) : (size_t)0, ws_need);
   b->mcc_minb = (gen_maxn >= ctx->mcc_long_n && ctx->ctas_per_sm1 > 0) ? 1 : 2;
+  // Split fetch plan.  The short band class runs last (side stream, on the SMs the long class leaves), so
+  // everything the long class wrote can cross PCIe meanwhile.  Needs a uniform batch (the z-score shuffle batch:
+  // every pair has the lengths of the original pair) so that the sections are strided 2-D copies.
+  b->split_fetch = false;
+  if (ctx->band && n_pairs >= 2 && b->n_band[0] > 0 && b->n_band[1] > 0 && b->n_general == 0 && b->groups.empty() &&
+      !std::getenv("RP_NO_SPLIT_FETCH")) {
+    bool uniform = true;
+    for (int p = 1; p < n_pairs && uniform; p++) uniform = pairs[p].n1 == pairs[0].n1 && pairs[p].n2 == pairs[0].n2;
+    if (uniform) {
+      const rp_dense_layout& L = b->layout[0];
+      b->pair_stride = b->layout[1].bp1 - L.bp1;
+      auto is_short = [&](int n) { return rp_kernel_plan(n, ctx->smem_optin, nullptr) == RP_KERNEL_BAND_2CTA; };
+      const bool s1 = is_short(pairs[0].n1), s2 = is_short(pairs[0].n2), s12 = is_short(pairs[0].n1 + pairs[0].n2);
+      struct Sec { size_t off, len; bool sh; };
+      const Sec secs[5] = {{L.bp1, L.n_bp1, s1}, {L.bp2, L.n_bp2, s2}, {L.up1, L.n_up1, s1}, {L.up2, L.n_up2, s2}, {L.hp, L.n_hp, s12}};
+      b->sect_long.clear(); b->sect_short.clear();
+      for (const Sec& x : secs) {   // sections are in layout order: merge neighbours of the same class
+        if (!x.len) continue;
+        auto& v = x.sh ? b->sect_short : b->sect_long;
+        if (!v.empty() && v.back().first + v.back().second == x.off) v.back().second += x.len;
+        else v.push_back({x.off - L.bp1, x.len});
+      }
+      b->split_fetch = !b->sect_long.empty() && !b->sect_short.empty();
+    }
+  }
 
   auto bail = [&](cudaError_t e, const char* what) {
     rp_batch_destroy(b);
@@ -699,6 +738,7 @@ int rp_batch_run(rp_batch* b) {
           ls = ctx->side_stream;
         }
         CU(rp::launch_band(db, b->band_grid[k], band_threads[k], band_smem[k], ls));
+        if (k == 0 && b->split_fetch) CU(cudaEventRecord(ctx->ev_main, st));   // the long class's outputs are final here
         if (ls != st) {                 // join before anything else of the batch runs
           CU(cudaEventRecord(ctx->ev_join, ls));
           CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -751,8 +791,22 @@ int rp_batch_fetch_dense(rp_batch* b, float* out, size_t out_floats) {
   if (out_floats < b->total_floats) return fail(ctx, RP_ERR_CAPACITY, "rp_batch_fetch_dense: buffer too small");
   CU(cudaSetDevice(ctx->device));
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  if (b->total_floats)
+  if (b->total_floats && b->split_fetch) {
+    // long-class sections: on the copy stream, as soon as the long class is done (ev_main), while the short class
+    // still computes; short-class sections: on the main stream, which has joined the side stream
+    const size_t pitch = b->pair_stride * sizeof(float);
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_main, 0));
+    for (const auto& sc : b->sect_long)
+      CU(cudaMemcpy2DAsync(out + sc.first, pitch, b->d_dense + sc.first, pitch, sc.second * sizeof(float), (size_t)b->n_pairs,
+                           cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    for (const auto& sc : b->sect_short)
+      CU(cudaMemcpy2DAsync(out + sc.first, pitch, b->d_dense + sc.first, pitch, sc.second * sizeof(float), (size_t)b->n_pairs,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+  } else if (b->total_floats) {
     CU(cudaMemcpyAsync(out, b->d_dense, b->total_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->timed_copies = true;

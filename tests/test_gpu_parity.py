@@ -339,3 +339,23 @@ def test_configs4_size_pair_matches_oracle(stage, oracle):
     opts = default_opts()
     r = stage.run_dense([(s1, s2)], opts, pinned=True)[0]
     _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, "1000x500")
+
+
+def test_split_fetch_of_uniform_batches(stage, bundled, monkeypatch):
+    """Shuffle batches (every pair the same lengths) whose problems fall into both band classes are fetched in
+    two parts -- the long class's sections while the short class still runs -- and give the same bytes as the
+    single copy (RP_NO_SPLIT_FETCH=1)."""
+    from ractip_b200 import default_opts, zscore_shuffles
+    s1, s2 = bundled["sequences"]["MicA"], bundled["sequences"]["ompA"]
+    r1, r2 = zscore_shuffles(s1, s2, 12, 3)
+    pairs = list(zip(r1, r2))
+    opts = default_opts()
+    a = stage.run_dense(pairs, opts)
+    b = stage.run_dense(pairs, opts, pinned=True)
+    monkeypatch.setenv("RP_NO_SPLIT_FETCH", "1")
+    c = stage.run_dense(pairs, opts)
+    for x, y, z in zip(a, b, c):
+        for name in ("bp1", "bp2", "up1", "up2", "hp"):
+            assert np.array_equal(getattr(x, name), getattr(z, name)), name
+            assert np.array_equal(getattr(y, name), getattr(z, name)), name
+        assert x.bp2.max() > 0 and x.bp1.max() > 0 and x.up1.max() > 0
