@@ -33,7 +33,7 @@ void layout(int n, int max_w, int n1, int n2, size_t& nbp, size_t& nup, size_t& 
 }  // namespace
 
 // one problem; band = 0: general kernel (solve_mcc), band = 1: shared-memory band kernel (solve_band),
-// band = 5..15: general kernel with wide split-sum bands of that width (solve_mcc_wide)
+// band = 5, 8, 10, 15: general kernel with wide split-sum bands of that width (solve_mcc_wide)
 static int run_problem(int band, const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,
                        float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
   int rc = rp::build_dev_model(*m, &g_model);
@@ -62,6 +62,9 @@ static int run_problem(int band, const rp_model* m, const char* seq, int n, int 
   if (band == 5) {
     SerialExecT<5> wx{T};
     rp::solve_mcc_wide(wx, c, p, dense.data(), lz, sh);
+  } else if (band == 8) {
+    SerialExecT<8> wx{T};
+    rp::solve_mcc_wide(wx, c, p, dense.data(), lz, sh);
   } else if (band == 10) {
     SerialExecT<10> wx{T};
     rp::solve_mcc_wide(wx, c, p, dense.data(), lz, sh);
@@ -87,7 +90,7 @@ extern "C" int emul_problem(const rp_model* m, const char* seq, int n, int cp, i
 }
 extern "C" int emul_wide_problem(int W, const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1,
                                  int n2, float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
-  if (W != 5 && W != 10 && W != 15) return -1;
+  if (W != 5 && W != 8 && W != 10 && W != 15) return -1;
   return run_problem(W, m, seq, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
 }
 extern "C" int emul_band_problem(const rp_model* m, const char* seq, int n, int cp, int kind, int max_w, int n1, int n2,

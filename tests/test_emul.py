@@ -109,7 +109,7 @@ def test_emulated_band_special_hairpins_and_bundled(emul, oracle, bundled):
     assert np.array_equal(hp, oracle.rnaduplex(s1, s2, 0.1))
 
 
-@pytest.mark.parametrize("W", [5, 10, 15])
+@pytest.mark.parametrize("W", [5, 8, 10, 15])
 def test_emulated_wide_bands_match_oracle(emul, oracle, W):
     """General schedule with W-diagonal split-sum bands (far pass + near terms at the finish, long problems)."""
     rng = np.random.default_rng(7000 + W)
