@@ -196,9 +196,10 @@ int grid_for(const rp_ctx* ctx, int nprob, size_t slot_bytes, int minb) {
     int v = std::atoi(e);
     if (v >= 1 && v < g) g = v;
   }
-  // keep the workspace within a budget (long sequences: fewer, fatter slots)
+  // keep the workspace within a budget (long sequences: fewer, fatter slots).  cudaMemGetInfo costs
+  // milliseconds: not asked when the workspace the context already holds is large enough.
   size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+  if ((size_t)g * slot_bytes > ctx->ws_bytes && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
     size_t budget = (free_b + ctx->ws_bytes) / 10 * 7;
     while (g > 1 && (size_t)g * slot_bytes > budget) g--;
   }

@@ -74,8 +74,16 @@ constexpr int GPACK = (MAXLOOP + 1) * (MAXLOOP + 2) / 2;   // 496
 
 RP_HD int band_ldb(int n) { return ((n + 1 + 7) / 8) * 8; }
 RP_HD int band_ngp(int n) { return (n + 7) / 8 + 3; }
+// partial sums of the split-sum band phases / of the interior items (they alias).  The CUDA build runs the
+// shuffle form of the band phases (mcc_band_shfl.cuh), where a warp owns 32-(BAND-1) rows: 2*BAND partials for
+// 28 rows per warp.  The host emulation runs the direct form: 2*BAND partials per thread.
 RP_HD size_t band_part_doubles(int n, int T) {
-  const size_t a = (size_t)2 * BAND * T, b = (size_t)(NSLICE + 1) * BR * band_ngp(n);
+#ifdef __CUDACC__
+  const size_t a = (size_t)2 * BAND * (32 - (BAND - 1)) * (T / 32);
+#else
+  const size_t a = (size_t)2 * BAND * T;
+#endif
+  const size_t b = (size_t)(NSLICE + 1) * BR * band_ngp(n);
   return a > b ? a : b;
 }
 RP_HD size_t band_shared_doubles(int n, int T) {

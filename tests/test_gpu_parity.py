@@ -245,7 +245,7 @@ def test_error_paths(stage, lib):
         stage.run_dense([("", "ACGU")], opts)
 
 
-@pytest.mark.parametrize("n1,n2", [(95, 1), (96, 3), (60, 40), (150, 65), (107, 108), (108, 108), (215, 1)])
+@pytest.mark.parametrize("n1,n2", [(95, 1), (96, 3), (60, 40), (150, 65), (107, 108), (108, 108), (215, 1), (111, 112), (112, 112), (223, 1), (224, 2)])
 def test_kernel_class_boundaries(stage, oracle, lib, n1, n2):
     """Lengths around the routing boundaries of rp_kernel_plan (two band CTAs per SM / one / general
     kernel): every route gives the oracle's numbers."""
