@@ -755,7 +755,18 @@ int rp_batch_run(rp_batch* b) {
     launches++;
   }
   if (b->n_mcc > 0) {
-    CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, ctx->mcc_wide, st));
+    // Few long problems (a single long pair, not a shuffle batch): one problem per thread-block cluster, so
+    // that its wavefront runs on several SMs.  With enough problems to fill the GPU one CTA per problem has
+    // the higher throughput.  RP_CLUSTER=0 / 1 switches the multi-CTA path off / forces it.
+    const int G = rp::cluster_ctas();
+    const char* ce = std::getenv("RP_CLUSTER");
+    const bool cluster = ce ? std::atoi(ce) != 0 : (b->mcc_minb == 1 && b->n_mcc * G <= ctx->sm_count);
+    if (cluster) {
+      const int ncl = std::max(1, std::min({b->n_mcc, grid, ctx->sm_count / G}));
+      CU(rp::launch_mcc_cluster(d, ncl, ctx->threads, st));
+    } else {
+      CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, ctx->mcc_wide, st));
+    }
     launches++;
   }
   if (b->n_duplex > 0) {

@@ -7,6 +7,7 @@
 // results in the reference's layouts, and pulls the next one.  The grid is
 // sized to the number of CTAs that are simultaneously resident
 // (SMs x occupancy), so the whole shuffle batch is ONE launch.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -37,6 +38,29 @@ struct CtaExecT {
 
 using CtaExec = CtaExecT<4>;
 
+// one CTA of a thread-block cluster that works on ONE problem (solve_mcc_cluster)
+template <int W>
+struct ClusterExec {
+  static constexpr int kBatch = 4;
+  static constexpr int kWide = W;
+  long long* prof;
+  __device__ __forceinline__ int rank() const { return (int)cooperative_groups::this_cluster().block_rank(); }
+  __device__ __forceinline__ int nranks() const { return (int)cooperative_groups::this_cluster().num_blocks(); }
+  __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+  template <class F>
+  __device__ __forceinline__ void phase(int id, F f) {
+    long long t0 = 0;
+    if (prof && threadIdx.x == 0) t0 = clock64();
+    f(threadIdx.x);
+    __syncthreads();
+    if (prof && threadIdx.x == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(prof + id), (unsigned long long)(clock64() - t0));
+      atomicAdd(reinterpret_cast<unsigned long long*>(prof + 32 + id), 1ull);
+    }
+  }
+  __device__ __forceinline__ void csync() { cooperative_groups::this_cluster().sync(); }
+};
+
 }  // namespace
 
 // Instantiated for two register budgets: <2> two CTAs per SM at 64 registers (many short problems
@@ -66,6 +90,38 @@ __global__ void __launch_bounds__(RP_MCC_THREADS, MINB) mcc_persistent(BatchDev 
     c.dbg = b.dbg;
     if (W > BAND) solve_mcc_wide(ex, c, p, b.dense, b.logz, sh);
     else solve_mcc(ex, c, p, b.dense, b.logz, sh);
+  }
+}
+
+// mcc_cluster_kernel: the multi-CTA wavefront for long problems when there are few of them (a single long
+// pair rather than a shuffle batch).  A cluster of RP_CLUSTER_CTAS CTAs works on one problem
+// (solve_mcc_cluster); clusters pull problems from the same cost-ordered queue, one workspace slot each.
+#ifndef RP_CLUSTER_CTAS
+#define RP_CLUSTER_CTAS 8
+#endif
+template <int W>
+__global__ void __cluster_dims__(RP_CLUSTER_CTAS, 1, 1) __launch_bounds__(RP_MCC_THREADS, 1) mcc_cluster_kernel(BatchDev b) {
+  namespace cg = cooperative_groups;
+  extern __shared__ double smem_raw[];
+  __shared__ int s_next;
+  cg::cluster_group cl = cg::this_cluster();
+  ClusterExec<W> ex;
+  ex.prof = b.prof;
+  Shared sh;
+  carve_shared(sh, smem_raw, blockDim.x, W);
+  const int cid = blockIdx.x / RP_CLUSTER_CTAS;
+  for (;;) {
+    if (cl.block_rank() == 0 && threadIdx.x == 0) s_next = atomicAdd(b.counter, 1);
+    cl.sync();
+    const int q = *cl.map_shared_rank(&s_next, 0);   // rank 0's copy, through distributed shared memory
+    cl.sync();                                       // everybody has read it before rank 0 draws again
+    if (q >= b.nprob) break;
+    const Problem p = b.probs[b.order[q]];
+    if (p.kind == KIND_DUPLEX) continue;
+    Ctx c;
+    bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)cid * b.slot_stride);
+    c.dbg = b.dbg;
+    solve_mcc_cluster(ex, c, p, b.dense, b.logz, sh);
   }
 }
 
@@ -413,6 +469,15 @@ cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, int w
   size_t smem = shared_bytes(threads, w);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<grid, threads, smem, st>>>(b);
+  return cudaGetLastError();
+}
+
+int cluster_ctas() { return RP_CLUSTER_CTAS; }
+cudaError_t launch_mcc_cluster(const BatchDev& b, int nclusters, int threads, cudaStream_t st) {
+  size_t smem = shared_bytes(threads, 10);
+  cudaError_t e = cudaFuncSetAttribute(mcc_cluster_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  mcc_cluster_kernel<10><<<nclusters * RP_CLUSTER_CTAS, threads, smem, st>>>(b);
   return cudaGetLastError();
 }
 

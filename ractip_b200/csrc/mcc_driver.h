@@ -288,6 +288,135 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
   emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M, &c.M->gfull[0][0]);
 }
 
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// general kernel, ONE problem on a thread-block CLUSTER (long problems when there are too few of them
+// to fill the GPU: a single 1000 x 500 pair instead of a shuffle batch).  Same phases as solve_mcc_wide;
+// the chunks of a diagonal (cells, far-pass rows) and the items of the flat passes (prologue, unpaired
+// windows, outputs) are dealt out over the G CTAs of the cluster.  A chunk's two phases (partial sums,
+// then the reduction / the finish of its cells) stay inside one CTA and need only __syncthreads; what
+// crosses CTAs -- every table in the problem's HBM workspace -- is ordered by one cluster barrier
+// (release/acquire at cluster scope, which also drops the L1) per dependency level: after the far pass
+// of a band and after the finishing phase of every diagonal.
+// Exec: phase(id, f) = f(threadIdx.x) + __syncthreads; csync() = cluster barrier; rank(), nranks().
+// ---------------------------------------------------------------------------
+template <class Exec>
+__device__ void solve_mcc_cluster(Exec& ex, Ctx& c, const Problem& p, float* dense, double* logz, const Shared& sh) {
+  constexpr int W = Exec::kWide;
+  const int T = sh.T, n = c.n;
+  const int R = ex.rank(), G = ex.nranks(), GT = G * T;
+  auto share = [&](int total, int cap) {   // chunk size that spreads `total` items over the G CTAs, at most `cap`
+    int ch = (total + G - 1) / G;
+    if (ch > cap) ch = cap;
+    return ch < 1 ? 1 : ch;
+  };
+  if (n + 2 <= RP_SMEM_SEQ) {
+    const uint8_t* gS = c.S;
+    ex.phase(PH_STAGE, [&](int tid) {
+      for (int x = tid; x <= n + 1; x += T) sh.S[x] = gS[x];
+    });
+    c.S = sh.S;
+  }
+  ex.phase(PH_PROLOGUE, [&](int tid) {
+    load_shared_model(*c.M, sh, tid);
+    prologue_vectors(c, R * T + tid, GT);
+    prologue_lists(c, R * T + tid, GT);
+  });
+  ex.csync();
+  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, R * T + tid, GT); });
+  ex.csync();
+
+  for (int d = TURN + 1; d <= n - 1; d++) {
+    if (d == wide_start_inside<W>(d)) {
+      const int rows = n - d;
+      const int chunk = share(rows, wide_chunk<W>(T));
+      for (int i0 = 1 + R * chunk; i0 <= rows; i0 += G * chunk) {
+        const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) { wide_inside_A_shfl<W, Exec::kBatch>(c, sh, d, i0, C, tid); });
+        ex.phase(PH_BAND_B, [&](int tid) { wide_inside_B_shfl<W>(c, sh, d, i0, C, tid); });
+      }
+      ex.csync();
+    }
+    const int cells = n - d;
+    const int chunk = share(cells, T);
+    for (int i0 = 1 + R * chunk; i0 <= cells; i0 += G * chunk) {
+      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
+      ex.phase(PH_INSIDE_A, [&](int tid) { inside_A(c, sh, d, i0, C, tid); });
+      ex.phase(PH_INSIDE_B, [&](int tid) { wide_inside_finish<W>(c, sh, d, i0, C, tid); });
+    }
+    ex.csync();
+  }
+  inside_end(c);
+  if (logz && R == 0) {
+    ex.phase(PH_LOGZ, [&](int tid) {
+      if (tid == 0) logz[(size_t)p.pair * 3 + p.which] = log(TB(c, T_Q, n - 1, 1)) + n * log(c.M->pf_scale);
+    });
+  }
+
+  for (int d = n - 1; d >= TURN + 1; d--) {
+    if (c.cp > 0) {   // the nick sums are O(n) per diagonal: one CTA
+      if (R == 0) {
+        const int np = T >= 128 ? T / 4 : 32;
+        double* red = T >= 128 ? sh.part : sh.red;
+        ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, red, 1, np, d, tid, T); });
+        ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, red, 1, np, d, tid, T); });
+      }
+      ex.csync();
+    }
+    if (d == wide_start_outside<W>(n, d)) {
+      const int rows = n - d + W - 1;
+      const int chunk = share(rows, wide_chunk<W>(T));
+      for (int r0 = R * chunk; r0 < rows; r0 += G * chunk) {
+        const int C = rows - r0 < chunk ? rows - r0 : chunk;
+        ex.phase(PH_BAND_A, [&](int tid) { wide_outside_A_shfl<W, Exec::kBatch>(c, sh, d, r0, C, tid); });
+        ex.phase(PH_BAND_B, [&](int tid) { wide_outside_B_shfl<W>(c, sh, d, r0, C, tid); });
+      }
+      ex.csync();
+    }
+    const int cells = n - d;
+    const int chunk = share(cells, T);
+    for (int i0 = 1 + R * chunk; i0 <= cells; i0 += G * chunk) {
+      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
+      ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
+      ex.phase(PH_OUTSIDE_B, [&](int tid) { wide_outside_finish<W>(c, sh, d, i0, C, tid); });
+    }
+    ex.csync();
+  }
+
+  // outputs and the unpaired-window pass: flat loops over all threads of the cluster, a cluster barrier
+  // wherever emit_outputs has a phase boundary
+  if (p.kind == KIND_LINEAR) {
+    if (p.out_bp >= 0) {
+      ex.phase(PH_WRITE_BP, [&](int tid) { write_bp(c, dense + p.out_bp, R * T + tid, GT); });
+      ex.csync();
+      ex.phase(PH_WRITE_BP, [&](int tid) { write_bp2(c, dense + p.out_bp, R * T + tid, GT); });
+    }
+    if (p.max_w > 0) {
+      ex.phase(PH_UN_HAIRPIN, [&](int tid) {
+        unstru_hairpin(c, R * T + tid, GT);
+        unstru_gap_specials(c, *c.M, R * T + tid, GT);
+      });
+      ex.csync();
+      ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(c, &c.M->gfull[0][0], 0, R * T + tid, GT); });
+      ex.csync();
+      ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(c, &c.M->gfull[0][0], 1, R * T + tid, GT); });
+      ex.csync();
+      ex.phase(PH_UN_DOMROWS, [&](int tid) { unstru_dom_rows(c, R * T + tid, GT); });
+      ex.csync();
+      ex.phase(PH_UN_DOMCOLS, [&](int tid) { unstru_dom_cols(c, R * T + tid, GT); });
+      ex.csync();
+      ex.phase(PH_UN_MLTAB, [&](int tid) { unstru_ml_tables(c, R * T + tid, GT); });
+      ex.csync();
+      if (p.out_up >= 0) ex.phase(PH_UN_WINDOWS, [&](int tid) { unstru_windows(c, dense + p.out_up, R * T + tid, GT); });
+    }
+  } else if (p.kind == KIND_COFOLD) {
+    if (p.out_hp >= 0)
+      ex.phase(PH_WRITE_HP, [&](int tid) { write_hp(c, dense + p.out_hp, p.n1, p.n2, p.th_hy, R * T + tid, GT); });
+  }
+  ex.csync();   // the slot is reused by the cluster's next problem
+}
+#endif
+
 // ---------------------------------------------------------------------------
 // band kernel: one problem per CTA, interior-loop operands in a shared-memory
 // ring of the last 32 diagonals (mcc_band.h); split sums, nick sums, unpaired

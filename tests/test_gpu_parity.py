@@ -359,3 +359,21 @@ def test_split_fetch_of_uniform_batches(stage, bundled, monkeypatch):
             assert np.array_equal(getattr(x, name), getattr(z, name)), name
             assert np.array_equal(getattr(y, name), getattr(z, name)), name
         assert x.bp2.max() > 0 and x.bp1.max() > 0 and x.up1.max() > 0
+
+
+@pytest.mark.parametrize("cluster", ["0", "1"])
+def test_multi_cta_wavefront_matches_oracle(model, oracle, monkeypatch, cluster):
+    """Long problems, few of them: one problem per thread-block cluster (RP_CLUSTER=1 forces the multi-CTA
+    wavefront, 0 the one-CTA-per-problem build); both against the oracle, incl. unpaired windows and a nick."""
+    from ractip_b200 import ProbabilityStage, default_opts
+    monkeypatch.setenv("RP_CLUSTER", cluster)
+    monkeypatch.setenv("RP_MCC_LONG_N", "224")
+    rng = np.random.default_rng(8800)
+    opts = default_opts()
+    pairs = [(rand_seq(rng, 300), rand_seq(rng, 130)), (rand_seq(rng, 230), rand_seq(rng, 261)), (rand_seq(rng, 40), rand_seq(rng, 610))]
+    st = ProbabilityStage(model)
+    try:
+        for (s1, s2), r in zip(pairs, st.run_dense(pairs, opts)):
+            _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"cluster={cluster} {len(s1)}x{len(s2)}")
+    finally:
+        st.close()
