@@ -261,7 +261,9 @@ enum {
   RP_KERNEL_GENERAL_WIDE = 3 /* the same with 128 registers, 1 CTA/SM and split  */
                             /* sums in bands of 10 diagonals: n >= 900.  A batch */
                             /* runs ALL its general-kernel problems in this build */
-                            /* when its longest one qualifies.                    */
+                            /* when its longest one qualifies; with few such      */
+                            /* problems (<= ~90) each runs on a thread-block       */
+                            /* cluster of 8 or 16 CTAs (multi-CTA wavefront).      */
 };
 int rp_kernel_plan(int n, size_t smem_limit, size_t* smem_bytes);
 

@@ -756,14 +756,17 @@ int rp_batch_run(rp_batch* b) {
   }
   if (b->n_mcc > 0) {
     // Few long problems (a single long pair, not a shuffle batch): one problem per thread-block cluster, so
-    // that its wavefront runs on several SMs.  With enough problems to fill the GPU one CTA per problem has
-    // the higher throughput.  RP_CLUSTER=0 / 1 switches the multi-CTA path off / forces it.
-    const int G = rp::cluster_ctas();
+    // that its wavefront runs on several SMs -- 16 CTAs per problem while that leaves no cluster waiting,
+    // 8 up to ~5 rounds of clusters.  Beyond that one CTA per problem has the higher throughput (a 1500-nt
+    // problem: 57 ms on 16 SMs, 76 ms on 8, ~400 ms on one).
+    // RP_CLUSTER=0 switches the multi-CTA path off, 8 / 16 force it with that cluster size.
     const char* ce = std::getenv("RP_CLUSTER");
-    const bool cluster = ce ? std::atoi(ce) != 0 : (b->mcc_minb == 1 && b->n_mcc * G <= ctx->sm_count);
-    if (cluster) {
+    int G = 0;
+    if (ce) G = std::atoi(ce) >= 16 ? 16 : std::atoi(ce) > 0 ? 8 : 0;
+    else if (b->mcc_minb == 1) G = b->n_mcc * 16 <= ctx->sm_count ? 16 : b->n_mcc <= 5 * (ctx->sm_count / 8) ? 8 : 0;
+    if (G) {
       const int ncl = std::max(1, std::min({b->n_mcc, grid, ctx->sm_count / G}));
-      CU(rp::launch_mcc_cluster(d, ncl, ctx->threads, st));
+      CU(rp::launch_mcc_cluster(d, ncl, G, ctx->threads, st));
     } else {
       CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, ctx->mcc_wide, st));
     }

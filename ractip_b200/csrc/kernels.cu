@@ -94,13 +94,11 @@ __global__ void __launch_bounds__(RP_MCC_THREADS, MINB) mcc_persistent(BatchDev 
 }
 
 // mcc_cluster_kernel: the multi-CTA wavefront for long problems when there are few of them (a single long
-// pair rather than a shuffle batch).  A cluster of RP_CLUSTER_CTAS CTAs works on one problem
-// (solve_mcc_cluster); clusters pull problems from the same cost-ordered queue, one workspace slot each.
-#ifndef RP_CLUSTER_CTAS
-#define RP_CLUSTER_CTAS 8
-#endif
-template <int W>
-__global__ void __cluster_dims__(RP_CLUSTER_CTAS, 1, 1) __launch_bounds__(RP_MCC_THREADS, 1) mcc_cluster_kernel(BatchDev b) {
+// pair rather than a shuffle batch).  A cluster of G CTAs works on one problem (solve_mcc_cluster); clusters
+// pull problems from the same cost-ordered queue, one workspace slot each.  G = 16 (beyond the portable
+// cluster size, opted in at launch) when there are at most sm_count/16 problems, else 8.
+template <int W, int G>
+__global__ void __cluster_dims__(G, 1, 1) __launch_bounds__(RP_MCC_THREADS, 1) mcc_cluster_kernel(BatchDev b) {
   namespace cg = cooperative_groups;
   extern __shared__ double smem_raw[];
   __shared__ int s_next;
@@ -109,7 +107,7 @@ __global__ void __cluster_dims__(RP_CLUSTER_CTAS, 1, 1) __launch_bounds__(RP_MCC
   ex.prof = b.prof;
   Shared sh;
   carve_shared(sh, smem_raw, blockDim.x, W);
-  const int cid = blockIdx.x / RP_CLUSTER_CTAS;
+  const int cid = blockIdx.x / G;
   for (;;) {
     if (cl.block_rank() == 0 && threadIdx.x == 0) s_next = atomicAdd(b.counter, 1);
     cl.sync();
@@ -472,12 +470,17 @@ cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, int w
   return cudaGetLastError();
 }
 
-int cluster_ctas() { return RP_CLUSTER_CTAS; }
-cudaError_t launch_mcc_cluster(const BatchDev& b, int nclusters, int threads, cudaStream_t st) {
+cudaError_t launch_mcc_cluster(const BatchDev& b, int nclusters, int ctas, int threads, cudaStream_t st) {
   size_t smem = shared_bytes(threads, 10);
-  cudaError_t e = cudaFuncSetAttribute(mcc_cluster_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  MccKernel k = ctas >= 16 ? mcc_cluster_kernel<10, 16> : mcc_cluster_kernel<10, 8>;
+  const int G = ctas >= 16 ? 16 : 8;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  mcc_cluster_kernel<10><<<nclusters * RP_CLUSTER_CTAS, threads, smem, st>>>(b);
+  if (G > 8) {   // beyond the portable cluster size
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<nclusters * G, threads, smem, st>>>(b);
   return cudaGetLastError();
 }
 

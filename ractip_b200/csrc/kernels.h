@@ -78,9 +78,8 @@ struct SparseDev {
 // minb = 2: 64-register build, two CTAs per SM; 1: 128 registers, one CTA per SM, split sums in bands of `wide` diagonals
 int mcc_max_ctas_per_sm(int threads, int minb, int wide);
 cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, int wide, cudaStream_t st);
-// multi-CTA wavefront: `nclusters` clusters of cluster_ctas() CTAs, one problem (and one workspace slot) per cluster
-int cluster_ctas();
-cudaError_t launch_mcc_cluster(const BatchDev& b, int nclusters, int threads, cudaStream_t st);
+// multi-CTA wavefront: `nclusters` clusters of `ctas` (8 or 16) CTAs, one problem (and one workspace slot) per cluster
+cudaError_t launch_mcc_cluster(const BatchDev& b, int nclusters, int ctas, int threads, cudaStream_t st);
 int band_max_ctas_per_sm(int threads, size_t smem);   // threads = 256 (2 CTAs/SM) or 512 (1 CTA/SM)
 cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, cudaStream_t st);
 int lockstep_max_ctas_per_sm(int threads);

@@ -361,10 +361,10 @@ def test_split_fetch_of_uniform_batches(stage, bundled, monkeypatch):
         assert x.bp2.max() > 0 and x.bp1.max() > 0 and x.up1.max() > 0
 
 
-@pytest.mark.parametrize("cluster", ["0", "1"])
+@pytest.mark.parametrize("cluster", ["0", "8", "16"])
 def test_multi_cta_wavefront_matches_oracle(model, oracle, monkeypatch, cluster):
-    """Long problems, few of them: one problem per thread-block cluster (RP_CLUSTER=1 forces the multi-CTA
-    wavefront, 0 the one-CTA-per-problem build); both against the oracle, incl. unpaired windows and a nick."""
+    """Long problems, few of them: one problem per thread-block cluster (RP_CLUSTER=8 / 16 force the multi-CTA
+    wavefront with that cluster size, 0 the one-CTA-per-problem build); both against the oracle, incl. unpaired windows and a nick."""
     from ractip_b200 import ProbabilityStage, default_opts
     monkeypatch.setenv("RP_CLUSTER", cluster)
     monkeypatch.setenv("RP_MCC_LONG_N", "224")
