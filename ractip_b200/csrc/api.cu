@@ -763,7 +763,8 @@ int rp_batch_run(rp_batch* b) {
     const char* ce = std::getenv("RP_CLUSTER");
     int G = 0;
     if (ce) G = std::atoi(ce) >= 16 ? 16 : std::atoi(ce) > 0 ? 8 : 0;
-    else if (b->mcc_minb == 1) G = b->n_mcc * 16 <= ctx->sm_count ? 16 : b->n_mcc <= 5 * (ctx->sm_count / 8) ? 8 : 0;
+    else if (b->n_mcc * 16 <= ctx->sm_count) G = 16;                      // any general-kernel length (measured: one 250 x 100 pair 17.2 -> 9.3 ms)
+    else if (b->n_mcc * 8 <= ctx->sm_count * (b->mcc_minb == 1 ? 5 : 4)) G = 8;   // up to 4-5 rounds of clusters (20 pairs of 400 x 300: 87 -> 56 ms; 40 pairs: 93 vs 106 ms)
     if (G) {
       const int ncl = std::max(1, std::min({b->n_mcc, grid, ctx->sm_count / G}));
       CU(rp::launch_mcc_cluster(d, ncl, G, ctx->threads, st));
