@@ -765,12 +765,15 @@ int rp_batch_run(rp_batch* b) {
     if (ce) G = std::atoi(ce) >= 16 ? 16 : std::atoi(ce) > 0 ? 8 : 0;
     else if (b->n_mcc * 16 <= ctx->sm_count) G = 16;                      // any general-kernel length (measured: one 250 x 100 pair 17.2 -> 9.3 ms)
     else if (b->n_mcc * 8 <= ctx->sm_count * (b->mcc_minb == 1 ? 5 : 4)) G = 8;   // up to 4-5 rounds of clusters (20 pairs of 400 x 300: 87 -> 56 ms; 40 pairs: 93 vs 106 ms)
-    if (G) {
+    // a cluster shape the device (or its current partitioning) cannot schedule fails at launch, before
+    // anything ran: fall back to the smaller cluster, then to one CTA per problem
+    bool launched = false;
+    for (; G && !launched; G = G == 16 ? 8 : 0) {
       const int ncl = std::max(1, std::min({b->n_mcc, grid, ctx->sm_count / G}));
-      CU(rp::launch_mcc_cluster(d, ncl, G, ctx->threads, st));
-    } else {
-      CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, ctx->mcc_wide, st));
+      if (rp::launch_mcc_cluster(d, ncl, G, ctx->threads, st) == cudaSuccess) launched = true;
+      else cudaGetLastError();
     }
+    if (!launched) CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, ctx->mcc_wide, st));
     launches++;
   }
   if (b->n_duplex > 0) {
