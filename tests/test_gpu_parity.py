@@ -330,14 +330,23 @@ def test_pinned_host_buffer_is_written_in_place(stage, bundled, monkeypatch):
                 assert np.array_equal(getattr(x, name), getattr(y, name)), (duplex, name)
 
 
-def test_configs4_size_pair_matches_oracle(stage, oracle):
-    """One pair of BASELINE configs[4]'s size (1000 x 500 nt, two-strand problem of 1500 nt) against the oracle."""
-    from ractip_b200 import default_opts
+@pytest.mark.parametrize("cluster", [None, "0"])
+def test_configs4_size_pair_matches_oracle(model, oracle, monkeypatch, cluster):
+    """One pair of BASELINE configs[4]'s size (1000 x 500 nt, two-strand problem of 1500 nt) against the oracle:
+    on the default route for a single pair (16-CTA clusters) and on the batch's route (one CTA per problem,
+    wide bands; RP_CLUSTER=0)."""
+    from ractip_b200 import ProbabilityStage, default_opts
+    if cluster is not None:
+        monkeypatch.setenv("RP_CLUSTER", cluster)
     rng = np.random.default_rng(20261018)
     s1 = "".join("ACGU"[x] for x in rng.integers(0, 4, 1000))
     s2 = "".join("ACGU"[x] for x in rng.integers(0, 4, 500))
     opts = default_opts()
-    r = stage.run_dense([(s1, s2)], opts, pinned=True)[0]
+    st = ProbabilityStage(model)
+    try:
+        r = st.run_dense([(s1, s2)], opts, pinned=True)[0]
+    finally:
+        st.close()
     _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, "1000x500")
 
 
@@ -361,13 +370,15 @@ def test_split_fetch_of_uniform_batches(stage, bundled, monkeypatch):
         assert x.bp2.max() > 0 and x.bp1.max() > 0 and x.up1.max() > 0
 
 
-@pytest.mark.parametrize("cluster", ["0", "8", "16"])
-def test_multi_cta_wavefront_matches_oracle(model, oracle, monkeypatch, cluster):
+@pytest.mark.parametrize("cluster,long_n", [("0", "224"), ("8", "224"), ("16", "224"), ("0", "100000")])
+def test_multi_cta_wavefront_matches_oracle(model, oracle, monkeypatch, cluster, long_n):
     """Long problems, few of them: one problem per thread-block cluster (RP_CLUSTER=8 / 16 force the multi-CTA
-    wavefront with that cluster size, 0 the one-CTA-per-problem build); both against the oracle, incl. unpaired windows and a nick."""
+    wavefront with that cluster size, 0 the one-CTA-per-problem builds: the 128-register wide-band one with
+    RP_MCC_LONG_N=224, the 64-register one with the threshold out of reach); all against the oracle, incl.
+    unpaired windows and a nick."""
     from ractip_b200 import ProbabilityStage, default_opts
     monkeypatch.setenv("RP_CLUSTER", cluster)
-    monkeypatch.setenv("RP_MCC_LONG_N", "224")
+    monkeypatch.setenv("RP_MCC_LONG_N", long_n)
     rng = np.random.default_rng(8800)
     opts = default_opts()
     pairs = [(rand_seq(rng, 300), rand_seq(rng, 130)), (rand_seq(rng, 230), rand_seq(rng, 261)), (rand_seq(rng, 40), rand_seq(rng, 610))]
