@@ -354,14 +354,14 @@ __device__ void solve_mcc_cluster(Exec& ex, Ctx& c, const Problem& p, float* den
   }
 
   for (int d = n - 1; d >= TURN + 1; d--) {
-    if (c.cp > 0) {   // the nick sums are O(n) per diagonal: one CTA
-      if (R == 0) {
-        const int np = T >= 128 ? T / 4 : 32;
-        double* red = T >= 128 ? sh.part : sh.red;
-        ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, red, 1, np, d, tid, T); });
-        ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, red, 1, np, d, tid, T); });
-      }
-      ex.csync();
+    if (c.cp > 0) {
+      // The nick sums are O(n) per diagonal.  EVERY CTA computes them (same operands, same order: the same
+      // bits) and stores the four results itself, so its finishing phase below depends on nothing another
+      // CTA does in this step -- no cluster barrier here; the redundant stores carry identical values.
+      const int np = T >= 128 ? T / 4 : 32;
+      double* red = T >= 128 ? sh.part : sh.red;
+      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, red, 1, np, d, tid, T); });
+      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, red, 1, np, d, tid, T); });
     }
     if (d == wide_start_outside<W>(n, d)) {
       const int rows = n - d + W - 1;
