@@ -3,10 +3,10 @@
 
 Prints, per pair, the CUDA-event time of the kernels (device-resident batch), the end-to-end time of
 rp_run_dense (host buffers in and out) and the oracle port's single-thread time for the same pair
-(the reference is single-threaded, src/ractip.cpp:1494).  Test/measurement aid; the product path never
-touches the oracle.
+(the reference is single-threaded, src/ractip.cpp:1494).  Measurement aid that lives under tests/ because it
+times the oracle next to the GPU path (not collected by pytest); the product path never touches the oracle.
 
-    python tools/bundled_latency.py [--reps 20]
+    python tests/bundled_latency.py [--reps 20]
 """
 import argparse
 import json

@@ -1,6 +1,6 @@
 """The --zscore shuffle generator against the REFERENCE's own uShuffle
 (src/ushuffle.c, compiled into oracle/_ref; golden outputs in tests/golden/ushuffle.json
-made by tools/gen_golden.py with the driving sequence of src/ractip.cpp:1636-1643)."""
+made by tests/golden/gen_golden.py with the driving sequence of src/ractip.cpp:1636-1643)."""
 import json
 from collections import Counter
 from pathlib import Path
