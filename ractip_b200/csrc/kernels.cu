@@ -20,6 +20,7 @@ namespace {
 template <int NB = 4, int W = BAND>
 struct CtaExecT {
   static constexpr int kBatch = NB;   // load-batch depth of the split-sum band phases (mcc_band_shfl.cuh)
+  static constexpr int kWideBatch = 8;   // ... of the wide far passes: one sum at a time leaves registers for 8 steps' loads
   static constexpr int kWide = W;     // diagonals per split-sum band of the general kernel (solve_mcc_wide when > BAND)
   long long* prof;  // optional per-phase cycle counters (RP_PROFILE=1), else null
   __device__ __forceinline__ int nthreads() const { return blockDim.x; }
@@ -42,6 +43,7 @@ using CtaExec = CtaExecT<4>;
 template <int W>
 struct ClusterExec {
   static constexpr int kBatch = 4;
+  static constexpr int kWideBatch = 8;
   static constexpr int kWide = W;
   long long* prof;
   __device__ __forceinline__ int rank() const { return (int)cooperative_groups::this_cluster().block_rank(); }

@@ -216,7 +216,7 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
         const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
         ex.phase(PH_BAND_A, [&](int tid) {
 #ifdef __CUDA_ARCH__
-          wide_inside_A_shfl<W, Exec::kBatch>(c, sh, d, i0, C, tid);
+          wide_inside_A_shfl<W, Exec::kWideBatch>(c, sh, d, i0, C, tid);
 #else
           wide_inside_A<W>(c, sh, d, i0, C, tid);
 #endif
@@ -263,7 +263,7 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
         const int C = rows - r0 < chunk ? rows - r0 : chunk;
         ex.phase(PH_BAND_A, [&](int tid) {
 #ifdef __CUDA_ARCH__
-          wide_outside_A_shfl<W, Exec::kBatch>(c, sh, d, r0, C, tid);
+          wide_outside_A_shfl<W, Exec::kWideBatch>(c, sh, d, r0, C, tid);
 #else
           wide_outside_A<W>(c, sh, d, r0, C, tid);
 #endif
@@ -332,7 +332,7 @@ __device__ void solve_mcc_cluster(Exec& ex, Ctx& c, const Problem& p, float* den
       const int chunk = share(rows, wide_chunk<W>(T));
       for (int i0 = 1 + R * chunk; i0 <= rows; i0 += G * chunk) {
         const int C = rows - i0 + 1 < chunk ? rows - i0 + 1 : chunk;
-        ex.phase(PH_BAND_A, [&](int tid) { wide_inside_A_shfl<W, Exec::kBatch>(c, sh, d, i0, C, tid); });
+        ex.phase(PH_BAND_A, [&](int tid) { wide_inside_A_shfl<W, Exec::kWideBatch>(c, sh, d, i0, C, tid); });
         ex.phase(PH_BAND_B, [&](int tid) { wide_inside_B_shfl<W>(c, sh, d, i0, C, tid); });
       }
       ex.csync();
@@ -368,7 +368,7 @@ __device__ void solve_mcc_cluster(Exec& ex, Ctx& c, const Problem& p, float* den
       const int chunk = share(rows, wide_chunk<W>(T));
       for (int r0 = R * chunk; r0 < rows; r0 += G * chunk) {
         const int C = rows - r0 < chunk ? rows - r0 : chunk;
-        ex.phase(PH_BAND_A, [&](int tid) { wide_outside_A_shfl<W, Exec::kBatch>(c, sh, d, r0, C, tid); });
+        ex.phase(PH_BAND_A, [&](int tid) { wide_outside_A_shfl<W, Exec::kWideBatch>(c, sh, d, r0, C, tid); });
         ex.phase(PH_BAND_B, [&](int tid) { wide_outside_B_shfl<W>(c, sh, d, r0, C, tid); });
       }
       ex.csync();
