@@ -259,7 +259,7 @@ enum {
   RP_KERNEL_BAND_2CTA = 1,  /* shared-memory band kernel, 256 threads, 2 CTA/SM */
   RP_KERNEL_GENERAL = 2,    /* HBM-table wavefront kernel (any length), 2 CTA/SM */
   RP_KERNEL_GENERAL_WIDE = 3 /* the same with 128 registers, 1 CTA/SM and split  */
-                            /* sums in bands of 10 diagonals: n >= 900.  A batch */
+                            /* sums in bands of 10 diagonals: n >= 700.  A batch */
                             /* runs ALL its general-kernel problems in this build */
                             /* when its longest one qualifies; with few such      */
                             /* problems (<= ~90) each runs on a thread-block       */

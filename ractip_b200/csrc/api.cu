@@ -31,7 +31,7 @@ struct rp_ctx {
   int sm_count = 0;
   int ctas_per_sm = 0;       // general kernel, 64-register build (two CTAs per SM)
   int ctas_per_sm1 = 0;      // general kernel, 128-register build (one CTA per SM: long problems)
-  int mcc_long_n = 900;      // problems at least this long run the 128-register build (RP_MCC_LONG_N)
+  int mcc_long_n = 700;      // problems at least this long run the 128-register build (RP_MCC_LONG_N)
   int mcc_wide = 10;         // ... with split-sum bands of this many diagonals (RP_MCC_WIDE: 5, 10, 15)
   int ls_threads = RP_LS_THREADS;
   int ls_ctas_per_sm = 0;
@@ -220,7 +220,7 @@ int rp_kernel_plan(int n, size_t smem_limit, size_t* smem_bytes) {
   if (s256 <= half_sm) { if (smem_bytes) *smem_bytes = s256; return RP_KERNEL_BAND_2CTA; }
   if (smem_bytes) *smem_bytes = s512;
   if (s512 <= smem_limit) return RP_KERNEL_BAND_1CTA;
-  return n >= 900 ? RP_KERNEL_GENERAL_WIDE : RP_KERNEL_GENERAL;   // rp_ctx::mcc_long_n default
+  return n >= 700 ? RP_KERNEL_GENERAL_WIDE : RP_KERNEL_GENERAL;   // rp_ctx::mcc_long_n default
 }
 
 const char* rp_strerror(int code) {

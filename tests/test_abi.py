@@ -94,7 +94,7 @@ def test_kernel_plan_routes_lengths_by_shared_memory(lib):
     assert lib.rp_kernel_plan(215, 0, C.byref(smem)) == 0 and smem.value <= 232448
     assert lib.rp_kernel_plan(223, 0, C.byref(smem)) == 0 and smem.value <= 232448 - 64   # OxyS x fhlA (222) still fits
     assert lib.rp_kernel_plan(224, 0, None) == 2
-    assert lib.rp_kernel_plan(1500, 0, None) == 3 and lib.rp_kernel_plan(899, 0, None) == 2 and lib.rp_kernel_plan(900, 0, None) == 3
+    assert lib.rp_kernel_plan(1500, 0, None) == 3 and lib.rp_kernel_plan(699, 0, None) == 2 and lib.rp_kernel_plan(700, 0, None) == 3
     # monotone in n, and every band answer respects the limit it was given
     prev = 1
     for n in range(1, 400):
