@@ -13,6 +13,12 @@
 #include "kernels.h"
 #include "mcc_driver.h"
 
+#ifdef RP_TUNE
+#define RP_EXPROF(p) (p)
+#else
+#define RP_EXPROF(p) false
+#endif
+
 namespace rp {
 
 namespace {
@@ -27,10 +33,10 @@ struct CtaExecT {
   template <class F>
   __device__ __forceinline__ void phase(int id, F f) {
     long long t0 = 0;
-    if (prof && threadIdx.x == 0) t0 = clock64();
+    if (RP_EXPROF(prof) && threadIdx.x == 0) t0 = clock64();
     f(threadIdx.x);
     __syncthreads();
-    if (prof && threadIdx.x == 0) {
+    if (RP_EXPROF(prof) && threadIdx.x == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(prof + id), (unsigned long long)(clock64() - t0));
       atomicAdd(reinterpret_cast<unsigned long long*>(prof + 32 + id), 1ull);
     }
@@ -52,10 +58,10 @@ struct ClusterExec {
   template <class F>
   __device__ __forceinline__ void phase(int id, F f) {
     long long t0 = 0;
-    if (prof && threadIdx.x == 0) t0 = clock64();
+    if (RP_EXPROF(prof) && threadIdx.x == 0) t0 = clock64();
     f(threadIdx.x);
     __syncthreads();
-    if (prof && threadIdx.x == 0) {
+    if (RP_EXPROF(prof) && threadIdx.x == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(prof + id), (unsigned long long)(clock64() - t0));
       atomicAdd(reinterpret_cast<unsigned long long*>(prof + 32 + id), 1ull);
     }

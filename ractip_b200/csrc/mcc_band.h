@@ -427,7 +427,7 @@ RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int
   for (int x = T - 1 - tid; x < cells; x += T) {
     const int i = 1 + x;
     double v;
-    if (c.dbg & 8) v = 0.;
+    if (RP_DBG(c) & 8) v = 0.;
     else if (SIGN > 0) v = inside_specials_band(c, bs, d, i);
     else v = outside_specials_band(c, bs, d, i);
     bs.ipart[(size_t)NSLICE * BR * bs.NGP + seg_slot(sg, bs, i)] = v;
@@ -439,7 +439,7 @@ RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int
       const int g = GB * b + hl;
       if (g >= NG) continue;
       double tot[BR];
-      if (c.dbg & 1) {
+      if (RP_DBG(c) & 1) {
 #pragma unroll
         for (int r = 0; r < BR; r++) tot[r] = 0.;
       } else {
@@ -565,7 +565,7 @@ template <class C>
 RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
   const int T = sh.T, n = c.n, cells = n - d;
   const SmallModel& M = *bs.sm;
-  if (c.dbg & 16) return;
+  if (RP_DBG(c) & 16) return;
   const int u = d - 1;  // hairpin size
   const int e = d - band_start_inside(d);
   const int vprev = (d & 1) ? V_U0 : V_U1, vcur = (d & 1) ? V_U1 : V_U0;
@@ -574,7 +574,7 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
     // ---- (1) loads
 #ifdef __CUDA_ARCH__
     long long tp0 = 0;
-    if (c.prof && tid == 0) tp0 = clock64();
+    if (RP_PROF(c) && tid == 0) tp0 = clock64();
 #endif
     const double* safe = c.ptr(T_Q, 0, 1);
     const double sM = ldg_now(c.ptr(T_QM2, d, i));
@@ -618,9 +618,9 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
     const size_t ro = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, i);
 #ifdef __CUDA_ARCH__
     long long tp1 = 0;
-    if (c.prof && tid == 0) tp1 = clock64();
+    if (RP_PROF(c) && tid == 0) tp1 = clock64();
 #endif
-    if (c.dbg & 128) { bs.sIv[i] = sM + sQ + qm2c + qm1l + qm1r + qql + uprev + hpw + scd + nq[0] + nq[1] + nq[2] + nq[3] + spv + nk1 + nk2; continue; }
+    if (RP_DBG(c) & 128) { bs.sIv[i] = sM + sQ + qm2c + qm1l + qm1r + qql + uprev + hpw + scd + nq[0] + nq[1] + nq[2] + nq[3] + spv + nk1 + nk2; continue; }
     // ---- (3) combine
 #pragma unroll
     for (int a = 0; a < BAND - 1; a++) sQ += M.scale_small[a + 1] * nq[a];   // q(i,i+a) = scale^(a+1), a <= TURN
@@ -629,14 +629,14 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
     qb += sI;
     qb += qm2c * k1;
     qb += k2 * nk1 * nk2;
-    if (!(c.dbg & 256)) RP_ST_STREAM(TB(c, T_QB, d, i), qb);
+    if (!(RP_DBG(c) & 256)) RP_ST_STREAM(TB(c, T_QB, d, i), qb);
     const double fI = qb * gI, f1 = qb * g1, fA = qb * gA;
     bs.TI[ro] = fI; bs.T1[ro] = f1; bs.TA[ro] = fA;
     if (wide) { RP_ST_STREAM(TB(c, T_QBI, d, i), fI); RP_ST_STREAM(TB(c, T_QB1N, d, i), f1); RP_ST_STREAM(TB(c, T_QBAU, d, i), fA); }
     const double qm1 = qm1l * m1 + qb * k3;
     const double U = mU * (qm1r + uprev);
     const double qq = qql * M.scale1 + qb * k4;
-    if (!(c.dbg & 256)) {
+    if (!(RP_DBG(c) & 256)) {
       TB(c, T_QM1, d, i) = qm1;
       VEC(c, vcur, i) = U;
       TB(c, T_QM, d, i) = qm1 + sM + U;
@@ -644,12 +644,12 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
       TB(c, T_Q, d, i) = scd + qq + sQ;
     } else bs.sIv[i] = qq + qm1 + U;
 #ifdef __CUDA_ARCH__
-    if (c.prof && tid == 0) {
+    if (RP_PROF(c) && tid == 0) {
       const long long tp2 = clock64();
-      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 24), (unsigned long long)(tp1 - tp0));
-      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 25), (unsigned long long)(tp2 - tp1));
-      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 32 + 24), 1ull);
-      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 32 + 25), 1ull);
+      atomicAdd(reinterpret_cast<unsigned long long*>(RP_PROF(c) + 24), (unsigned long long)(tp1 - tp0));
+      atomicAdd(reinterpret_cast<unsigned long long*>(RP_PROF(c) + 25), (unsigned long long)(tp2 - tp1));
+      atomicAdd(reinterpret_cast<unsigned long long*>(RP_PROF(c) + 32 + 24), 1ull);
+      atomicAdd(reinterpret_cast<unsigned long long*>(RP_PROF(c) + 32 + 25), 1ull);
     }
 #endif
   }
@@ -657,7 +657,7 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
 
 template <class C>
 RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
-  if (c.dbg & 16) return;
+  if (RP_DBG(c) & 16) return;
   const int T = sh.T, n = c.n, cells = n - d;
   const SmallModel& M = *bs.sm;
   for (int x = tid; x < cells; x += T) {
@@ -695,7 +695,7 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     const double gM = (tz && ss(c, k, k + 1) && ss(c, l - 1, l)) ? M.expMLclosing * ml_stem_bf(M, rt, sj1, si1) : 0.;
     const double sIraw = bs.sIv[k];
     const size_t ro = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, k);
-    if (c.dbg & 128) { bs.sIv[k] = sP + sL + qbv + plp + mcp + pmp + prp + q5 + q3 + qo + qn; continue; }
+    if (RP_DBG(c) & 128) { bs.sIv[k] = sP + sL + qbv + plp + mcp + pmp + prp + q5 + q3 + qo + qn; continue; }
     // ---- (3) combine
     const bool live = tz && qbv != 0.;
     const double PL = mlr ? plp * M.mlb1 + mcp : 0.;
@@ -720,8 +720,8 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
 
 template <int SIGN, class C>
 RP_HD void band_collect(const C& c, const BandShared& bs, int dsum, int dnext, int tid, int T) {
-  if (c.dbg & 32) return;
-  const int reps = (c.dbg & 512) ? 2 : 1;   // tuning aid: the same code twice tells cold-code cost from work
+  if (RP_DBG(c) & 32) return;
+  const int reps = (RP_DBG(c) & 512) ? 2 : 1;   // tuning aid: the same code twice tells cold-code cost from work
 #pragma unroll 1
   for (int rep = 0; rep < reps; rep++) {
     if (dsum >= 0) {

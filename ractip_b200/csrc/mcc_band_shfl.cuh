@@ -25,10 +25,10 @@ __device__ __forceinline__ double shfl_down_f64(double v, int delta) { return __
 // fine-grained probes (RP_PROFILE): thread 0 accumulates the cycles between two marks into slot k
 #define RP_MARK(k)                                                                                       \
   do {                                                                                                   \
-    if (c.prof && tid == 0) {                                                                            \
+    if (RP_PROF(c) && tid == 0) {                                                                            \
       const long long now__ = clock64();                                                                 \
-      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + (k)), (unsigned long long)(now__ - tmark)); \
-      atomicAdd(reinterpret_cast<unsigned long long*>(c.prof + 32 + (k)), 1ull);                         \
+      atomicAdd(reinterpret_cast<unsigned long long*>(RP_PROF(c) + (k)), (unsigned long long)(now__ - tmark)); \
+      atomicAdd(reinterpret_cast<unsigned long long*>(RP_PROF(c) + 32 + (k)), 1ull);                         \
       tmark = clock64();                                                                                 \
     }                                                                                                    \
   } while (0)
@@ -67,8 +67,8 @@ __device__ __forceinline__ void inside_band_A_shfl(const Ctx& c, const Shared& s
   double m[BAND], q[BAND];
 #pragma unroll
   for (int e = 0; e < BAND; e++) m[e] = q[e] = 0.;
-  long long tmark = (c.prof && tid == 0) ? clock64() : 0;
-  if (!(c.dbg & 2)) {
+  long long tmark = (RP_PROF(c) && tid == 0) ? clock64() : 0;
+  if (!(RP_DBG(c) & 2)) {
     const int amax = d0 - 1;
     const int lim = d0 - TURN - 2;
     const int askip = c.cp > 0 ? c.cp - 1 - i : -1;
@@ -185,8 +185,8 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
   double pr[BAND], ml[BAND];
 #pragma unroll
   for (int e = 0; e < BAND; e++) pr[e] = ml[e] = 0.;
-  long long tmark = (c.prof && tid == 0) ? clock64() : 0;
-  if (!(c.dbg & 2)) {
+  long long tmark = (RP_PROF(c) && tid == 0) ? clock64() : 0;
+  if (!(RP_DBG(c) & 2)) {
     {  // PR, row k; t = j - (k+d0+TURN+3)
       const int k = 1 + r;
       const int tmax = n - k - d0 - (TURN + 3);   // decreases along the lanes: a lane past its tmax feeds zeros

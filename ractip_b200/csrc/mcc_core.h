@@ -39,6 +39,16 @@
 #define RP_HD inline
 #endif
 
+// Tuning hooks (RP_DEBUG_SKIP switches, RP_PROFILE cycle counters) exist only in a -DRP_TUNE build: in the
+// product build they cost code size, and the per-diagonal loops have to fit the 32 KB instruction cache.
+#ifdef RP_TUNE
+#define RP_DBG(c) ((c).dbg)
+#define RP_PROF(c) ((c).prof)
+#else
+#define RP_DBG(c) 0
+#define RP_PROF(c) (static_cast<long long*>(nullptr))
+#endif
+
 namespace rp {
 
 // ---------------------------------------------------------------------------
@@ -573,7 +583,7 @@ RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int typ
   int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
   if (maxpo - 1 < u1max) u1max = maxpo - 1;
   double sI = 0., s1 = 0., sA = 0.;
-  if (!(c.dbg & 1))
+  if (!(RP_DBG(c) & 1))
     interior_rows<1>(sh, c.ptr(T_QBI, d, i), c.ptr(T_QB1N, d, i), c.ptr(T_QBAU, d, i), c.dstep(), c.pstep(), u1max, maxu2,
                      ddmax, sl, SI, sI, s1, sA);
   double accI = M.mmI[type][si1][sj1] * sI + M.mm1n[type][si1][sj1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
@@ -596,7 +606,7 @@ template <class C>
 RP_HD void inside_splits(const C& c, int d, int i, int slice, int S, double& accM, double& accQ) {
   const int ds = c.dstep(), ps = c.pstep();
   accM = 0.; accQ = 0.;
-  if (c.dbg & 2) return;
+  if (RP_DBG(c) & 2) return;
   // QM2(i,j) = sum_a qm[a][i] * qm1[d-1-a][i+1+a], a = TURN+1 .. d-2-TURN; the split k=i+1+a may not be the nick
   const int cntM = d - 2 * TURN - 2;
   if (cntM > 0) {
@@ -681,7 +691,7 @@ RP_HD void inside_band_A(const Ctx& c, const Shared& sh, int d0, int i0, int C, 
   double m[BAND], q[BAND];
 #pragma unroll
   for (int e = 0; e < BAND; e++) m[e] = q[e] = 0.;
-  if (!(c.dbg & 2)) {
+  if (!(RP_DBG(c) & 2)) {
     const int amax = d0 - 1;                    // largest a any diagonal of the band needs
     const int lim = d0 - TURN - 2;              // term a belongs to diagonal d0+e iff a <= lim + e
     const int askip = c.cp > 0 ? c.cp - 1 - i : -1;  // split k = i+1+a on the nick (M only)
@@ -882,7 +892,7 @@ RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl
   int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
   if (maxpo - 1 < u1max) u1max = maxpo - 1;
   double sI = 0., s1 = 0., sA = 0.;
-  if (!(c.dbg & 1))
+  if (!(RP_DBG(c) & 1))
     interior_rows<-1>(sh, c.ptr(T_OUTI, d, k), c.ptr(T_OUT1N, d, k), c.ptr(T_OUTAU, d, k), c.dstep(), c.pstep(), u1max,
                       maxu2, ddmax, sl, SI, sI, s1, sA);
   double accI = M.mmI[t2][sq1][sp1] * sI + M.mm1n[t2][sq1][sp1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
@@ -906,7 +916,7 @@ template <class C>
 RP_HD void outside_splits(const C& c, int d, int k, bool pairs, int slice, int S, double& accP, double& accL) {
   const int ds = c.dstep(), ps = c.pstep(), n = c.n, l = k + d;
   accP = 0.; accL = 0.;
-  if (c.dbg & 2) return;
+  if (RP_DBG(c) & 2) return;
   // PR(k,l) = sum_b Mc[d+2+b][k] * qm[b][l+1], b = TURN+1 .. n-l-2   [k is the closing 5' end]
   if (l + 2 <= n && ss(c, l, l + 1)) {
     const int cnt = n - l - 2 - TURN;
@@ -990,7 +1000,7 @@ RP_HD void outside_band_A(const Ctx& c, const Shared& sh, int d0, int r0, int C,
   double pr[BAND], ml[BAND];
 #pragma unroll
   for (int e = 0; e < BAND; e++) pr[e] = ml[e] = 0.;
-  if (!(c.dbg & 2)) {
+  if (!(RP_DBG(c) & 2)) {
     {  // PR, row k; t = j - (k+d0+TURN+3), valid for diagonal d0-e iff t >= -e
       const int k = 1 + r;
       const int tmax = n - k - d0 - (TURN + 3);
@@ -1143,7 +1153,7 @@ RP_HD void wide_inside_A(const Ctx& c, const Shared& sh, int d0, int i0, int C, 
   const long es = c.dstep();
   double m[W], q[W];
   for (int e = 0; e < W; e++) m[e] = q[e] = 0.;
-  if (!(c.dbg & 2)) {
+  if (!(RP_DBG(c) & 2)) {
     const int amax = d0 - 1, lim = d0 - TURN - 2;
     const int askip = c.cp > 0 ? c.cp - 1 - i : -1;
     for (int a = slice; a <= amax; a += S) {
@@ -1217,7 +1227,7 @@ RP_HD void wide_outside_A(const Ctx& c, const Shared& sh, int d0, int r0, int C,
   const int r = r0 + cell, n = c.n, ds = c.dstep(), ps = c.pstep();
   double pr[W], ml[W];
   for (int e = 0; e < W; e++) pr[e] = ml[e] = 0.;
-  if (!(c.dbg & 2)) {
+  if (!(RP_DBG(c) & 2)) {
     {  // PR, row k; t = b - (TURN+1) - e: Mc on diagonal d0+TURN+3+t (final iff t >= -(TURN+1)), qm on diagonal TURN+1+t+e
       const int k = 1 + r;
       const int tmax = n - k - d0 - (TURN + 3);
@@ -1356,7 +1366,7 @@ RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
   const int n = c.n;
   if (n < 7) return;   // rows 0..5 of the scratch must exist; shorter sequences have no such loops to speak of (handled below)
   const int nsl = gap_special_slices(n);
-  const int items = (c.dbg & 4) ? 0 : 2 * 3 * nsl * n;
+  const int items = (RP_DBG(c) & 4) ? 0 : 2 * 3 * nsl * n;
   for (int x = tid; x < items; x += T) {
     const int a = x % n + 1;
     int y = x / n;
@@ -1435,7 +1445,7 @@ RP_HD void unstru_gap_specials(C& c, const MT& M, int tid, int T) {
 template <class C>
 RP_HD void unstru_gaps(C& c, const double* gfull, int side, int tid, int T) {
   const int n = c.n, ds = c.dstep(), ps = c.pstep();
-  const int items = (c.dbg & 4) ? 0 : n * (MAXLOOP + 1);
+  const int items = (RP_DBG(c) & 4) ? 0 : n * (MAXLOOP + 1);
   const int tabO[3] = {T_OUTI, T_OUT1N, T_OUTAU};
   const int tabQ[3] = {T_QBI, T_QB1N, T_QBAU};
   for (int x = tid; x < items; x += T) {

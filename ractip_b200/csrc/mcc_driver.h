@@ -42,7 +42,7 @@ RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* d
     if (probs[0].max_w > 0) {
       ex.phase(PH_UN_HAIRPIN, [&](int tid) {
 #ifdef __CUDA_ARCH__
-        long long* prof = get(tid % G).prof;
+        long long* prof = RP_PROF(get(tid % G));
         const long long t0 = (prof && tid == 0) ? clock64() : 0;
 #endif
         unstru_hairpin(get(tid % G), tid / G, nct);
@@ -527,7 +527,7 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     }
     ex.phase(PH_OUTSIDE_A, [&](int tid) {
       if (dfin >= 0) band_outside_B(c, sh, bs, dfin, wide, tid);
-      if (nick && tid < 128 && !(c.dbg & 64)) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
+      if (nick && tid < 128 && !(RP_DBG(c) & 64)) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
       if (dnew >= 0) band_interior_A<-1>(c, bs, dnew, tid, T);
     });
     if (dnew < 0) break;

@@ -69,7 +69,7 @@ __device__ __forceinline__ void wide_inside_A_shfl(const Ctx& c, const Shared& s
     double acc[W], bv[W];
 #pragma unroll
     for (int e = 0; e < W; e++) acc[e] = bv[e] = 0.;
-    if (a_lo <= a_hi && !(c.dbg & 2)) {
+    if (a_lo <= a_hi && !(RP_DBG(c) & 2)) {
       {  // prime the chain: elements e >= 1 of the first step that are final (diagonal < d0) and inside their row
         const double* B = c.ptr(tB, d0 - 1 - a_lo, i + 1 + a_lo);
 #pragma unroll
@@ -145,7 +145,7 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
     for (int e = 0; e < W; e++) acc[e] = bv[e] = 0.;
     const int tmax0 = __shfl_sync(0xffffffffu, tmax, 0);
     const int tfirst = -(TURN + 1);
-    if (tmax0 >= tfirst && !(c.dbg & 2)) {
+    if (tmax0 >= tfirst && !(RP_DBG(c) & 2)) {
       const int per = (tmax0 - tfirst + 1 + S - 1) / S;
       const int t_lo = tfirst + slice * per;
       int t_hi = t_lo + per - 1;
@@ -208,7 +208,7 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
     }
     const int ifar = k0 - 2;
     const int ifar_hi = __shfl_sync(0xffffffffu, ifar, HWW - 1);   // largest among the owning lanes
-    if (!(c.dbg & 2)) {
+    if (!(RP_DBG(c) & 2)) {
 #pragma unroll 1
       for (int i = 1 + slice; i <= ifar_hi; i += NB * S) {
         double A[NB], b0[NB];
