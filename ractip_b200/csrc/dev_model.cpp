@@ -124,6 +124,26 @@ int build_dev_model(const rp_model& m, DevModel* out) {
       }
     }
   }
+  // finished weights of the table-driven small loops, multiplied in the order the kernels used to
+  for (int t = 0; t < 8; t++)
+    for (int t2 = 0; t2 < 8; t2++) {
+      D.spw[SPW_STACK + t * 8 + t2] = D.expstack[t][t2] * D.scale_small[2];
+      D.spw[SPW_BULGE1 + t * 8 + t2] = D.expbulge[1] * D.expstack[t][t2] * D.scale_small[3];
+      for (int a = 0; a < 5; a++)
+        for (int b = 0; b < 5; b++) {
+          D.spw[SPW_INT11 + ((t * 8 + t2) * 5 + a) * 5 + b] = D.int11[t][t2][a][b] * D.scale_small[4];
+          // SPW_23 [type=t][si1=a][sj1=b][t2r=t2][sq1][sp1]
+          for (int q = 0; q < 5; q++)
+            for (int pp = 0; pp < 5; pp++)
+              D.spw[SPW_23 + ((((t * 5 + a) * 5 + b) * 8 + t2) * 5 + q) * 5 + pp] =
+                  D.expinternal[5] * D.expninio[1] * D.mm23[t][a][b] * D.mm23[t2][q][pp] * D.scale_small[7];
+          for (int c = 0; c < 5; c++) {
+            D.spw[SPW_INT21 + (((t * 8 + t2) * 5 + a) * 5 + b) * 5 + c] = D.int21[t][t2][a][b][c] * D.scale_small[5];
+            for (int d = 0; d < 5; d++)
+              D.spw[SPW_INT22 + ((((t * 8 + t2) * 5 + a) * 5 + b) * 5 + c) * 5 + d] = D.int22[t][t2][a][b][c][d] * D.scale_small[6];
+          }
+        }
+    }
   D.i_TermAU = m.TerminalAU37;
   D.i_ninio = m.ninio37;
   D.i_MAX_NINIO = m.MAX_NINIO;

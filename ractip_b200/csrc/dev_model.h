@@ -30,6 +30,18 @@ constexpr int MAXLOOP = RP_MAXLOOP;
 enum { CLS_GENERIC = 0, CLS_1N = 1, CLS_BULGE = 2, CLS_SPECIAL = 3, CLS_NONE = 255 };
 constexpr int GROW_LD = 32;
 
+// Table-driven small loops (the nine shapes that do not factorise: stack, 1-bulge, 1x1, 1x2, 2x1, 2x2, 2x3,
+// 3x2): ONE flat table of finished weights, scale included, so that a look-up is an index computation and
+// a single load (DevModel::spw; index arithmetic in special_loop, mcc_core.h).
+//   SPW_STACK  [type][t2r]                          expstack * scale[2]
+//   SPW_BULGE1 [type][t2r]                          expbulge[1] * expstack * scale[3]
+//   SPW_INT11  [type][t2r][si1][sj1]                int11 * scale[4]
+//   SPW_INT21  [type][t2r][a][b][c]                 int21 * scale[5]   (index order of ViennaRNA's int21)
+//   SPW_INT22  [type][t2r][si1][sp1][sq1][sj1]      int22 * scale[6]
+//   SPW_23     [type][si1][sj1][t2r][sq1][sp1]      expinternal[5]*expninio[1]*mm23*mm23*scale[7]
+constexpr int SPW_STACK = 0, SPW_BULGE1 = 64, SPW_INT11 = 128, SPW_INT21 = SPW_INT11 + 1600,
+              SPW_INT22 = SPW_INT21 + 8000, SPW_23 = SPW_INT22 + 40000, SPW_SIZE = SPW_23 + 40000;
+
 struct DevModel {
   double pf_scale, scale1, mlb1;  // scale1 = 1/pf_scale, mlb1 = expMLbase*scale1
   double kT, lxc;
@@ -42,6 +54,7 @@ struct DevModel {
   double int11[8][8][5][5];
   double int21[8][8][5][5][5];
   double int22[8][8][5][5][5][5];
+  double spw[SPW_SIZE];   // finished weights of the table-driven small loops (see above)
   // special hairpins: k-mers as base-8 codes of the 1..4 encoding
   int n_tetra, n_tri, n_hex;
   int tetra_code[200], tri_code[40], hex_code[200];

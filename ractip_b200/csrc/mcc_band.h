@@ -48,17 +48,14 @@ constexpr int NSLICE = 16;       // row pairs (q, 30-q)
 struct SmallModel {
   double scale1, mlb1, expMLclosing, expMLintern, expTermAU, inv_expTermAU;
   double scale_small[10];
-  double expbulge[2], expinternal[6], expninio[2];
-  double expstack[8][8];
-  double mmI[8][5][5], mmH[8][5][5], mmM[8][5][5], mmExt[8][5][5], mm1n[8][5][5], mm23[8][5][5];
+  double mmI[8][5][5], mmH[8][5][5], mmM[8][5][5], mmExt[8][5][5], mm1n[8][5][5];
   double dangle5[8][5], dangle3[8][5];
-  const double (*int11)[8][5][5];         // the large tables stay in HBM/L2
-  const double (*int21)[8][5][5][5];
-  const double (*int22)[8][5][5][5][5];
+  const double* spw;                      // finished weights of the table-driven small loops: stay in HBM/L2
   int special_hp, pad;
 };
 constexpr int SM_DOUBLES = (int)((sizeof(SmallModel) + 7) / 8);
 
+struct DiagDesc;
 struct BandShared {
   int LDB, LD8;   // ring row stride in doubles (multiple of 8) and sub-row length LDB/8
   int NGP;        // stride of the group-transposed arrays (>= max number of groups of a diagonal)
@@ -69,8 +66,10 @@ struct BandShared {
   double *gA, *g1;         // [32] bulge weight g(0,s), 1xn weight g(1,s-1)
   double* sIv;             // [n+2] finished interior sums of the diagonal that is being completed (by cell)
   SmallModel* sm;
+  DiagDesc* desc;          // [NDESC] per-diagonal descriptors
 };
 constexpr int GPACK = (MAXLOOP + 1) * (MAXLOOP + 2) / 2;   // 496
+constexpr int DESC_DOUBLES = 4 * 6;                        // NDESC descriptors of 12 ints (DiagDesc, below)
 
 RP_HD int band_ldb(int n) { return ((n + 1 + 7) / 8) * 8; }
 RP_HD int band_ngp(int n) { return (n + 7) / 8 + 3; }
@@ -88,7 +87,7 @@ RP_HD size_t band_part_doubles(int n, int T) {
 }
 RP_HD size_t band_shared_doubles(int n, int T) {
   return band_part_doubles(n, T) + 128 /*red*/ + (size_t)3 * BSLOTS * band_ldb(n) + (size_t)3 * BR * band_ngp(n) +
-         GPACK + 64 + (size_t)(n + 2) + SM_DOUBLES + (size_t)(n + 2 + 7) / 8 + 2;
+         GPACK + 64 + (size_t)(n + 2) + SM_DOUBLES + DESC_DOUBLES + (size_t)(n + 2 + 7) / 8 + 2;
 }
 RP_HD size_t band_shared_bytes(int n, int T) { return band_shared_doubles(n, T) * sizeof(double); }
 
@@ -109,6 +108,7 @@ RP_HD void carve_band(Shared& sh, BandShared& bs, void* base, int n, int T) {
   bs.g1 = p; p += 32;
   bs.sIv = p; p += n + 2;
   bs.sm = reinterpret_cast<SmallModel*>(p); p += SM_DOUBLES;
+  bs.desc = reinterpret_cast<DiagDesc*>(p); p += DESC_DOUBLES;
   sh.S = reinterpret_cast<uint8_t*>(p);
   sh.grow = nullptr; sh.ghead_b = nullptr; sh.ghead_1 = nullptr;  // the factorised-row tables of the general kernel are not used
 }
@@ -128,9 +128,7 @@ RP_HD void load_band_weights(const DevModel& M, const BandShared& bs, int tid, i
     S.scale1 = M.scale1; S.mlb1 = M.mlb1; S.expMLclosing = M.expMLclosing; S.expMLintern = M.expMLintern;
     S.expTermAU = M.expTermAU; S.inv_expTermAU = 1.0 / M.expTermAU;
     for (int k = 0; k < 10; k++) S.scale_small[k] = M.scale_small[k];
-    for (int k = 0; k < 2; k++) { S.expbulge[k] = M.expbulge[k]; S.expninio[k] = M.expninio[k]; }
-    for (int k = 0; k < 6; k++) S.expinternal[k] = M.expinternal[k];
-    S.int11 = M.int11; S.int21 = M.int21; S.int22 = M.int22;
+    S.spw = M.spw;
     S.special_hp = M.special_hp; S.pad = 0;
   }
   for (int x = tid; x < 200; x += T) {
@@ -139,8 +137,6 @@ RP_HD void load_band_weights(const DevModel& M, const BandShared& bs, int tid, i
     (&S.mmM[0][0][0])[x] = (&M.mmM[0][0][0])[x];
     (&S.mmExt[0][0][0])[x] = (&M.mmExt[0][0][0])[x];
     (&S.mm1n[0][0][0])[x] = (&M.mm1n[0][0][0])[x];
-    (&S.mm23[0][0][0])[x] = (&M.mm23[0][0][0])[x];
-    if (x < 64) (&S.expstack[0][0])[x] = (&M.expstack[0][0])[x];
     if (x < 40) {
       (&S.dangle5[0][0])[x] = (&M.dangle5[0][0])[x];
       (&S.dangle3[0][0])[x] = (&M.dangle3[0][0])[x];
@@ -183,6 +179,31 @@ RP_HD int seg_slot(const Segs& s, const BandShared& bs, int i) {
   const int k = (i >= s.b[1]) + (i >= s.b[2]);
   const int o = i - s.b[k];
   return (o & (BR - 1)) * bs.NGP + s.G[k] + (o >> 3);
+}
+
+// Everything the phases of one diagonal need to know about its layout, worked out ONCE (by one thread, a
+// phase ahead) and kept in shared memory: the strand segments, the item schedule and the thread roles.
+// (Every thread used to redo this arithmetic in every phase: ~6 % of all executed instructions.)
+struct DiagDesc {
+  Segs sg;
+  int gsh, NB, nitems, t0;
+};
+constexpr int NDESC = 4;   // ring of descriptors (diagonal d at d & 3): a descriptor lives for three phases
+static_assert(sizeof(DiagDesc) * NDESC <= DESC_DOUBLES * sizeof(double), "descriptor ring");
+RP_HD void band_make_desc(DiagDesc& D, int n, int cp, int d, int T) {
+  D.sg = make_segs(n, cp, d);
+  const int NG = D.sg.G[3], cells = n - d;
+  // an item block is GB lanes = GB consecutive groups: a half-warp, or a quarter-warp when the whole
+  // diagonal fits in 8 groups (4 slices per warp: half the instructions on the short diagonals)
+  D.gsh = NG <= 8 ? 3 : 4;
+  const int GB = 1 << D.gsh;
+  D.NB = (NG + GB - 1) >> D.gsh;
+  D.nitems = NSLICE * D.NB;
+  // Thread roles of the long phase: the first `cells` threads complete the previous diagonal, the
+  // last `cells` do the small loops; when they fit, the items go to the threads in between, so that
+  // no thread has two jobs.
+  const int Cw = (cells + 1 + 31) & ~31;   // (the previous diagonal has one more cell)
+  D.t0 = (D.nitems * GB + 2 * Cw <= T) ? Cw : 0;
 }
 
 // Global load that is issued WHERE IT IS WRITTEN: at the register cap the compiler otherwise sinks
@@ -240,6 +261,7 @@ RP_HD void interior_item(const BandShared& bs, int n, int cp, int d, const Segs&
   const double* f1 = bs.c1 + g;
   const double* fA = bs.cA + g;
   const int NGP = bs.NGP, LD8 = bs.LD8;
+#pragma unroll 1
   for (int h = 0; h < 2; h++) {
     const int s = h == 0 ? q : MAXLOOP - q;
     if (h == 1 && s == q) break;
@@ -267,26 +289,20 @@ RP_HD void interior_item(const BandShared& bs, int n, int cp, int d, const Segs&
     const RingPtr r1 = ring_ptr(bs.T1 + ro + (P0 >> 3));
     const RingPtr rA = ring_ptr(bs.TA + ro + (P0 >> 3));
 #define RP_IX(e) (((e) & 7) * LD8 + ((e) >> 3))
-    {  // bulge ends (0,s),(s,0): elements r and r+s; 1xn ends (1,s-1),(s-1,1): elements r+1 and r+s-1
-      int ixL[BR + 1], ixR[BR + 1];
-#pragma unroll
-      for (int j = 0; j <= BR; j++) {
-        ixL[j] = RP_IX(b + j);           // element j
-        ixR[j] = RP_IX(b + s - 1 + j);   // element s-1+j
-      }
-      const double wa = bs.gA[s], w1 = bs.g1[s];
-      const unsigned xl = (unsigned)(0 - clo), xr = (unsigned)(s - 1 - clo);  // (element) - clo of ixL[0], ixR[0]
+    // bulge ends (0,s),(s,0): elements r and r+s of the bulge-class row; 1xn ends (1,s-1),(s-1,1): elements r+1
+    // and r+s-1 of the 1xn-class row.  ONE rolled loop over the two tables (code size: the per-diagonal loops
+    // have to fit the 32 KB instruction cache; the arithmetic is the same either way).
+#pragma unroll 1
+    for (int tb = 0; tb < (s >= 4 ? 2 : 1); tb++) {
+      const RingPtr rp = tb ? r1 : rA;
+      const double* f = tb ? f1 : fA;
+      const double w = tb ? bs.g1[s] : bs.gA[s];
+      const int eL = tb, eR = s - tb;          // first element of the left / right run
+      const unsigned xl = (unsigned)(eL - clo), xr = (unsigned)(eR - clo);
 #pragma unroll
       for (int r = 0; r < BR; r++) {
-        const double x0 = ring_ld(rA, ixL[r], xl + r, span), x1 = ring_ld(rA, ixR[r + 1], xr + r + 1, span);
-        tot[r] += fA[r * NGP] * (wa * (x0 + x1));
-      }
-      if (s >= 4) {
-#pragma unroll
-        for (int r = 0; r < BR; r++) {
-          const double x0 = ring_ld(r1, ixL[r + 1], xl + r + 1, span), x1 = ring_ld(r1, ixR[r], xr + r, span);
-          tot[r] += f1[r * NGP] * (w1 * (x0 + x1));
-        }
+        const double x0 = ring_ld(rp, RP_IX(b + eL + r), xl + r, span), x1 = ring_ld(rp, RP_IX(b + eR + r), xr + r, span);
+        tot[r] += f[r * NGP] * (w * (x0 + x1));
       }
     }
     if (s >= 6) {  // generic taps t = 2 .. s-2: tap-major walk with a sliding register window
@@ -410,18 +426,10 @@ RP_HD double outside_specials_band(const C& c, const BandShared& bs, int d, int 
 template <int SIGN, class C>
 RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int T) {
   const int n = c.n, cells = n - d;
-  const Segs sg = make_segs(n, c.cp, d);
-  const int NG = sg.G[3];
-  // an item block is GB lanes = GB consecutive groups: a half-warp, or a quarter-warp when the whole
-  // diagonal fits in 8 groups (4 slices per warp: half the instructions on the short diagonals)
-  const int gsh = NG <= 8 ? 3 : 4, GB = 1 << gsh;   // (shifts: runtime integer divisions cost ~25 dependent instructions each)
-  const int NB = (NG + GB - 1) >> gsh;
-  const int nitems = NSLICE * NB;
-  // Thread roles of the long phase: the first `cells` threads complete the previous diagonal, the
-  // last `cells` do the small loops below; when they fit, the items go to the threads in between,
-  // so that no thread has two jobs.
-  const int Cw = (cells + 1 + 31) & ~31;   // (the previous diagonal has one more cell)
-  const int t0 = (nitems * GB + 2 * Cw <= T) ? Cw : 0;
+  // layout, item schedule and thread roles of this diagonal: worked out once, a phase ahead (band_make_desc)
+  const DiagDesc& D = bs.desc[d & (NDESC - 1)];
+  const Segs& sg = D.sg;
+  const int NG = sg.G[3], gsh = D.gsh, GB = 1 << gsh, NB = D.NB, nitems = D.nitems, t0 = D.t0;
   const int smax = SIGN > 0 ? d - 6 : n - 3 - d;
   // small loops first: their table look-ups are in flight while the row items run
   for (int x = T - 1 - tid; x < cells; x += T) {
@@ -482,7 +490,7 @@ RP_HD void band_cfac_inside(const C& c, const BandShared& bs, int d, int tid, in
   const SmallModel& M = *bs.sm;
   const int cells = c.n - d;
   if (cells <= 0) return;
-  const Segs sg = make_segs(c.n, c.cp, d);
+  const Segs& sg = bs.desc[d & (NDESC - 1)].sg;
   for (int x = tid; x < BR * sg.G[3]; x += T) {  // every slot of every group, cells past a segment end get 0
     const int g = x / BR, r = x % BR;
     const int k = (g >= sg.G[1]) + (g >= sg.G[2]);
@@ -508,7 +516,7 @@ RP_HD void band_cfac_outside(const C& c, const BandShared& bs, int d, int tid, i
   const SmallModel& M = *bs.sm;
   const int n = c.n, cells = n - d;
   if (cells <= 0 || d <= TURN) return;
-  const Segs sg = make_segs(n, c.cp, d);
+  const Segs& sg = bs.desc[d & (NDESC - 1)].sg;
   for (int x = tid; x < BR * sg.G[3]; x += T) {
     const int g = x / BR, r = x % BR;
     const int kk = (g >= sg.G[1]) + (g >= sg.G[2]);
@@ -725,7 +733,7 @@ RP_HD void band_collect(const C& c, const BandShared& bs, int dsum, int dnext, i
 #pragma unroll 1
   for (int rep = 0; rep < reps; rep++) {
     if (dsum >= 0) {
-      const Segs sg = make_segs(c.n, c.cp, dsum);
+      const Segs& sg = bs.desc[dsum & (NDESC - 1)].sg;
       const int cells = c.n - dsum;
       for (int x = tid; x < cells; x += T) bs.sIv[1 + x] = band_interior_sum<SIGN>(c, bs, dsum, sg, 1 + x);
     }

@@ -260,16 +260,20 @@ RP_HD int special_index(int u1, int u2) {
 // (si1,sj1), inner pair of reversed type t2r with neighbours (sp1,sq1)
 template <class MT>
 RP_HD double special_loop(const MT& M, int s, int type, int t2r, int si1, int sj1, int sp1, int sq1) {
+  // one look-up in the table of finished weights (DevModel::spw, dev_model.h); with a compile-time s the
+  // switch folds away and the index is a handful of integer multiply-adds
+  int ix;
   switch (s) {
-    case 0: return M.expstack[type][t2r] * M.scale_small[2];
+    case 0: ix = SPW_STACK + type * 8 + t2r; break;
     case 1:
-    case 2: return M.expbulge[1] * M.expstack[type][t2r] * M.scale_small[3];
-    case 3: return M.int11[type][t2r][si1][sj1] * M.scale_small[4];
-    case 4: return M.int21[type][t2r][si1][sq1][sj1] * M.scale_small[5];   // u1=1,u2=2
-    case 5: return M.int21[t2r][type][sq1][si1][sp1] * M.scale_small[5];   // u1=2,u2=1
-    case 6: return M.int22[type][t2r][si1][sp1][sq1][sj1] * M.scale_small[6];
-    default: return M.expinternal[5] * M.expninio[1] * M.mm23[type][si1][sj1] * M.mm23[t2r][sq1][sp1] * M.scale_small[7];
+    case 2: ix = SPW_BULGE1 + type * 8 + t2r; break;
+    case 3: ix = SPW_INT11 + ((type * 8 + t2r) * 5 + si1) * 5 + sj1; break;
+    case 4: ix = SPW_INT21 + (((type * 8 + t2r) * 5 + si1) * 5 + sq1) * 5 + sj1; break;   // u1=1,u2=2
+    case 5: ix = SPW_INT21 + (((t2r * 8 + type) * 5 + sq1) * 5 + si1) * 5 + sp1; break;   // u1=2,u2=1
+    case 6: ix = SPW_INT22 + ((((type * 8 + t2r) * 5 + si1) * 5 + sp1) * 5 + sq1) * 5 + sj1; break;
+    default: ix = SPW_23 + ((((type * 5 + si1) * 5 + sj1) * 8 + t2r) * 5 + sq1) * 5 + sp1; break;
   }
+  return M.spw[ix];
 }
 
 // hairpin weight of pair (i,j), including scale[u+2]

@@ -440,8 +440,13 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     });
     c.S = sh.S;
   }
-  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, tid, T); });
+  ex.phase(PH_PROLOGUE2, [&](int tid) {
+    prologue2(c, tid, T);
+    if (tid == T - 1 && TURN + 1 <= n - 1) band_make_desc(bs.desc[(TURN + 1) & (NDESC - 1)], n, c.cp, TURN + 1, T);
+  });
 
+  // Per-diagonal descriptors (strand segments, item schedule, thread roles: DiagDesc) are worked out by ONE
+  // thread during the long phase of the step before their first use.
   // Schedule: the completion ("finish") of diagonal d runs one step late, in the same long phase
   // as the interior items of the next diagonal, so that its HBM/L2 round trips and the nick sums
   // hide behind the items' arithmetic.  Per diagonal: one long phase, then one quick phase that
@@ -455,6 +460,7 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     ex.phase(PH_INSIDE_A, [&](int tid) {
       if (dfin >= 0) band_inside_B(c, sh, bs, dfin, wide, tid);
       if (dnew >= 0) band_interior_A<1>(c, bs, dnew, tid, T);
+      if (tid == T - 1 && d + 1 <= n - 1) band_make_desc(bs.desc[(d + 1) & (NDESC - 1)], n, c.cp, d + 1, T);
     });
     if (dnew < 0) break;
     ex.phase(PH_CFAC, [&](int tid) { band_collect<1>(c, bs, dnew, d + 1 <= n - 1 ? d + 1 : -1, tid, T); });
@@ -495,6 +501,8 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
   // Nick sums of diagonal x (outside_nick1/2, they need out of every diagonal > x) ride along one
   // step late as well: first half in the long phase of step x-1, second half in the quick phase
   // after it; their results are first read when diagonal x-1 is completed, in step x-2.
+  if (n - 1 >= TURN + 1)
+    ex.phase(PH_CFAC, [&](int tid) { if (tid == 0) band_make_desc(bs.desc[(n - 1) & (NDESC - 1)], n, c.cp, n - 1, T); });
   ex.phase(PH_CFAC, [&](int tid) { band_collect<-1>(c, bs, -1, n - 1 >= TURN + 1 ? n - 1 : -1, tid, T); });
   for (int d = n - 1; d >= TURN; d--) {
     const int dfin = d + 1 <= n - 1 ? d + 1 : -1;
@@ -529,6 +537,7 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
       if (dfin >= 0) band_outside_B(c, sh, bs, dfin, wide, tid);
       if (nick && tid < 128 && !(RP_DBG(c) & 64)) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
       if (dnew >= 0) band_interior_A<-1>(c, bs, dnew, tid, T);
+      if (tid == T - 1 && d - 1 >= TURN + 1) band_make_desc(bs.desc[(d - 1) & (NDESC - 1)], n, c.cp, d - 1, T);
     });
     if (dnew < 0) break;
     ex.phase(PH_CFAC, [&](int tid) {
