@@ -156,17 +156,22 @@ int rp_dense_plan(const rp_pair* pairs, int n_pairs, const rp_opts* opts,
 
 /* Sparse (thresholded) records in the reference's variable-creation order
  * (src/ractip.cpp:557-567 x: j ascending then i descending; :598-609 z: i
- * ascending then j ascending), 0-based like the consumer's loops. */
+ * ascending then j ascending; :619-628 v and :639-648 w: start i ascending,
+ * then window-length index j = min_w-1 .. max_w-1 ascending, the region being
+ * bases i..i+j), 0-based like the consumer's loops.  v/w are empty when the
+ * reference would not create them (min_w <= 1 or max_w < min_w, :526). */
 typedef struct rp_rec { int32_t i, j; float p; } rp_rec;
 
 typedef struct rp_sparse_layout {
   size_t x, y, z;            /* offsets into the rp_rec buffer               */
   size_t cap_x, cap_y, cap_z;/* capacities (records)                         */
-  size_t up1, up2;           /* offsets (floats) into the float buffer       */
-  size_t n_up1, n_up2;
+  size_t up1, up2;           /* offsets (floats) into the OPTIONAL float     */
+  size_t n_up1, n_up2;       /* buffer of the dense window tables            */
+  size_t v, w;               /* offsets into the rp_rec buffer               */
+  size_t cap_v, cap_w;
 } rp_sparse_layout;
 
-typedef struct rp_sparse_counts { int32_t n_x, n_y, n_z, overflow; } rp_sparse_counts;
+typedef struct rp_sparse_counts { int32_t n_x, n_y, n_z, overflow, n_v, n_w; } rp_sparse_counts;
 
 int rp_sparse_plan(const rp_pair* pairs, int n_pairs, const rp_opts* opts,
                    rp_sparse_layout* layout, size_t* total_recs, size_t* total_floats);
@@ -198,6 +203,8 @@ void rp_host_free(void* p);
 int rp_run_dense(rp_ctx* ctx, const rp_pair* pairs, int n_pairs,
                  const rp_opts* opts, float* out, size_t out_floats);
 
+/* `ups` (the dense window tables next to the lists) may be NULL: the v/w lists
+ * carry every up[i][j] the integer programme reads (src/ractip.cpp:621-627). */
 int rp_run_sparse(rp_ctx* ctx, const rp_pair* pairs, int n_pairs,
                   const rp_opts* opts, rp_rec* recs, size_t n_recs,
                   float* ups, size_t n_floats, rp_sparse_counts* counts);

@@ -9,5 +9,9 @@ without the built library or without a GPU raises.
 from .stage import (DeviceBatch, PairProbabilities, PairRecords, ProbabilityStage, RpError,
                     bp_offsets, default_model, default_opts, zscore_shuffles)
 
-__all__ = ["DeviceBatch", "PairProbabilities", "PairRecords", "ProbabilityStage", "RpError",
+from .ip import (IPModel, JointPrediction, default_ip_opts, energy_of_duplex, energy_of_structure,  # noqa: E402
+                 solve_joint, solve_ss, zscore_statistic)
+
+__all__ = ["IPModel", "JointPrediction", "default_ip_opts", "energy_of_duplex", "energy_of_structure",
+           "solve_joint", "solve_ss", "zscore_statistic", "DeviceBatch", "PairProbabilities", "PairRecords", "ProbabilityStage", "RpError",
            "bp_offsets", "default_model", "default_opts", "zscore_shuffles"]

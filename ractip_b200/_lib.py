@@ -73,11 +73,19 @@ class RpRec(C.Structure):
 
 class RpSparseLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("x", "y", "z", "cap_x", "cap_y", "cap_z", "up1", "up2", "n_up1", "n_up2")]
+                ("x", "y", "z", "cap_x", "cap_y", "cap_z", "up1", "up2", "n_up1", "n_up2", "v", "w", "cap_v", "cap_w")]
 
 
 class RpSparseCounts(C.Structure):
-    _fields_ = [("n_x", C.c_int32), ("n_y", C.c_int32), ("n_z", C.c_int32), ("overflow", C.c_int32)]
+    _fields_ = [("n_x", C.c_int32), ("n_y", C.c_int32), ("n_z", C.c_int32), ("overflow", C.c_int32),
+                ("n_v", C.c_int32), ("n_w", C.c_int32)]
+
+
+class RpIpOpts(C.Structure):
+    """rp_ip_opts (include/ractip_ip.h): the RactIP members that shape the integer programme."""
+    _fields_ = [("alpha", C.c_float), ("beta", C.c_float), ("th_ss", C.c_float), ("th_hy", C.c_float),
+                ("th_ac", C.c_float), ("max_w", C.c_int), ("min_w", C.c_int), ("acc_max", C.c_int),
+                ("acc_max_ss", C.c_int), ("acc_num", C.c_int), ("in_pk", C.c_int), ("stacking", C.c_int)]
 
 
 class RpTiming(C.Structure):
@@ -94,6 +102,9 @@ EXPORTS = [
     "rp_batch_fetch_dense", "rp_batch_fetch_sparse", "rp_batch_sparse_device", "rp_batch_fetch_logz",
     "rp_batch_destroy", "rp_last_timing", "rp_measure_peaks", "rp_zscore_shuffles",
     "rp_alg_flops_mcc", "rp_version", "rp_kernel_plan",
+    # include/ractip_ip.h (host-side consumer: integer programme, energy evaluation)
+    "rp_ip_opts_default", "rp_ip_build", "rp_ip_build_sparse", "rp_ip_build_ss", "rp_ip_dims", "rp_ip_export",
+    "rp_ip_decode", "rp_ip_free", "rp_energy_of_structure", "rp_energy_of_duplex",
 ]
 
 _lib = None
@@ -141,6 +152,16 @@ def load() -> C.CDLL:
         "rp_alg_flops_mcc": (C.c_double, [i]),
         "rp_version": (C.c_char_p, []),
         "rp_kernel_plan": (i, [i, sz, P(sz)]),
+        "rp_ip_opts_default": (None, [P(RpIpOpts)]),
+        "rp_ip_build": (i, [P(RpIpOpts), i, i, vp, vp, vp, vp, vp, P(vp)]),
+        "rp_ip_build_sparse": (i, [P(RpIpOpts), i, i, vp, i, vp, i, vp, i, vp, i, vp, i, P(vp)]),
+        "rp_ip_build_ss": (i, [P(RpIpOpts), i, vp, vp, P(vp)]),
+        "rp_ip_dims": (i, [vp, P(i), P(i), P(i)]),
+        "rp_ip_export": (i, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "rp_ip_decode": (i, [vp, vp, C.c_char_p, C.c_char_p, vp, vp]),
+        "rp_ip_free": (None, [vp]),
+        "rp_energy_of_structure": (i, [P(RpModel), C.c_char_p, C.c_char_p, i, i, P(C.c_float)]),
+        "rp_energy_of_duplex": (i, [P(RpModel), C.c_char_p, i, C.c_char_p, i, C.c_char_p, C.c_char_p, P(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol

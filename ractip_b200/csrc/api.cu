@@ -291,9 +291,17 @@ int rp_sparse_plan(const rp_pair* pairs, int n_pairs, const rp_opts* opts, rp_sp
     l.cap_z = !(opts->th_hy > 0.f) ? all
                                    : std::min(all, (size_t)std::min(pairs[p].n1, pairs[p].n2) *
                                                        ((size_t)std::floor(1.0 / opts->th_hy) + 1));
+    // accessible regions: one variable per (start, length) with length in min_w..max_w, when the
+    // reference creates them at all (enable_accessibility, src/ractip.cpp:526)
+    const bool acc = opts->min_w > 1 && opts->max_w >= opts->min_w;
+    const size_t nlen = acc ? (size_t)(opts->max_w - opts->min_w + 1) : 0;
+    l.cap_v = (size_t)pairs[p].n1 * nlen;
+    l.cap_w = (size_t)pairs[p].n2 * nlen;
     l.x = roff; roff += l.cap_x;
     l.y = roff; roff += l.cap_y;
     l.z = roff; roff += l.cap_z;
+    l.v = roff; roff += l.cap_v;
+    l.w = roff; roff += l.cap_w;
     l.n_up1 = (size_t)pairs[p].n1 * w; l.n_up2 = (size_t)pairs[p].n2 * w;
     l.up1 = foff; foff += l.n_up1;
     l.up2 = foff; foff += l.n_up2;
@@ -851,6 +859,8 @@ int sparse_prepare(rp_batch* b) {
     q.up1_src = (long long)L.up1; q.up2_src = (long long)L.up2;
     q.up1_dst = (long long)S.up1; q.up2_dst = (long long)S.up2;
     q.n_up1 = (int)S.n_up1; q.n_up2 = (int)S.n_up2;
+    q.v = (long long)S.v; q.w = (long long)S.w;
+    q.cap_v = (int)S.cap_v; q.cap_w = (int)S.cap_w;
   }
   CU(pool_alloc(ctx, &b->d_spairs, np * sizeof(rp::SparsePair)));
   CU(cudaMemcpy(b->d_spairs, sp.data(), np * sizeof(rp::SparsePair), cudaMemcpyHostToDevice));
@@ -861,19 +871,20 @@ int sparse_launch(rp_batch* b, rp_rec* d_recs, float* d_ups, rp_sparse_counts* d
   rp_ctx* ctx = b->ctx;
   rp::SparseDev s;
   s.pairs = b->d_spairs; s.dense = b->d_dense; s.recs = d_recs; s.ups = d_ups; s.counts = d_counts;
-  s.th_ss = b->opts.th_ss; s.th_hy = b->opts.th_hy;
+  s.th_ss = b->opts.th_ss; s.th_hy = b->opts.th_hy; s.th_ac = b->opts.th_ac;
+  s.min_w = b->opts.min_w; s.max_w = b->opts.max_w;
   CU(cudaMemsetAsync(d_counts, 0, b->n_pairs * sizeof(rp_sparse_counts), ctx->stream));
-  CU(rp::launch_sparse(s, b->n_pairs, ctx->stream));
-  ctx->timing.kernel_launches += 2;
+  CU(rp::launch_sparse(s, b->n_pairs, d_ups != nullptr, ctx->stream));
+  ctx->timing.kernel_launches += d_ups ? 2 : 1;
   return RP_OK;
 }
 }  // namespace
 
 extern "C" int rp_batch_sparse_device(rp_batch* b, void* recs_dev, size_t n_recs, void* ups_dev, size_t n_floats,
                                       void* counts_dev) {
-  if (!b || !recs_dev || !counts_dev || (!ups_dev && b->total_upf)) return RP_ERR_ARG;
+  if (!b || !recs_dev || !counts_dev) return RP_ERR_ARG;
   rp_ctx* ctx = b->ctx;
-  if (n_recs < b->total_recs || n_floats < b->total_upf)
+  if (n_recs < b->total_recs || (ups_dev && n_floats < b->total_upf))
     return fail(ctx, RP_ERR_CAPACITY, "rp_batch_sparse_device: buffer too small");
   CU(cudaSetDevice(ctx->device));
   if (b->n_pairs == 0) return RP_OK;
@@ -885,9 +896,9 @@ extern "C" int rp_batch_sparse_device(rp_batch* b, void* recs_dev, size_t n_recs
 
 extern "C" int rp_batch_fetch_sparse(rp_batch* b, rp_rec* recs, size_t n_recs, float* ups, size_t n_floats,
                                      rp_sparse_counts* counts) {
-  if (!b || !recs || !counts || (!ups && b->total_upf)) return RP_ERR_ARG;
+  if (!b || !recs || !counts) return RP_ERR_ARG;
   rp_ctx* ctx = b->ctx;
-  if (n_recs < b->total_recs || n_floats < b->total_upf)
+  if (n_recs < b->total_recs || (ups && n_floats < b->total_upf))
     return fail(ctx, RP_ERR_CAPACITY, "rp_batch_fetch_sparse: buffer too small");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -900,11 +911,11 @@ extern "C" int rp_batch_fetch_sparse(rp_batch* b, rp_rec* recs, size_t n_recs, f
     CU(pool_alloc(ctx, &b->d_ups, std::max<size_t>(1, b->total_upf) * sizeof(float)));
     CU(pool_alloc(ctx, &b->d_counts, np * sizeof(rp_sparse_counts)));
   }
-  rc = sparse_launch(b, b->d_recs, b->d_ups, b->d_counts);
+  rc = sparse_launch(b, b->d_recs, ups ? b->d_ups : nullptr, b->d_counts);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[2], st));
   if (b->total_recs) CU(cudaMemcpyAsync(recs, b->d_recs, b->total_recs * sizeof(rp_rec), cudaMemcpyDeviceToHost, st));
-  if (b->total_upf) CU(cudaMemcpyAsync(ups, b->d_ups, b->total_upf * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (ups && b->total_upf) CU(cudaMemcpyAsync(ups, b->d_ups, b->total_upf * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(counts, b->d_counts, np * sizeof(rp_sparse_counts), cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(ctx->ev[3], st));
   CU(cudaStreamSynchronize(st));

@@ -184,6 +184,13 @@ int build_dev_model(const rp_model& m, DevModel* out) {
       else if (u2 == 0) D.ghead_b[u1] = g;  // rows >= 2: bulge (u1,0)
       else D.ghead_1[u1] = g;               // rows >= 3: 1xn (u1,1)
     }
+  for (int sdiag = 0; sdiag <= MAXLOOP; sdiag++)
+    for (int t = 0; t <= sdiag; t++)
+      D.gpack[sdiag * (sdiag + 1) / 2 + t] = D.gcls[t][sdiag - t] == CLS_GENERIC ? D.gfull[t][sdiag - t] : 0.;
+  for (int sdiag = 0; sdiag < 32; sdiag++) {
+    D.gA[sdiag] = (sdiag >= 2 && sdiag <= MAXLOOP) ? D.gfull[0][sdiag] : 0.;
+    D.g1[sdiag] = (sdiag >= 4 && sdiag <= MAXLOOP) ? D.gfull[1][sdiag - 1] : 0.;
+  }
   return RP_OK;
 }
 

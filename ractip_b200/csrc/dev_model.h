@@ -55,6 +55,11 @@ struct DevModel {
   double int21[8][8][5][5][5];
   double int22[8][8][5][5][5][5];
   double spw[SPW_SIZE];   // finished weights of the table-driven small loops (see above)
+  // Band kernel's view of the factorised weights, ready to be copied into shared memory:
+  //   gpack[s*(s+1)/2 + t] = g(t, s-t) where (t, s-t) is GENERIC, else 0;  gA[s] = g(0,s) (bulge, s >= 2);
+  //   g1[s] = g(1,s-1) (1xn, s >= 4)
+  double gpack[(MAXLOOP + 1) * (MAXLOOP + 2) / 2 + 8];
+  double gA[32], g1[32];
   // special hairpins: k-mers as base-8 codes of the 1..4 encoding
   int n_tetra, n_tri, n_hex;
   int tetra_code[200], tri_code[40], hex_code[200];

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) duplex_kernel(BatchDev b) {
 // (src/ractip.cpp:557-567 for x/y: j ascending, i descending; :598-609 for z:
 // i ascending, j ascending).  One warp per list: ballot + popcount keeps order.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(96) sparse_kernel(SparseDev s) {
+__global__ void __launch_bounds__(160) sparse_kernel(SparseDev s) {
   const int pair = blockIdx.x;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const SparsePair sp = s.pairs[pair];
@@ -381,6 +381,32 @@ __global__ void __launch_bounds__(96) sparse_kernel(SparseDev s) {
       }
     }
     if (count > cap) overflow = 1;
+  } else if (warp >= 3) {
+    // accessible regions (src/ractip.cpp:619-628 v, :639-648 w): start i ascending, length index j ascending
+    const int L = warp == 3 ? sp.n1 : sp.n2;
+    const float* up = s.dense + (warp == 3 ? sp.up1_src : sp.up2_src);
+    rp_rec* out = s.recs + (warp == 3 ? sp.v : sp.w);
+    const int cap = warp == 3 ? sp.cap_v : sp.cap_w;
+    const int j0 = s.min_w - 1, nj = cap > 0 ? s.max_w - j0 : 0;   // cap == 0: accessibility is off, no variables
+    const int total = nj > 0 ? L * nj : 0;
+    for (int x0 = 0; x0 < total; x0 += 32) {
+      const int x = x0 + lane;
+      float p = 0.f;
+      bool hit = false;
+      int i = 0, j = 0;
+      if (x < total) {
+        i = x / nj; j = j0 + x % nj;
+        p = up[(size_t)i * s.max_w + j];
+        hit = p > s.th_ac;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = count + __popc(m & ((1u << lane) - 1));
+        if (pos < cap) { out[pos].i = i; out[pos].j = j; out[pos].p = p; }
+      }
+      count += __popc(m);
+    }
+    if (count > cap) overflow = 1;
   } else {
     const float* hp = s.dense + sp.hp;
     rp_rec* out = s.recs + sp.z;
@@ -405,8 +431,8 @@ __global__ void __launch_bounds__(96) sparse_kernel(SparseDev s) {
     if (count > sp.cap_z) overflow = 1;
   }
   if (lane == 0) {
-    int* cnt = reinterpret_cast<int*>(&s.counts[pair]);
-    cnt[warp] = count;
+    int* cnt = reinterpret_cast<int*>(&s.counts[pair]);   // {n_x, n_y, n_z, overflow, n_v, n_w}
+    cnt[warp < 3 ? warp : warp + 1] = count;
     if (overflow) atomicOr(&cnt[3], 1);
   }
 }
@@ -534,10 +560,10 @@ cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_sparse(const SparseDev& s, int n_pairs, cudaStream_t st) {
-  sparse_kernel<<<n_pairs, 96, 0, st>>>(s);
+cudaError_t launch_sparse(const SparseDev& s, int n_pairs, bool with_ups, cudaStream_t st) {
+  sparse_kernel<<<n_pairs, 160, 0, st>>>(s);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess || !with_ups) return e;
   gather_up_kernel<<<n_pairs, 256, 0, st>>>(s);
   return cudaGetLastError();
 }

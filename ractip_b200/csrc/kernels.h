@@ -64,6 +64,8 @@ struct SparsePair {
   int cap_x, cap_y, cap_z;
   long long up1_src, up2_src, up1_dst, up2_dst;
   int n_up1, n_up2;
+  long long v, w;                      // record offsets of the accessible-region lists
+  int cap_v, cap_w;
 };
 
 struct SparseDev {
@@ -72,7 +74,8 @@ struct SparseDev {
   rp_rec* recs;
   float* ups;
   rp_sparse_counts* counts;
-  float th_ss, th_hy;
+  float th_ss, th_hy, th_ac;
+  int min_w, max_w;                    // window-length indices min_w-1 .. max_w-1 are scanned (src/ractip.cpp:622)
 };
 
 // minb = 2: 64-register build, two CTAs per SM; 1: 128 registers, one CTA per SM, split sums in bands of `wide` diagonals
@@ -85,7 +88,7 @@ cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, c
 int lockstep_max_ctas_per_sm(int threads);
 cudaError_t launch_lockstep(const BatchDev& b, int grid, int threads, cudaStream_t st);
 cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st);
-cudaError_t launch_sparse(const SparseDev& s, int n_pairs, cudaStream_t st);
+cudaError_t launch_sparse(const SparseDev& s, int n_pairs, bool with_ups, cudaStream_t st);
 cudaError_t launch_peak_fp64(double* out, int grid, int iters, cudaStream_t st);
 cudaError_t launch_peak_smem(double* out, int grid, int iters, cudaStream_t st);
 

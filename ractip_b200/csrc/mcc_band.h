@@ -114,15 +114,8 @@ RP_HD void carve_band(Shared& sh, BandShared& bs, void* base, int n, int T) {
 }
 
 RP_HD void load_band_weights(const DevModel& M, const BandShared& bs, int tid, int T) {
-  for (int x = tid; x < (MAXLOOP + 1) * (MAXLOOP + 1); x += T) {
-    const int s = x / (MAXLOOP + 1), t = x % (MAXLOOP + 1);
-    if (t > s) continue;
-    bs.G[s * (s + 1) / 2 + t] = M.gcls[t][s - t] == CLS_GENERIC ? M.gfull[t][s - t] : 0.;
-  }
-  for (int s = tid; s < 32; s += T) {
-    bs.gA[s] = (s >= 2 && s <= MAXLOOP) ? M.gfull[0][s] : 0.;
-    bs.g1[s] = (s >= 4 && s <= MAXLOOP) ? M.gfull[1][s - 1] : 0.;
-  }
+  for (int x = tid; x < GPACK; x += T) bs.G[x] = M.gpack[x];   // packed on the host (build_dev_model)
+  for (int s = tid; s < 32; s += T) { bs.gA[s] = M.gA[s]; bs.g1[s] = M.g1[s]; }
   SmallModel& S = *bs.sm;
   if (tid == 0) {
     S.scale1 = M.scale1; S.mlb1 = M.mlb1; S.expMLclosing = M.expMLclosing; S.expMLintern = M.expMLintern;

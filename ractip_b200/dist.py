@@ -3,16 +3,21 @@
 The shuffles of the loop at reference src/ractip.cpp:1638-1657 are independent
 (only four float accumulators cross iterations, :1626-1627,1655-1656), so rank r
 of W takes shuffles r, r+W, r+2W, ... and runs the probability stage on them.
-What the host-side ILP needs afterwards -- the thresholded variable lists and
-the unpaired-window tables of every shuffle -- is exchanged with ONE all-gather
-of a fixed-capacity byte buffer per rank:
+What the host-side ILP needs afterwards -- the thresholded variable lists x, y, z
+and the accessible-region lists v, w of every shuffle (src/ractip.cpp:557-567,
+578-588, 598-609, 619-628, 639-648; the lists carry every probability the integer
+programme reads, so no dense table travels) -- is exchanged with ONE all-gather of
+a fixed-capacity byte buffer per rank:
 
-    [ rp_rec records | up floats | rp_sparse_counts ]      (each part 256-B aligned)
+    [ rp_rec records | rp_sparse_counts ]      (each part 256-B aligned)
 
 Capacities come from rp_sparse_plan (a bound, not a count), so every rank's
 buffer has the same size and no size exchange is needed.  torch.distributed does
 the transport (NCCL over NVLink on GPUs, gloo in the CPU tests); the kernels
-write straight into the buffer through rp_batch_sparse_device.
+write straight into the buffer through rp_batch_sparse_device.  Stream order:
+rp_batch_sparse_device is asynchronous on the CONTEXT's stream; either make that
+the stream the collective runs on (rp_set_stream(torch's current stream), as
+bench.py does) or call DeviceBatch.sync() before gather().
 """
 from __future__ import annotations
 
@@ -26,6 +31,7 @@ from ._lib import RpOpts, RpPair, RpSparseLayout
 from .stage import REC_DTYPE, PairRecords
 
 ALIGN = 256
+CNT_BYTES = 24   # sizeof(rp_sparse_counts): n_x, n_y, n_z, overflow, n_v, n_w
 
 
 def shard_indices(n: int, rank: int, world: int) -> List[int]:
@@ -61,27 +67,33 @@ class ShardPlan:
         self.pairs, self.opts, self.rank, self.world = list(pairs), opts, rank, world
         self.n = len(self.pairs)
         self.shards = [shard_indices(self.n, r, world) for r in range(world)]
-        self.layouts, recs, ups, cnts = [], [], [], []
+        self.layouts, recs, cnts = [], [], []
         for r in range(world):
-            lay, tr, tf = _plan([self.pairs[i] for i in self.shards[r]], opts)
+            lay, tr, _tf = _plan([self.pairs[i] for i in self.shards[r]], opts)
             self.layouts.append(lay)
             recs.append(tr * REC_DTYPE.itemsize)
-            ups.append(tf * 4)
-            cnts.append(len(self.shards[r]) * 16)
+            cnts.append(len(self.shards[r]) * CNT_BYTES)
         # identical section sizes on every rank: the maximum over ranks
-        self.rec_bytes, self.up_bytes, self.cnt_bytes = _up(max(recs)), _up(max(ups)), _up(max(cnts))
-        self.nbytes = self.rec_bytes + self.up_bytes + self.cnt_bytes
+        self.rec_bytes, self.cnt_bytes = _up(max(recs)), _up(max(cnts))
+        self.nbytes = self.rec_bytes + self.cnt_bytes
 
     @property
     def my_pairs(self) -> List[Tuple[str, str]]:
         return [self.pairs[i] for i in self.shards[self.rank]]
 
-    def section_offsets(self) -> Tuple[int, int, int]:
-        return 0, self.rec_bytes, self.rec_bytes + self.up_bytes
+    def section_offsets(self) -> Tuple[int, int]:
+        return 0, self.rec_bytes
 
-    def capacities(self) -> Tuple[int, int]:
-        """(records, floats) the local buffer can hold: what rp_batch_sparse_device is told."""
-        return self.rec_bytes // REC_DTYPE.itemsize, self.up_bytes // 4
+    def capacity(self) -> int:
+        """Records the local buffer can hold: what rp_batch_sparse_device is told."""
+        return self.rec_bytes // REC_DTYPE.itemsize
+
+    def fill(self, batch, local) -> None:
+        """Have the batch's kernels write this rank's lists and counts into `local` (a CUDA uint8 tensor of
+        nbytes): rp_batch_sparse_device without the dense window tables."""
+        base = local.data_ptr()
+        batch.stage._check(batch.lib.rp_batch_sparse_device(batch.handle, C.c_void_p(base), self.capacity(),
+                                                            C.c_void_p(0), 0, C.c_void_p(base + self.rec_bytes)))
 
     def rec_view(self, buf: np.ndarray) -> np.ndarray:
         """The record section of one rank's buffer as a structured array."""
@@ -104,22 +116,18 @@ class ShardPlan:
     def unpack(self, gathered: np.ndarray) -> List[PairRecords]:
         """Gathered bytes (host) -> per-shuffle records in the ORIGINAL batch order."""
         gathered = np.ascontiguousarray(gathered).view(np.uint8).reshape(self.world, self.nbytes)
-        w = max(self.opts.max_w, 0)
         out: List[PairRecords] = [None] * self.n  # type: ignore
-        o_rec, o_up, o_cnt = self.section_offsets()
+        o_rec, o_cnt = self.section_offsets()
         for r in range(self.world):
             buf = gathered[r]
             recs = self.rec_view(buf)
-            ups = buf[o_up:o_up + self.up_bytes].view(np.float32)
-            cnts = buf[o_cnt:o_cnt + self.cnt_bytes].view(np.int32).reshape(-1, 4)
+            cnts = buf[o_cnt:o_cnt + len(self.shards[r]) * CNT_BYTES].view(np.int32).reshape(-1, CNT_BYTES // 4)
             for k, gi in enumerate(self.shards[r]):
                 S = self.layouts[r][k]
-                s1, s2 = self.pairs[gi]
-                nx, ny, nz, ov = (int(v) for v in cnts[k])
+                nx, ny, nz, ov, nv, nw = (int(v) for v in cnts[k])
                 if ov:
                     raise RuntimeError(f"record capacity exceeded for shuffle {gi}")
                 out[gi] = PairRecords(
-                    x=recs[S.x:S.x + nx], y=recs[S.y:S.y + ny], z=recs[S.z:S.z + nz],
-                    up1=ups[S.up1:S.up1 + S.n_up1].reshape(len(s1), w),
-                    up2=ups[S.up2:S.up2 + S.n_up2].reshape(len(s2), w))
+                    x=recs[S.x:S.x + nx], y=recs[S.y:S.y + ny], z=recs[S.z:S.z + nz], up1=None, up2=None,
+                    v=recs[S.v:S.v + nv], w=recs[S.w:S.w + nw])
         return out

@@ -81,8 +81,10 @@ class PairRecords:
     x: np.ndarray   # structured (i, j, p), 0-based, bp1 > th_ss
     y: np.ndarray   # bp2 > th_ss
     z: np.ndarray   # hp > th_hy
-    up1: np.ndarray
-    up2: np.ndarray
+    up1: Optional[np.ndarray]   # dense window tables (None when not fetched)
+    up2: Optional[np.ndarray]
+    v: Optional[np.ndarray] = None   # (start i, length index j, p): up1[i][j] > th_ac, j in [min_w-1, max_w)  (:619-628)
+    w: Optional[np.ndarray] = None   # the same for s2 (:639-648)
 
 
 REC_DTYPE = np.dtype([("i", np.int32), ("j", np.int32), ("p", np.float32)])
@@ -130,15 +132,18 @@ class DeviceBatch:
         self.stage._check(self.lib.rp_batch_fetch_dense(self.handle, out.ctypes.data, out.size))
         return out
 
-    def fetch_sparse(self, recs=None, ups=None, counts=None):
+    def fetch_sparse(self, recs=None, ups=None, counts=None, with_ups: bool = True):
+        """Thresholded lists x, y, z, v, w (+ the dense window tables unless with_ups=False).
+        counts[k] = (n_x, n_y, n_z, overflow, n_v, n_w)."""
         if recs is None:
             recs = np.zeros(max(self.total_recs, 1), dtype=REC_DTYPE)
-        if ups is None:
+        if ups is None and with_ups:
             ups = np.empty(max(self.total_upf, 1), dtype=np.float32)
         if counts is None:
-            counts = np.zeros((max(self.n, 1), 4), dtype=np.int32)
+            counts = np.zeros((max(self.n, 1), 6), dtype=np.int32)
         self.stage._check(self.lib.rp_batch_fetch_sparse(self.handle, recs.ctypes.data, recs.size,
-                                                         ups.ctypes.data, ups.size, counts.ctypes.data))
+                                                         C.c_void_p(ups.ctypes.data if ups is not None else 0),
+                                                         ups.size if ups is not None else 0, counts.ctypes.data))
         return recs, ups, counts
 
     def fetch_logz(self) -> np.ndarray:
@@ -165,11 +170,13 @@ class DeviceBatch:
         w = max(self.opts.max_w, 0)
         for k, (s1, s2) in enumerate(self.pairs):
             S = self.slayout[k]
-            nx, ny, nz = int(counts[k][0]), int(counts[k][1]), int(counts[k][2])
+            nx, ny, nz, nv, nw = (int(counts[k][0]), int(counts[k][1]), int(counts[k][2]), int(counts[k][4]),
+                                  int(counts[k][5]))
             out.append(PairRecords(
                 x=recs[S.x:S.x + nx], y=recs[S.y:S.y + ny], z=recs[S.z:S.z + nz],
-                up1=ups[S.up1:S.up1 + S.n_up1].reshape(len(s1), w),
-                up2=ups[S.up2:S.up2 + S.n_up2].reshape(len(s2), w)))
+                up1=None if ups is None else ups[S.up1:S.up1 + S.n_up1].reshape(len(s1), w),
+                up2=None if ups is None else ups[S.up2:S.up2 + S.n_up2].reshape(len(s2), w),
+                v=recs[S.v:S.v + nv], w=recs[S.w:S.w + nw]))
         return out
 
     def close(self):

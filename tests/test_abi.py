@@ -13,9 +13,10 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_library_exports_every_declared_symbol(lib):
-    hdr = (ROOT / "include" / "ractip_prob.h").read_text()
-    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(rp_[a-z0-9_]+)\s*\(", hdr))
+    declared = set()
+    for h in sorted((ROOT / "include").glob("*.h")):   # ractip_prob.h (probability stage), ractip_ip.h (consumer side)
+        hdr = re.sub(r"/\*.*?\*/", " ", h.read_text(), flags=re.S)
+        declared |= set(re.findall(r"\b(rp_[a-z0-9_]+)\s*\(", hdr))
     from ractip_b200 import _lib
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
@@ -28,7 +29,7 @@ def test_struct_sizes_match_the_header(lib):
     # rp_model: 4-byte ints and 8-byte doubles with natural alignment
     ints = 64 + 31 * 3 + 200 * 6 + 40 * 2 + 1600 + 8000 + 40000 + 7 + 200 + 40 + 200
     assert C.sizeof(RpModel) >= ints * 4 + 1401 + 241 + 1801
-    assert C.sizeof(RpRec) == 12 and C.sizeof(RpSparseCounts) == 16 and C.sizeof(RpDenseLayout) == 80
+    assert C.sizeof(RpRec) == 12 and C.sizeof(RpSparseCounts) == 24 and C.sizeof(RpDenseLayout) == 80
 
 
 def test_dense_and_sparse_plans(lib):
@@ -50,6 +51,7 @@ def test_dense_and_sparse_plans(lib):
     tr, tf = C.c_size_t(), C.c_size_t()
     assert lib.rp_sparse_plan(pairs, 2, C.byref(o), sl, C.byref(tr), C.byref(tf)) == 0
     assert sl[1].cap_x == 73 and sl[1].cap_y == 138 and sl[1].cap_z == 72 * 10
+    assert sl[1].cap_v == 72 * 11 and sl[1].cap_w == 137 * 11 and sl[1].w == sl[1].v + sl[1].cap_v   # lengths 5..15 (:622)
     assert tf.value == (10 + 9 + 72 + 137) * 15
     # bad arguments are reported, not crashed on
     assert lib.rp_dense_plan(None, 1, C.byref(o), lay, C.byref(tot)) == 1

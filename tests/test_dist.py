@@ -26,37 +26,46 @@ def _pairs():
             for _ in range(7)]  # odd count: ranks get 4 and 3 shuffles
 
 
+def oracle_lists(oracle, s1, s2, opts):
+    """Thresholded lists x, y, z, v, w from the oracle's matrices, in the reference's creation order
+    (src/ractip.cpp:557-567, 578-588, 598-609, 619-628, 639-648)."""
+    bp1, up1 = oracle.rnafold(s1, opts.max_w)
+    bp2, up2 = oracle.rnafold(s2, opts.max_w)
+    hp = oracle.rnaduplex(s1, s2, opts.th_hy)
+
+    def xs(bp, L):
+        out = []
+        for j in range(1, L):
+            for i in range(j - 1, -1, -1):
+                p = bp[(i + 1) * (2 * L + 1 - (i + 1)) // 2 + j + 1]
+                if p > np.float32(opts.th_ss):
+                    out.append((i, j, p))
+        return out
+
+    def vs(up):
+        if not (opts.min_w > 1 and opts.max_w >= opts.min_w):
+            return []
+        return [(i, j, up[i][j]) for i in range(up.shape[0]) for j in range(opts.min_w - 1, opts.max_w)
+                if up[i][j] > np.float32(opts.th_ac)]
+    z = [(i, j, hp[i + 1][j + 1]) for i in range(len(s1)) for j in range(len(s2))
+         if hp[i + 1][j + 1] > np.float32(opts.th_hy)]
+    return xs(bp1, len(s1)), xs(bp2, len(s2)), z, vs(up1), vs(up2)
+
+
 def _fill_from_oracle(plan, oracle, opts):
     """Write the oracle's thresholded lists into a local gather buffer, at the plan's layout."""
-    from ractip_b200.stage import REC_DTYPE
+    from ractip_b200.dist import CNT_BYTES
     buf = np.zeros(plan.nbytes, dtype=np.uint8)
-    o_rec, o_up, o_cnt = plan.section_offsets()
+    o_rec, o_cnt = plan.section_offsets()
     recs = plan.rec_view(buf)
-    ups = buf[o_up:o_up + plan.up_bytes].view(np.float32)
-    cnts = buf[o_cnt:o_cnt + plan.cnt_bytes].view(np.int32).reshape(-1, 4)
+    cnts = buf[o_cnt:o_cnt + len(plan.my_pairs) * CNT_BYTES].view(np.int32).reshape(-1, CNT_BYTES // 4)
     for k, (s1, s2) in enumerate(plan.my_pairs):
         S = plan.layouts[plan.rank][k]
-        bp1, up1 = oracle.rnafold(s1, opts.max_w)
-        bp2, up2 = oracle.rnafold(s2, opts.max_w)
-        hp = oracle.rnaduplex(s1, s2, opts.th_hy)
-
-        def xs(bp, L):
-            out = []
-            for j in range(1, L):
-                for i in range(j - 1, -1, -1):
-                    p = bp[(i + 1) * (2 * L + 1 - (i + 1)) // 2 + j + 1]
-                    if p > np.float32(opts.th_ss):
-                        out.append((i, j, p))
-            return out
-        x, y = xs(bp1, len(s1)), xs(bp2, len(s2))
-        z = [(i, j, hp[i + 1][j + 1]) for i in range(len(s1)) for j in range(len(s2))
-             if hp[i + 1][j + 1] > np.float32(opts.th_hy)]
-        for off, lst in ((S.x, x), (S.y, y), (S.z, z)):
+        x, y, z, v, w = oracle_lists(oracle, s1, s2, opts)
+        for off, lst in ((S.x, x), (S.y, y), (S.z, z), (S.v, v), (S.w, w)):
             for t, (i, j, p) in enumerate(lst):
                 recs[off + t] = (i, j, p)
-        cnts[k] = (len(x), len(y), len(z), 0)
-        ups[S.up1:S.up1 + S.n_up1] = up1.ravel()
-        ups[S.up2:S.up2 + S.n_up2] = up2.ravel()
+        cnts[k] = (len(x), len(y), len(z), 0, len(v), len(w))
     return buf
 
 
@@ -78,7 +87,7 @@ def _worker(rank, world, port, q):
         gathered = plan.gather(local)
         res = plan.unpack(gathered.numpy())
         # every rank must now hold every shuffle, in the original order
-        summary = [(r.x.tolist(), r.y.tolist(), r.z.tolist(), float(r.up1.sum()), float(r.up2.sum())) for r in res]
+        summary = [(r.x.tolist(), r.y.tolist(), r.z.tolist(), r.v.tolist(), r.w.tolist()) for r in res]
         q.put((rank, summary, plan.shards, plan.nbytes))
     finally:
         dist.destroy_process_group()
@@ -106,9 +115,9 @@ def test_two_ranks_gloo_gather_matches_single_process(oracle):
     opts = default_opts(max_w=6, min_w=3)
     plan = ShardPlan(_pairs(), opts, 0, 1)
     truth = plan.unpack(_fill_from_oracle(plan, oracle, opts))
-    summary = [(r.x.tolist(), r.y.tolist(), r.z.tolist(), float(r.up1.sum()), float(r.up2.sum())) for r in truth]
+    summary = [(r.x.tolist(), r.y.tolist(), r.z.tolist(), r.v.tolist(), r.w.tolist()) for r in truth]
     assert summary == s0
-    assert any(len(t[0]) for t in summary) and any(len(t[2]) for t in summary)  # non-trivial content
+    assert any(len(t[0]) for t in summary) and any(len(t[2]) for t in summary) and any(len(t[3]) for t in summary)
 
 
 def test_shard_plan_capacities_are_rank_independent():
@@ -119,7 +128,7 @@ def test_shard_plan_capacities_are_rank_independent():
     plans = [ShardPlan(pairs, opts, r, 4) for r in range(4)]
     assert len({p.nbytes for p in plans}) == 1
     assert sorted(i for p in plans for i in p.shards[p.rank]) == list(range(len(pairs)))
-    assert all(p.rec_bytes % 256 == 0 and p.up_bytes % 256 == 0 for p in plans)
+    assert all(p.rec_bytes % 256 == 0 and p.cnt_bytes % 256 == 0 for p in plans)
 
 
 @pytest.mark.gpu
@@ -134,15 +143,12 @@ def test_device_resident_records_roundtrip(stage, bundled):
     buf = torch.zeros(plan.nbytes, dtype=torch.uint8, device="cuda")
     b = stage.batch(plan.my_pairs, opts)
     b.run()
-    o_rec, o_up, o_cnt = plan.section_offsets()
-    cap_r, cap_f = plan.capacities()
-    base = buf.data_ptr()
-    stage._check(stage.lib.rp_batch_sparse_device(b.handle, C.c_void_p(base + o_rec), cap_r, C.c_void_p(base + o_up),
-                                                  cap_f, C.c_void_p(base + o_cnt)))
+    plan.fill(b, buf)
     b.sync()
     res = plan.unpack(plan.gather(buf).cpu().numpy())
     ref = stage.run_sparse(pairs, opts)
     b.close()
     for a, r in zip(res, ref):
         assert a.x.tolist() == r.x.tolist() and a.y.tolist() == r.y.tolist() and a.z.tolist() == r.z.tolist()
-        assert np.array_equal(a.up1, r.up1) and np.array_equal(a.up2, r.up2)
+        assert a.v.tolist() == r.v.tolist() and a.w.tolist() == r.w.tolist()
+        assert len(r.v) > 0 and len(r.w) > 0

@@ -388,3 +388,124 @@ def test_multi_cta_wavefront_matches_oracle(model, oracle, monkeypatch, cluster,
             _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"cluster={cluster} {len(s1)}x{len(s2)}")
     finally:
         st.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: end-to-end consumers, oracle-derived lists, the full batch, non-default models
+# ---------------------------------------------------------------------------------------------
+def test_joint_structures_identical_to_oracle_on_all_bundled_pairs(stage, oracle, model, bundled):
+    """north_star: identical predicted joint dot-bracket structures on every data/*.fa pair.  The integer
+    programme (ractip_b200/ip.py over csrc/ipmodel.cpp; src/ractip.cpp:552-1316) is fed once with the GPU's
+    matrices, once with the GPU's thresholded lists (x, y, z, v, w) and once with the oracle's matrices."""
+    from ractip_b200 import default_opts, solve_joint
+    from test_ip import README_DIS, oracle_probs
+    opts = default_opts()
+    pairs = [(bundled["sequences"][a], bundled["sequences"][b]) for a, b in bundled["pairs"]]
+    dense = stage.run_dense(pairs, opts)
+    lists = stage.run_sparse(pairs, opts)
+    for (a, b), (s1, s2), d, l in zip(bundled["pairs"], pairs, dense, lists):
+        g = solve_joint(model, s1, s2, d, energies=True)
+        gl = solve_joint(model, s1, s2, d, recs=l)
+        o = solve_joint(model, s1, s2, oracle_probs(oracle, s1, s2), energies=True)
+        assert (g.r1, g.r2) == (o.r1, o.r2), (a, b)
+        assert (gl.r1, gl.r2) == (o.r1, o.r2), (a, b, "lists")
+        assert (g.e1, g.e2, g.e3) == (o.e1, o.e2, o.e3)
+        assert abs(g.objective - o.objective) < 1e-5
+    # the README example (README.md:91-97): exact once the near-threshold window 11..23 is not a variable
+    from ractip_b200 import default_ip_opts
+    s = bundled["sequences"]["DIS"]
+    k = [p for p, (a, b) in enumerate(bundled["pairs"]) if a == "DIS"][0]
+    r = solve_joint(model, s, s, dense[k], default_ip_opts(th_ac=0.004))
+    assert (r.r1, r.r2) == README_DIS
+
+
+def test_sparse_lists_against_oracle_derived_lists(stage, oracle, bundled):
+    """x, y, z, v, w records of rp_run_sparse against lists cut from the ORACLE's matrices in the reference's
+    creation order (src/ractip.cpp:557-567, 578-588, 598-609, 619-628, 639-648)."""
+    from ractip_b200 import default_opts
+    from test_dist import oracle_lists
+    for kw in (dict(), dict(min_w=3, max_w=8, th_ac=0.01), dict(min_w=1, max_w=4), dict(max_w=1, min_w=5)):
+        opts = default_opts(**kw)
+        pairs = [(bundled["sequences"][a], bundled["sequences"][b]) for a, b in bundled["pairs"]]
+        for (s1, s2), sp in zip(pairs, stage.run_sparse(pairs, opts)):
+            want = oracle_lists(oracle, s1, s2, opts)
+            for got, ref, th in zip((sp.x, sp.y, sp.z, sp.v, sp.w), want,
+                                    (opts.th_ss, opts.th_ss, opts.th_hy, opts.th_ac, opts.th_ac)):
+                gi = [(int(r["i"]), int(r["j"])) for r in got]
+                ri = [(i, j) for i, j, _ in ref]
+                if gi != ri:   # only values within float noise of the threshold may differ in presence
+                    odd = set(gi) ^ set(ri)
+                    pv = {(i, j): p for i, j, p in ref}
+                    pv.update({(int(r["i"]), int(r["j"])): float(r["p"]) for r in got})
+                    assert all(abs(pv[k] - float(np.float32(th))) < 3e-7 for k in odd), (kw, odd)
+                    assert [k for k in gi if k not in odd] == [k for k in ri if k not in odd]
+                else:
+                    assert np.abs(np.array([r["p"] for r in got], dtype=np.float64) -
+                                  np.array([p for _, _, p in ref], dtype=np.float64)).max(initial=0) <= TOL
+
+
+def test_full_1000_shuffle_batch_against_the_oracle(stage, oracle, bundled):
+    """BASELINE configs[3] at full size: EVERY one of the 1000 shuffled pairs against the oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+    from ractip_b200 import default_opts, zscore_shuffles
+    s1, s2 = bundled["sequences"]["MicA"], bundled["sequences"]["ompA"]
+    r1, r2 = zscore_shuffles(s1, s2, 1000, 1)
+    pairs = list(zip(r1, r2))
+    opts = default_opts()
+    res = stage.run_dense(pairs, opts)
+    with ThreadPoolExecutor(16) as ex:   # the oracle releases the GIL inside its C calls
+        oras = list(ex.map(lambda p: _oracle_pair(oracle, p[0], p[1], opts), pairs))
+    for k, ((a, c), r, ora) in enumerate(zip(pairs, res, oras)):
+        _compare(r, ora, a, c, opts, f"shuffle {k}")
+
+
+@pytest.mark.parametrize("variant", ["special_hp0", "pf_smooth0", "par_overlay"])
+def test_parity_under_non_default_models(variant, bundled, tmp_path):
+    """The kernels under other energy models: tetra_loop off, pf_smooth off, and a -P overlay
+    (rp_model_read_par, src/ractip.cpp:1568-1569) that changes stacking, hairpin and multiloop values."""
+    from oracle.oracle import Oracle
+    from ractip_b200 import ProbabilityStage, default_model, default_opts
+    m = default_model()
+    if variant == "special_hp0":
+        m.special_hp = 0
+    elif variant == "pf_smooth0":
+        m.pf_smooth = 0
+    else:
+        par = tmp_path / "overlay.par"
+        lines = ["## RNAfold parameter file v2.0", "", "# stack"]
+        rng = np.random.default_rng(5)
+        for _ in range(7):
+            lines.append(" ".join(str(int(v)) for v in rng.integers(-340, -60, 7)))
+        lines += ["", "# hairpin", "INF INF INF 540 560 570 540 600 550 640",
+                  "650 660 670 680 690 690 700 710 710 720", "720 730 730 740 740 750 750 750 760 760", "770",
+                  "", "# ML_params", "0 0 930 3000 -90 -220", "", "# NINIO", "60 320 300", "", "#END", ""]
+        par.write_text("\n".join(lines))
+        m = default_model(param_file=str(par))
+        assert m.ML_closing37 == 930 and m.ninio37 == 60
+    st = ProbabilityStage(m)
+    orc = Oracle(m)
+    opts = default_opts()
+    try:
+        for a, b in [("DIS", "DIS"), ("CopA", "CopT"), ("MicA", "ompA")]:
+            s1, s2 = bundled["sequences"][a], bundled["sequences"][b]
+            _compare(st.solve_probabilities(s1, s2, opts), _oracle_pair(orc, s1, s2, opts), s1, s2, opts, variant)
+    finally:
+        st.close()
+
+
+def test_random_sweep_of_lengths_nick_positions_and_letters(stage, oracle):
+    """Hypothesis-style sweep: lengths 1..260 (every kernel route), every nick position class, N / T /
+    lower-case letters; 120 seeded pairs in three ragged batches."""
+    from ractip_b200 import default_opts
+    rng = np.random.default_rng(20261018)
+    opts = default_opts()
+    alphabets = ["ACGU", "ACGU", "GCGCAU", "ACGUN", "ACGTacgu"]
+    for batch in range(3):
+        pairs = []
+        for _ in range(40):
+            tot = int(rng.choice([rng.integers(2, 40), rng.integers(40, 120), rng.integers(120, 261)]))
+            n1 = int(rng.integers(1, tot))
+            al = alphabets[int(rng.integers(0, len(alphabets)))]
+            pairs.append((rand_seq(rng, n1, al), rand_seq(rng, tot - n1, al)))
+        for (s1, s2), r in zip(pairs, stage.run_dense(pairs, opts)):
+            _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"sweep {len(s1)}x{len(s2)}")

@@ -1,0 +1,229 @@
+"""Consumer side of the probability stage: the integer programme of RactIP::solve /
+solve_ss (reference src/ractip.cpp:552-1225, 1366-1465), decoding (:1227-1316) and energy evaluation
+(:1254,1299,1457,1528-1559).
+
+CPU tests feed the ORACLE's matrices; GPU tests (test_gpu_parity.py) feed the kernels' matrices through the
+same code and must predict the same joint structures.
+
+The only output the reference holds for the whole pipeline is the DIS x DIS example of README.md:91-97.
+Under the default options the model built here has a better optimum than the README's structure: the
+accessible window 11..23 of DIS has P(unpaired) = 0.0038 against th_ac = 0.003 (a near-threshold variable),
+and with it four more kissing pairs beat the two inner pairs of the stem.  With th_ac >= 0.004 the README
+strings are reproduced exactly.  Both facts are asserted below; DESIGN.md section 5 discusses them.
+"""
+import itertools
+import math
+
+import numpy as np
+import pytest
+
+from test_dist import oracle_lists
+
+README_DIS = ("((((.(((((((..[[[[[[.)))))))...))))", "((((.(((((((..]]]]]].)))))))...))))")   # README.md:94,97
+
+
+def oracle_probs(oracle, s1, s2, max_w=15, th_hy=0.1):
+    from ractip_b200 import bp_offsets
+    from ractip_b200.stage import PairProbabilities
+    bp1, up1 = oracle.rnafold(s1, max_w)
+    bp2, up2 = oracle.rnafold(s2, max_w)
+    hp = oracle.rnaduplex(s1, s2, th_hy)
+    return PairProbabilities(bp1, bp_offsets(len(s1)), up1, bp2, bp_offsets(len(s2)), up2, hp)
+
+
+def well_formed(r1, r2):
+    """'(' ')' nested per strand; '[' in r1 and ']' in r2 in equal numbers (external pairs never cross)."""
+    for r in (r1, r2):
+        depth = 0
+        for ch in r:
+            depth += ch == "("
+            depth -= ch == ")"
+            assert depth >= 0
+        assert depth == 0
+    assert r1.count("[") == r2.count("]") and "]" not in r1 and "[" not in r2
+
+
+def test_readme_dis_example(oracle, model, bundled):
+    from ractip_b200 import default_ip_opts, solve_joint
+    s = bundled["sequences"]["DIS"]
+    P = oracle_probs(oracle, s, s)
+    # README strings, once the near-threshold accessible window 11..23 (P = 0.0038) is below th_ac
+    r = solve_joint(model, s, s, P, default_ip_opts(th_ac=0.004))
+    assert (r.r1, r.r2) == README_DIS
+    obj_readme = r.objective
+    # default options: that window is a variable, and the optimum uses it
+    assert 0.003 < P.up1[10][12] < 0.004
+    d = solve_joint(model, s, s, P, energies=True)
+    assert d.r1 == "((((.((((([[..[[[[[[.[[)))))...))))" and d.r2 == "((((.(((((]]..]]]]]].]])))))...))))"
+    assert d.objective > obj_readme + 0.5
+    # the README's helices are all in it but the two inner pairs of the 7-bp stem
+    assert all(a == b or (a in "[]" and b in "()") for a, b in zip(d.r1, README_DIS[0]) if b != ".")
+    assert d.e1 == pytest.approx(d.e2) and d.e1 < 0 and d.e3 < 0
+
+
+def test_joint_structures_of_bundled_pairs_are_well_formed(oracle, model, bundled):
+    from ractip_b200 import solve_joint
+    for a, b in bundled["pairs"]:
+        s1, s2 = bundled["sequences"][a], bundled["sequences"][b]
+        r = solve_joint(model, s1, s2, oracle_probs(oracle, s1, s2), energies=True)
+        well_formed(r.r1, r.r2)
+        assert r.r1.count("[") >= 2, (a, b)      # every bundled pair is a known interaction
+        assert len(r.r1) == len(s1) and len(r.r2) == len(s2)
+        # no isolated external pair (stacking rows, src/ractip.cpp:1148-1167)
+        assert "[" not in [r.r1[k] for k in range(len(s1)) if r.r1[k] == "[" and
+                           (k == 0 or r.r1[k - 1] != "[") and (k + 1 == len(s1) or r.r1[k + 1] != "[")]
+        assert -60 < r.e3 < 5.0   # a short helix does not always pay for DuplexInit (OxyS x fhlA: +0.2)
+
+
+def test_model_from_lists_equals_model_from_matrices(oracle, bundled):
+    """rp_ip_build_sparse on the thresholded lists == rp_ip_build on the dense matrices, column for column."""
+    from ractip_b200 import IPModel, default_ip_opts, default_opts
+    from ractip_b200.stage import REC_DTYPE, PairRecords
+    opts = default_opts()
+    for a, b in [("DIS", "DIS"), ("CopA", "CopT"), ("Tar", "Tarstar")]:
+        s1, s2 = bundled["sequences"][a], bundled["sequences"][b]
+        P = oracle_probs(oracle, s1, s2)
+        x, y, z, v, w = (np.array(l, dtype=REC_DTYPE) for l in oracle_lists(oracle, s1, s2, opts))
+        for kw in (dict(), dict(acc_max=1), dict(min_w=0, max_w=0), dict(beta=0.3, acc_num=2), dict(in_pk=0, stacking=0)):
+            io = default_ip_opts(**kw)
+            if io.max_w == 0:   # accessibility off: rnafold still runs with max(1, max_w) (src/ractip.cpp:546)
+                bp1, up1 = oracle.rnafold(s1, 1)
+                bp2, up2 = oracle.rnafold(s2, 1)
+                Pk = type(P)(bp1, P.offset1, up1, bp2, P.offset2, up2, P.hp)
+            else:
+                Pk = P
+            d = IPModel.joint(Pk, io)
+            s = IPModel.joint_sparse(len(s1), len(s2), PairRecords(x, y, z, None, None, v, w), io)
+            assert (d.n_cols, d.n_rows, d.nnz) == (s.n_cols, s.n_rows, s.nnz), kw
+            for f in ("obj", "row_kind", "row_lo", "row_hi", "ia", "ja", "ar"):
+                assert np.array_equal(getattr(d, f), getattr(s, f)), (kw, f)
+            d.close(); s.close()
+
+
+def test_model_shape_follows_the_reference(oracle, bundled):
+    """Column and row counts from the reference's loops (src/ractip.cpp:552-653, 717-994) for a small case."""
+    from ractip_b200 import IPModel, default_ip_opts, default_opts
+    s1, s2 = bundled["sequences"]["Tar"], bundled["sequences"]["Tarstar"]
+    n1, n2 = len(s1), len(s2)
+    P = oracle_probs(oracle, s1, s2)
+    x, y, z, v, w = oracle_lists(oracle, s1, s2, default_opts())
+    m = IPModel.joint(P, default_ip_opts())
+    assert m.n_cols == len(x) + n1 + len(y) + n2 + len(z) + n1 + n2 + len(v) + 2 * n1 + len(w) + 2 * n2
+    # objective: p - th_ss, alpha (p - th_hy), beta (up - th_ac) in float arithmetic, creation order
+    f = np.float32
+    want = [f(p) - f(0.5) for _, _, p in x] + [0.0] * n1 + [f(p) - f(0.5) for _, _, p in y] + [0.0] * n2 + \
+           [f(0.7) * (f(p) - f(0.1)) for _, _, p in z]
+    assert np.array_equal(m.obj[:len(want)], np.array(want, dtype=np.float64))
+    assert not m.obj[len(want):].any()          # beta = 0 by default
+    # first rows: the one-hot rows of s1 (FX 1), each starting with x_un[i]
+    assert m.row_kind[0] == 4 and m.row_lo[0] == 1 and m.ja[0] == len(x)
+    val, cols = m.solve()
+    assert val == pytest.approx(float(m.obj @ np.round(cols)))
+    m.close()
+
+
+def test_solve_ss_and_acc_max(oracle, model, bundled):
+    from ractip_b200 import default_ip_opts, solve_joint, solve_ss
+    s = bundled["sequences"]["DIS"]
+    bp, _ = oracle.rnafold(s, 15)
+    ea, r, e = solve_ss(model, s, bp, energy=True)
+    assert r == "((((.(((((((.........)))))))...))))" and ea > 0 and e < 0
+    # a masked base cannot pair (the --acc-max-ss call, src/ractip.cpp:1263-1271)
+    usable = np.ones(len(s), dtype=np.uint8)
+    usable[5:12] = 0
+    _, r2 = solve_ss(model, s, bp, usable=usable)
+    assert set(r2[5:12]) == {"."}
+    # --acc-max: no internal-pair variables at all; --acc-max-ss adds them back outside the chosen region
+    P = oracle_probs(oracle, s, s)
+    a = solve_joint(model, s, s, P, default_ip_opts(acc_max=1, beta=1.0), energies=True)
+    assert "(" not in a.r1 and a.r1.count("[") >= 6 and a.e1 > 0    # -kT ln(up) of the chosen region
+    b = solve_joint(model, s, s, P, default_ip_opts(acc_max=1, acc_max_ss=1, beta=1.0))
+    assert b.r1.count("[") == a.r1.count("[") and "(" in b.r1
+    well_formed(b.r1, b.r2)
+
+
+# ------------------------------------------------------------------ energy evaluation
+def all_structures(n, cp=0, turn=3):
+    """Every non-crossing structure on 1..n with hairpins of >= turn unpaired bases (same-strand pairs only:
+    a pair across the nick has no minimum distance beyond the model's own j-i > TURN rule)."""
+    out = []
+
+    def rec(i, cur):
+        if i > n:
+            out.append(dict(cur))
+            return
+        rec(i + 1, cur)   # i unpaired (as far as pairs opening at i go)
+        if i in cur.values():
+            return
+        for j in range(i + turn + 1, n + 1):
+            pass
+    # simple O(Catalan) enumeration over pair tables
+    def gen(lo, hi):
+        """structures on the interval [lo, hi] as lists of pairs"""
+        if hi - lo < turn + 1:
+            return [[]]
+        res = list(gen(lo + 1, hi))          # lo unpaired
+        for j in range(lo + turn + 1, hi + 1):
+            for inner in gen(lo + 1, j - 1):
+                for rest in gen(j + 1, hi):
+                    res.append([(lo, j)] + inner + rest)
+        return res
+    return gen(1, n)
+
+
+def to_string(n, pairs):
+    s = ["."] * n
+    for i, j in pairs:
+        s[i - 1], s[j - 1] = "(", ")"
+    return "".join(s)
+
+
+def can_pair(a, b):
+    return a + b in ("AU", "UA", "GC", "CG", "GU", "UG")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_energy_evaluation_sums_to_the_partition_function(lib, oracle, seed):
+    """sum_S exp(-E(S)/kT) over ALL structures == Z of the oracle's DP, single strand and two strands,
+    with the clipped (pf_smooth = 0) tables the integer evaluation uses; DuplexInit is not part of the
+    two-strand ensemble and is taken out of E for the structures that join the strands."""
+    import ctypes as C
+    from conftest import rand_seq
+    from oracle.oracle import Oracle
+    from ractip_b200 import default_model, energy_of_structure
+    m = default_model()
+    m.pf_smooth = 0
+    orc = Oracle(m)
+    kT = (37.0 + 273.15) * 1.98717 / 1000.0
+    rng = np.random.default_rng(seed)
+    for n, cp in ((11, 0), (12, 0), (12, 6), (11, 8)):
+        seq = rand_seq(rng, n, "GCGCAU")
+        _, _, logz = orc.fold(seq, cp)
+        tot = 0.0
+        for pairs in all_structures(n):
+            if not all(can_pair(seq[i - 1], seq[j - 1]) for i, j in pairs):
+                continue
+            e = energy_of_structure(m, seq, to_string(n, pairs), cp if cp else -1)
+            if cp and any(i < cp <= j for i, j in pairs):
+                e -= m.DuplexInit37 / 100.0
+            tot += math.exp(-e / kT)
+        assert math.log(tot) == pytest.approx(logz, abs=2e-5), (seq, cp)   # E is rounded to float32 kcal/mol
+
+
+def test_energy_of_duplex_and_zscore(model, bundled):
+    from ractip_b200 import energy_of_duplex, energy_of_structure, zscore_statistic
+    s = bundled["sequences"]["DIS"]
+    r1, r2 = README_DIS
+    e3 = energy_of_duplex(model, s, s, r1, r2)
+    # brackets only: the same as evaluating the six kissing pairs on the concatenation with a nick
+    rr = (r1 + r2).replace("(", ".").replace(")", ".").replace("[", "(").replace("]", ")")
+    assert e3 == pytest.approx(energy_of_structure(model, s + s, rr, len(s) + 1))
+    assert e3 == pytest.approx(energy_of_structure(model, s + s, rr, -1) + 0.0, abs=50) and e3 < 0
+    # DuplexInit is added exactly once
+    lone = "." * 14 + "((((((" + "." * 15
+    e_open = energy_of_structure(model, s + s, "." * 70, len(s) + 1)
+    assert e_open == 0.0
+    # z-score: (e - mean) / sd in float (src/ractip.cpp:1658-1669)
+    a, b = zscore_statistic(-20.0, -9.0, [(-10.0, -6.0), (-12.0, -7.0), (-8.0, -5.0), (-10.0, -6.0)])
+    assert a == pytest.approx((-20.0 + 10.0) / math.sqrt(2.0), rel=1e-5)
+    assert b == pytest.approx((-11.0 + 4.0) / math.sqrt(0.5), rel=1e-5)
