@@ -7,6 +7,9 @@
 * ushuffle.json : outputs of the REFERENCE's own src/ushuffle.c (compiled where it
   lies into oracle/_ref by oracle/Makefile) driven exactly like
   src/ractip.cpp:1636-1643: srandom(seed); alternate shuffle(s1,k=2), shuffle(s2,k=2).
+* default_model.bin : the bytes of the rp_model struct rp_model_default(use_bl=1) fills (BL* tables from
+  src/boltzmann_param.c over the residual Turner-2004 tables), so that bench.py's reference arm and other
+  checker-side code can run the oracle without loading the product library.
 """
 import ctypes as C
 import json
@@ -33,7 +36,15 @@ def read_fa(p):
     return name, seq
 
 
+def write_default_model():
+    import ctypes
+    from ractip_b200 import default_model
+    m = default_model()
+    (ROOT / "tests" / "golden" / "default_model.bin").write_bytes(ctypes.string_at(ctypes.addressof(m), ctypes.sizeof(m)))
+
+
 def main():
+    write_default_model()
     seqs = {}
     for fa in sorted((REF / "data").glob("*.fa")):
         _, s = read_fa(fa)
