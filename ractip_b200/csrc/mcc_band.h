@@ -150,7 +150,9 @@ struct Segs {
   int b[4];   // first cell of each segment, b[3] = n-d+1
   int G[4];   // first group of each segment, G[3] = number of groups
 };
-RP_HD Segs make_segs(int n, int cp, int d) {
+// `cross_only`: only the cells that join the two strands (segment 1) exist -- the outside pass of a two-strand
+// problem needs no others (see cross_lo / cross_hi in mcc_core.h): segments 0 and 2 come out empty.
+RP_HD Segs make_segs(int n, int cp, int d, bool cross_only = false) {
   Segs s;
   const int C = n - d;
   s.b[0] = 1; s.b[3] = C + 1;
@@ -163,6 +165,7 @@ RP_HD Segs make_segs(int n, int cp, int d) {
     if (b2 < b1) b2 = b1;
     s.b[1] = b1; s.b[2] = b2;
   }
+  if (cross_only && cp > 0) { s.b[0] = s.b[1]; s.b[3] = s.b[2]; }
   s.G[0] = 0;
   for (int k = 0; k < 3; k++) s.G[k + 1] = s.G[k] + (s.b[k + 1] - s.b[k] + BR - 1) / BR;
   return s;
@@ -183,9 +186,9 @@ struct DiagDesc {
 };
 constexpr int NDESC = 4;   // ring of descriptors (diagonal d at d & 3): a descriptor lives for three phases
 static_assert(sizeof(DiagDesc) * NDESC <= DESC_DOUBLES * sizeof(double), "descriptor ring");
-RP_HD void band_make_desc(DiagDesc& D, int n, int cp, int d, int T) {
-  D.sg = make_segs(n, cp, d);
-  const int NG = D.sg.G[3], cells = n - d;
+RP_HD void band_make_desc(DiagDesc& D, int n, int cp, int d, int T, bool cross_only = false) {
+  D.sg = make_segs(n, cp, d, cross_only);
+  const int NG = D.sg.G[3], cells = D.sg.b[3] - D.sg.b[0];
   // an item block is GB lanes = GB consecutive groups: a half-warp, or a quarter-warp when the whole
   // diagonal fits in 8 groups (4 slices per warp: half the instructions on the short diagonals)
   D.gsh = NG <= 8 ? 3 : 4;
@@ -418,15 +421,15 @@ RP_HD double outside_specials_band(const C& c, const BandShared& bs, int d, int 
 // the CTA (idle or lightly loaded in the item schedule) and form slice NSLICE.
 template <int SIGN, class C>
 RP_HD void band_interior_A(const C& c, const BandShared& bs, int d, int tid, int T) {
-  const int n = c.n, cells = n - d;
+  const int n = c.n;
   // layout, item schedule and thread roles of this diagonal: worked out once, a phase ahead (band_make_desc)
   const DiagDesc& D = bs.desc[d & (NDESC - 1)];
   const Segs& sg = D.sg;
   const int NG = sg.G[3], gsh = D.gsh, GB = 1 << gsh, NB = D.NB, nitems = D.nitems, t0 = D.t0;
   const int smax = SIGN > 0 ? d - 6 : n - 3 - d;
   // small loops first: their table look-ups are in flight while the row items run
-  for (int x = T - 1 - tid; x < cells; x += T) {
-    const int i = 1 + x;
+  for (int x = T - 1 - tid; x < sg.b[3] - sg.b[0]; x += T) {   // (the active cells: all, or the inter-strand ones)
+    const int i = sg.b[0] + x;
     double v;
     if (RP_DBG(c) & 8) v = 0.;
     else if (SIGN > 0) v = inside_specials_band(c, bs, d, i);
@@ -659,10 +662,11 @@ RP_HD void band_inside_B(C& c, const Shared& sh, const BandShared& bs, int d, bo
 template <class C>
 RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, bool wide, int tid) {
   if (RP_DBG(c) & 16) return;
-  const int T = sh.T, n = c.n, cells = n - d;
+  const int T = sh.T, n = c.n;
   const SmallModel& M = *bs.sm;
-  for (int x = tid; x < cells; x += T) {
-    const int k = 1 + x, l = k + d;
+  const int k_lo = cross_lo(c, d), k_hi = cross_hi(c, d);   // two strands: only the inter-strand cells
+  for (int x = tid; x <= k_hi - k_lo; x += T) {
+    const int k = k_lo + x, l = k + d;
     const bool mlr = l < n && ss(c, l, l + 1);
     const bool mll = k > 1 && ss(c, k - 1, k);
     // ---- (1) loads
@@ -727,8 +731,8 @@ RP_HD void band_collect(const C& c, const BandShared& bs, int dsum, int dnext, i
   for (int rep = 0; rep < reps; rep++) {
     if (dsum >= 0) {
       const Segs& sg = bs.desc[dsum & (NDESC - 1)].sg;
-      const int cells = c.n - dsum;
-      for (int x = tid; x < cells; x += T) bs.sIv[1 + x] = band_interior_sum<SIGN>(c, bs, dsum, sg, 1 + x);
+      const int first = sg.b[0], cells = sg.b[3] - sg.b[0];
+      for (int x = tid; x < cells; x += T) bs.sIv[first + x] = band_interior_sum<SIGN>(c, bs, dsum, sg, first + x);
     }
     if (dnext >= 0) {
       if (SIGN > 0) band_cfac_inside(c, bs, dnext, tid, T);

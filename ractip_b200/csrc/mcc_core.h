@@ -222,6 +222,17 @@ RP_HD int rtype(int t) { return t == 0 ? 0 : (t == 7 ? 7 : ((t - 1) ^ 1) + 1); }
 template <class C>
 RP_HD bool ss(const C& c, int a, int b) { return c.cp <= 0 || a >= c.cp || b < c.cp; }
 
+// Outside pass of a two-strand problem: RactIP keeps only the probabilities of pairs that JOIN the strands
+// (i < cp <= j; reference src/ractip.cpp:451-453), and the outside value of such a pair depends on enclosing
+// pairs only, which join the strands as well (exterior, interior and multiloop contexts alike; the
+// nicked-loop context exists for same-strand stems only).  So the outside wavefront of a two-strand problem
+// runs over the inter-strand cells of a diagonal, k in [cross_lo, cross_hi], and needs no nick sums.
+// Single strand: all cells.
+template <class C>
+RP_HD int cross_lo(const C& c, int d) { return c.cp > 0 ? (c.cp - d > 1 ? c.cp - d : 1) : 1; }
+template <class C>
+RP_HD int cross_hi(const C& c, int d) { return c.cp > 0 ? (c.cp - 1 < c.n - d ? c.cp - 1 : c.n - d) : c.n - d; }
+
 // (MT: DevModel, or the shared-memory copy of its small tables used by the band kernel)
 template <class MT>
 RP_HD double ext_stem(const MT& M, int type, int s5, int s3) {

@@ -141,11 +141,8 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
   }
 
   // ---- outside: longest spans first
+  // (two strands: only the inter-strand cells of a diagonal, no nick sums -- cross_lo / cross_hi in mcc_core.h)
   for (int d = n - 1; d >= TURN + 1; d--) {
-    if (c.cp > 0) {
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, sh.red, 1, 32, d, tid, T); });
-      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, sh.red, 1, 32, d, tid, T); });
-    }
     if ((n - 1 - d) % BAND == 0) {  // a band of diagonals d, d-1, ..., d-BAND+1 starts here
       const int rows = n - d + BAND - 1;
       int chunk = make_split(rows, T).Cp;
@@ -170,10 +167,10 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
         });
       }
     }
-    const int cells = n - d;
+    const int lo = cross_lo(c, d), hi = cross_hi(c, d), cells = hi - lo + 1;
     const int chunk = cells < T ? cells : T;
-    for (int i0 = 1; i0 <= cells; i0 += chunk) {
-      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
+    for (int i0 = lo; i0 <= hi; i0 += chunk) {
+      const int C = hi - i0 + 1 < chunk ? hi - i0 + 1 : chunk;
       ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
       ex.phase(PH_OUTSIDE_B, [&](int tid) { outside_B(c, sh, d, i0, C, tid); });
     }
@@ -246,13 +243,6 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
   }
 
   for (int d = n - 1; d >= TURN + 1; d--) {
-    if (c.cp > 0) {
-      // long strands: each of the four nick sums over T/4 threads (partials in the partial-sum buffer, idle here)
-      const int np = T >= 128 ? T / 4 : 32;
-      double* red = T >= 128 ? sh.part : sh.red;
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, red, 1, np, d, tid, T); });
-      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, red, 1, np, d, tid, T); });
-    }
     if (d == wide_start_outside<W>(n, d)) {
       const int rows = n - d + W - 1;
       int chunk = make_split(rows, T).Cp;
@@ -277,10 +267,10 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
         });
       }
     }
-    const int cells = n - d;
+    const int lo = cross_lo(c, d), hi = cross_hi(c, d), cells = hi - lo + 1;
     const int chunk = cells < T ? cells : T;
-    for (int i0 = 1; i0 <= cells; i0 += chunk) {
-      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
+    for (int i0 = lo; i0 <= hi; i0 += chunk) {
+      const int C = hi - i0 + 1 < chunk ? hi - i0 + 1 : chunk;
       ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
       ex.phase(PH_OUTSIDE_B, [&](int tid) { wide_outside_finish<W>(c, sh, d, i0, C, tid); });
     }
@@ -354,15 +344,6 @@ __device__ void solve_mcc_cluster(Exec& ex, Ctx& c, const Problem& p, float* den
   }
 
   for (int d = n - 1; d >= TURN + 1; d--) {
-    if (c.cp > 0) {
-      // The nick sums are O(n) per diagonal.  EVERY CTA computes them (same operands, same order: the same
-      // bits) and stores the four results itself, so its finishing phase below depends on nothing another
-      // CTA does in this step -- no cluster barrier here; the redundant stores carry identical values.
-      const int np = T >= 128 ? T / 4 : 32;
-      double* red = T >= 128 ? sh.part : sh.red;
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(c, *c.M, red, 1, np, d, tid, T); });
-      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(c, red, 1, np, d, tid, T); });
-    }
     if (d == wide_start_outside<W>(n, d)) {
       const int rows = n - d + W - 1;
       const int chunk = share(rows, wide_chunk<W>(T));
@@ -373,10 +354,10 @@ __device__ void solve_mcc_cluster(Exec& ex, Ctx& c, const Problem& p, float* den
       }
       ex.csync();
     }
-    const int cells = n - d;
+    const int lo = cross_lo(c, d), hi = cross_hi(c, d), cells = hi - lo + 1;
     const int chunk = share(cells, T);
-    for (int i0 = 1 + R * chunk; i0 <= cells; i0 += G * chunk) {
-      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
+    for (int i0 = lo + R * chunk; i0 <= hi; i0 += G * chunk) {
+      const int C = hi - i0 + 1 < chunk ? hi - i0 + 1 : chunk;
       ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
       ex.phase(PH_OUTSIDE_B, [&](int tid) { wide_outside_finish<W>(c, sh, d, i0, C, tid); });
     }
@@ -502,12 +483,12 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
   // step late as well: first half in the long phase of step x-1, second half in the quick phase
   // after it; their results are first read when diagonal x-1 is completed, in step x-2.
   if (n - 1 >= TURN + 1)
-    ex.phase(PH_CFAC, [&](int tid) { if (tid == 0) band_make_desc(bs.desc[(n - 1) & (NDESC - 1)], n, c.cp, n - 1, T); });
+    ex.phase(PH_CFAC, [&](int tid) { if (tid == 0) band_make_desc(bs.desc[(n - 1) & (NDESC - 1)], n, c.cp, n - 1, T, true); });
   ex.phase(PH_CFAC, [&](int tid) { band_collect<-1>(c, bs, -1, n - 1 >= TURN + 1 ? n - 1 : -1, tid, T); });
   for (int d = n - 1; d >= TURN; d--) {
     const int dfin = d + 1 <= n - 1 ? d + 1 : -1;
     const int dnew = d >= TURN + 1 ? d : -1;
-    const bool nick = c.cp > 0 && dfin >= 0;
+    const bool nick = false;   // (only inter-strand cells are finished: the nicked-loop context never applies)
     // split sums of diagonals d .. d-BAND+1: operands on diagonals >= d+2, complete after the previous step
     if (dnew >= 0 && (n - 1 - d) % BAND == 0) {
       const int rows = n - d + BAND - 1;
@@ -537,7 +518,7 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
       if (dfin >= 0) band_outside_B(c, sh, bs, dfin, wide, tid);
       if (nick && tid < 128 && !(RP_DBG(c) & 64)) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
       if (dnew >= 0) band_interior_A<-1>(c, bs, dnew, tid, T);
-      if (tid == T - 1 && d - 1 >= TURN + 1) band_make_desc(bs.desc[(d - 1) & (NDESC - 1)], n, c.cp, d - 1, T);
+      if (tid == T - 1 && d - 1 >= TURN + 1) band_make_desc(bs.desc[(d - 1) & (NDESC - 1)], n, c.cp, d - 1, T, true);
     });
     if (dnew < 0) break;
     ex.phase(PH_CFAC, [&](int tid) {
