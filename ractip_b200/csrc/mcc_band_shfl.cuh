@@ -205,7 +205,10 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
       }
       // main part t = 0 .. tmax, a contiguous run per slice; the warp walks to lane 0's (largest) tmax
       const int tmax0 = __shfl_sync(0xffffffffu, tmax, 0);
-      if (tmax0 >= 0) {
+      // two strands: only inter-strand cells are finished in the outside pass (cross_lo / cross_hi): a warp whose
+      // rows all lie on strand 2 has nothing to sum
+      const bool pr_live = c.cp <= 0 || 1 + r0 + (warp - slice * sp.W) * HW < c.cp;
+      if (tmax0 >= 0 && pr_live) {
         const int per = (tmax0 + 1 + S - 1) / S;
         const int t_lo = slice * per;
         int t_hi = t_lo + per - 1;
@@ -257,7 +260,7 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
 #pragma unroll
         for (int e = 0; e < BAND; e++) {
           const int k = k0 + e, d = d0 - e;
-          cand[e] = k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) != 0;
+          cand[e] = k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) != 0 && (c.cp <= 0 || (k < c.cp && l >= c.cp));
           qbv[e] = cand[e] ? TB(c, T_QB, d, k) : 0.;
         }
 #pragma unroll
@@ -268,8 +271,10 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
       const int imax = k0 + (BAND - 1) - TURN - 3, imain = k0 - TURN - 3;
       // main part: B(e) = qm(i+1, k0+e-1) is the B(0) of the lane e places to the right, same step
       const int imain_hi = __shfl_sync(0xffffffffu, imain, HW - 1);   // largest among the owning lanes
+      // (two strands: a warp whose columns all lie on strand 1 has no inter-strand cell)
+      const bool ml_live = c.cp <= 0 || d0 - BAND + 2 + r0 + (warp - slice * sp.W) * HW + HW - 1 >= c.cp;
 #pragma unroll 1
-      for (int i = 1 + slice; i <= imain_hi; i += NB * S) {
+      for (int i = 1 + slice; ml_live && i <= imain_hi; i += NB * S) {
         double A[NB], b0[NB];
 #pragma unroll
         for (int u = 0; u < NB; u++) {

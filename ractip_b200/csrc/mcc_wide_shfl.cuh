@@ -145,7 +145,10 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
     for (int e = 0; e < W; e++) acc[e] = bv[e] = 0.;
     const int tmax0 = __shfl_sync(0xffffffffu, tmax, 0);
     const int tfirst = -(TURN + 1);
-    if (tmax0 >= tfirst && !(RP_DBG(c) & 2)) {
+    // two strands: only inter-strand cells are finished in the outside pass (cross_lo / cross_hi), so a warp whose
+    // rows all lie on strand 2 has nothing to sum (its zero partials are still written)
+    const bool pr_live = c.cp <= 0 || 1 + r0 + (warp - slice * sp.NW) * HWW < c.cp;
+    if (tmax0 >= tfirst && pr_live && !(RP_DBG(c) & 2)) {
       const int per = (tmax0 - tfirst + 1 + S - 1) / S;
       const int t_lo = tfirst + slice * per;
       int t_hi = t_lo + per - 1;
@@ -199,7 +202,7 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
 #pragma unroll
       for (int e = 0; e < W; e++) {
         const int k = k0 + e, d = d0 - e;
-        cand[e] = k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) != 0;
+        cand[e] = k > 2 && d > TURN && pair_type(base(c, k), base(c, l)) != 0 && (c.cp <= 0 || (k < c.cp && l >= c.cp));
         qbv[e] = cand[e] ? TB(c, T_QB, d, k) : 0.;
       }
 #pragma unroll
@@ -208,7 +211,9 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
     }
     const int ifar = k0 - 2;
     const int ifar_hi = __shfl_sync(0xffffffffu, ifar, HWW - 1);   // largest among the owning lanes
-    if (!(RP_DBG(c) & 2)) {
+    // (two strands: a warp whose columns all lie on strand 1 has no inter-strand cell)
+    const bool ml_live = c.cp <= 0 || d0 - W + 2 + r0 + (warp - slice * sp.NW) * HWW + HWW - 1 >= c.cp;
+    if (ml_live && !(RP_DBG(c) & 2)) {
 #pragma unroll 1
       for (int i = 1 + slice; i <= ifar_hi; i += NB * S) {
         double A[NB], b0[NB];
