@@ -119,7 +119,8 @@ uint64_t rp_model_digest(const rp_model* m);
 /* ------------------------------------------------------------------------ */
 typedef struct rp_pair {
   const char* s1; int n1;   /* first RNA, 5'->3', ACGU/T any case, not NUL-terminated-dependent */
-  const char* s2; int n2;   /* second RNA                                    */
+  const char* s2; int n2;   /* second RNA; n2 == 0 (s2 may be NULL): s1 alone, */
+                            /* only its bp/up sections are computed           */
 } rp_pair;
 
 /* options that change the probability stage (src/ractip.cpp:546-548,390,447) */
@@ -208,6 +209,22 @@ int rp_run_dense(rp_ctx* ctx, const rp_pair* pairs, int n_pairs,
 int rp_run_sparse(rp_ctx* ctx, const rp_pair* pairs, int n_pairs,
                   const rp_opts* opts, rp_rec* recs, size_t n_recs,
                   float* ups, size_t n_floats, rp_sparse_counts* counts);
+
+/* All GPUs of one box behind one handle (host threads over the single-device entry points): the batch is cut
+ * into contiguous blocks, pair k of n going to device k*G/n, and every device writes its block straight into
+ * the caller's one host buffer, in the layouts of rp_dense_plan / rp_sparse_plan for the WHOLE batch.  This is
+ * what the z-score loop of src/ractip.cpp:1638-1657 needs to use a multi-GPU box from one process.
+ * devices == NULL: devices 0 .. n_devices-1 (n_devices <= 0: every visible device). */
+typedef struct rp_multi rp_multi;
+int rp_multi_create(rp_multi** multi, const rp_model* m, const int* devices, int n_devices);
+int rp_multi_destroy(rp_multi* multi);
+int rp_multi_devices(const rp_multi* multi);
+const char* rp_multi_last_error(const rp_multi* multi);   /* multi may be NULL */
+int rp_multi_run_dense(rp_multi* multi, const rp_pair* pairs, int n_pairs,
+                       const rp_opts* opts, float* out, size_t out_floats);
+int rp_multi_run_sparse(rp_multi* multi, const rp_pair* pairs, int n_pairs,
+                        const rp_opts* opts, rp_rec* recs, size_t n_recs,
+                        rp_sparse_counts* counts);
 
 /* Device-resident batch (bench "value": inputs already in HBM). */
 typedef struct rp_batch rp_batch;

@@ -46,7 +46,23 @@ class ProbabilityStage {
     check(rp_create(&ctx_, model, device), nullptr);
     rp_opts_default(&opts_);
   }
-  ~ProbabilityStage() { rp_destroy(ctx_); }
+  // All (n_gpus <= 0) or the first n_gpus visible devices behind one stage: solve_batch() then cuts the batch
+  // into one contiguous block per device (rp_multi_*), which is how the z-score loop uses a multi-GPU box.
+  ProbabilityStage(const rp_model* model, int /*first_device*/, int n_gpus) {
+    rp_model m;
+    if (!model) {
+      check(rp_model_default(&m, 1), nullptr);
+      model = &m;
+    }
+    const int rc = rp_multi_create(&multi_, model, nullptr, n_gpus);
+    if (rc) throw std::runtime_error(std::string("ractip_prob: ") + rp_strerror(rc) + " -- " + rp_multi_last_error(nullptr));
+    rp_opts_default(&opts_);
+  }
+  ~ProbabilityStage() {
+    rp_destroy(ctx_);
+    rp_multi_destroy(multi_);
+  }
+  int devices() const { return multi_ ? rp_multi_devices(multi_) : 1; }
   ProbabilityStage(const ProbabilityStage&) = delete;
   ProbabilityStage& operator=(const ProbabilityStage&) = delete;
 
@@ -74,7 +90,12 @@ class ProbabilityStage {
     size_t total = 0;
     check(rp_dense_plan(pairs.data(), n, &opts_, lay.data(), &total), ctx_);
     std::vector<float> flat(total ? total : 1);
-    check(rp_run_dense(ctx_, pairs.data(), n, &opts_, flat.data(), flat.size()), ctx_);
+    if (multi_) {
+      const int rc = rp_multi_run_dense(multi_, pairs.data(), n, &opts_, flat.data(), flat.size());
+      if (rc) throw std::runtime_error(std::string("ractip_prob: ") + rp_strerror(rc) + " -- " + rp_multi_last_error(multi_));
+    } else {
+      check(rp_run_dense(ctx_, pairs.data(), n, &opts_, flat.data(), flat.size()), ctx_);
+    }
     out.assign(n, PairProbabilities());
     const int w = opts_.max_w > 0 ? opts_.max_w : 0;
     for (int k = 0; k < n; k++) {
@@ -88,13 +109,13 @@ class ProbabilityStage {
     }
   }
 
-  // RactIP::rnafold(fa, bp, offset, up, max_w), src/ractip.cpp:308-382.  The C ABI works on
-  // pairs; a lone sequence is paired with itself (one redundant two-strand problem).
+  // RactIP::rnafold(fa, bp, offset, up, max_w), src/ractip.cpp:308-382: a pair with an empty second
+  // sequence computes s1's sections only.  (The reference calls it with std::max(1, max_w_), :546.)
   void rnafold(const std::string& seq, VF& bp, VI& offset, VVF& up, unsigned max_w) {
     const int keep = opts_.max_w;
-    opts_.max_w = static_cast<int>(max_w);
+    opts_.max_w = static_cast<int>(max_w < 1 ? 1 : max_w);
     PairProbabilities r;
-    solve_probabilities(seq, seq, r);
+    solve_probabilities(seq, std::string(), r);
     opts_.max_w = keep;
     bp.swap(r.bp1);
     offset.swap(r.offset1);
@@ -122,6 +143,7 @@ class ProbabilityStage {
     for (int i = 0; i < rows; i++) out[i].assign(src + static_cast<size_t>(i) * cols, src + static_cast<size_t>(i + 1) * cols);
   }
   rp_ctx* ctx_ = nullptr;
+  rp_multi* multi_ = nullptr;
   rp_opts opts_;
 };
 

@@ -102,6 +102,8 @@ EXPORTS = [
     "rp_batch_fetch_dense", "rp_batch_fetch_sparse", "rp_batch_sparse_device", "rp_batch_fetch_logz",
     "rp_batch_destroy", "rp_last_timing", "rp_measure_peaks", "rp_zscore_shuffles",
     "rp_alg_flops_mcc", "rp_version", "rp_kernel_plan",
+    "rp_multi_create", "rp_multi_destroy", "rp_multi_devices", "rp_multi_last_error", "rp_multi_run_dense",
+    "rp_multi_run_sparse",
     # include/ractip_ip.h (host-side consumer: integer programme, energy evaluation)
     "rp_ip_opts_default", "rp_ip_build", "rp_ip_build_sparse", "rp_ip_build_ss", "rp_ip_dims", "rp_ip_export",
     "rp_ip_decode", "rp_ip_free", "rp_energy_of_structure", "rp_energy_of_duplex",
@@ -152,6 +154,12 @@ def load() -> C.CDLL:
         "rp_alg_flops_mcc": (C.c_double, [i]),
         "rp_version": (C.c_char_p, []),
         "rp_kernel_plan": (i, [i, sz, P(sz)]),
+        "rp_multi_create": (i, [P(vp), P(RpModel), P(i), i]),
+        "rp_multi_destroy": (i, [vp]),
+        "rp_multi_devices": (i, [vp]),
+        "rp_multi_last_error": (C.c_char_p, [vp]),
+        "rp_multi_run_dense": (i, [vp, P(RpPair), i, P(RpOpts), vp, sz]),
+        "rp_multi_run_sparse": (i, [vp, P(RpPair), i, P(RpOpts), vp, sz, vp]),
         "rp_ip_opts_default": (None, [P(RpIpOpts)]),
         "rp_ip_build": (i, [P(RpIpOpts), i, i, vp, vp, vp, vp, vp, P(vp)]),
         "rp_ip_build_sparse": (i, [P(RpIpOpts), i, i, vp, i, vp, i, vp, i, vp, i, vp, i, P(vp)]),

@@ -33,14 +33,6 @@ struct rp_ctx {
   int ctas_per_sm1 = 0;      // general kernel, 128-register build (one CTA per SM: long problems)
   int mcc_long_n = 700;      // problems at least this long run the 128-register build (RP_MCC_LONG_N)
   int mcc_wide = 10;         // ... with split-sum bands of this many diagonals (RP_MCC_WIDE: 5, 10, 15)
-  int ls_threads = RP_LS_THREADS;
-  int ls_ctas_per_sm = 0;
-  // The batch-lockstep schedule is OFF by default: measured on B200 (1000 MicA x ompA shuffles) it
-  // runs 113 ms against 80 ms for the general kernel -- interleaving 8 problems per CTA puts their
-  // interior-loop bands (8 x 161 KB) out of L1's reach and the dense (uncompacted) interior sums
-  // then stream ~600 MB per pair through L2.  RP_LOCKSTEP=1 enables it (kept for the next round:
-  // it needs shared-memory staging / register tiling of the interior window to pay off).
-  bool lockstep = false;
   // Band kernel (mcc_band.h): problems whose 32-diagonal ring fits in shared memory.  Class L: 512
   // threads, one CTA per SM; class S: 256 threads, two CTAs per SM.  RP_BAND=0 disables it (A/B aid).
   bool band = true;
@@ -64,6 +56,12 @@ struct rp_ctx {
   // milliseconds and cudaFree synchronises the device: fatal for the one-shot host calls)
   std::vector<std::pair<void*, size_t>> pool_free;
   std::vector<std::pair<void*, size_t>> pool_live;
+  // lifetime: batches hold a reference; rp_destroy with batches alive only marks the context closed, the last
+  // rp_batch_destroy tears it down (a batch handle never outlives the memory it points into)
+  int live_batches = 0;
+  bool closing = false;
+  cudaStream_t ws_stream = nullptr;   // stream of the last launch that used the workspace / a pooled buffer
+  long long* d_prof = nullptr;        // RP_PROFILE counters (per context: per device)
 };
 
 struct rp_batch {
@@ -82,19 +80,13 @@ struct rp_batch {
   uint8_t* d_seq = nullptr;
   Problem* d_probs = nullptr;
   int* d_order = nullptr;
-  // lockstep groups (same-shape problems, RP_LS_G per CTA)
-  std::vector<rp::GroupDev> groups;
   int mcc_minb = 2;           // register budget of the general kernel for this batch (kernels.h)
-  int grid_cached = -1, ls_grid_cached = -1;  // launch shapes, fixed at the first run (cudaMemGetInfo is slow)
+  int grid_cached = -1;       // launch shape, fixed at the first run (cudaMemGetInfo is slow)
   int n_general = 0;          // problems left to the general kernel + duplex (entries of order after the band classes)
   // band classes: order = [class L | class S | general]
   int n_band[2] = {0, 0};
   int band_maxn[2] = {0, 0};
   int band_grid[2] = {-1, -1};
-  int ls_maxn = 0;
-  rp::GroupDev* d_groups = nullptr;
-  uint8_t* d_gseq = nullptr;
-  int* d_gcounter = nullptr;
   int* d_counter = nullptr;
   float* d_dense = nullptr;
   // Split fetch (uniform batches whose problems fall into both band classes, nothing else launched): sections of a
@@ -103,11 +95,12 @@ struct rp_batch {
   bool split_fetch = false;
   size_t pair_stride = 0;
   std::vector<std::pair<size_t, size_t>> sect_long, sect_short;
-  float* dense_out = nullptr;   // set by rp_run_dense: the caller's pinned host buffer, written by the kernels directly
   double* d_logz = nullptr;
   // sparse
   std::vector<rp_sparse_layout> slayout;
   size_t total_recs = 0, total_upf = 0;
+  bool has_single = false;              // some pair has n2 == 0: its unused output sections are zero-filled once
+  cudaStream_t last_stream = nullptr;   // stream the batch last ran on (rp_set_stream may have moved the context on)
   rp::SparsePair* d_spairs = nullptr;
   rp_rec* d_recs = nullptr;
   float* d_ups = nullptr;
@@ -136,23 +129,38 @@ size_t bp_len(int L) { return (size_t)(L + 1) * (size_t)(L + 2) / 2; }
 int check_pairs(const rp_pair* pairs, int n_pairs, const rp_opts* opts) {
   if (!pairs || !opts || n_pairs < 0) return RP_ERR_ARG;
   for (int p = 0; p < n_pairs; p++)
-    if (!pairs[p].s1 || !pairs[p].s2 || pairs[p].n1 < 1 || pairs[p].n2 < 1) return RP_ERR_ARG;
+    if (!pairs[p].s1 || pairs[p].n1 < 1 || pairs[p].n2 < 0 || (pairs[p].n2 > 0 && !pairs[p].s2)) return RP_ERR_ARG;   // n2 == 0: s1 alone
   return RP_OK;
 }
 
 int ensure_workspace(rp_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return RP_OK;
   if (ctx->ws) {
+    if (ctx->ws_stream && ctx->ws_stream != ctx->stream) CU(cudaStreamSynchronize(ctx->ws_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaFree(ctx->ws));
     ctx->ws = nullptr;
     ctx->ws_bytes = 0;
   }
-  CU(cudaMalloc(&ctx->ws, bytes));
+  cudaError_t e = cudaMalloc(&ctx->ws, bytes);
+  if (e != cudaSuccess) {   // give the cached buffers of destroyed batches back to the driver and retry once
+    cudaGetLastError();
+    for (auto& f : ctx->pool_free) cudaFree(f.first);
+    ctx->pool_free.clear();
+    e = cudaMalloc(&ctx->ws, bytes);
+  }
+  if (e != cudaSuccess) { ctx->ws = nullptr; return fail(ctx, RP_ERR_CUDA, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e)); }
   ctx->ws_bytes = bytes;
   return RP_OK;
 }
 
+size_t pool_cached_bytes(const rp_ctx* ctx) {
+  size_t t = 0;
+  for (const auto& f : ctx->pool_free) t += f.second;
+  return t;
+}
+
+size_t pool_cached_bytes(const rp_ctx* ctx);
 cudaError_t pool_alloc(rp_ctx* ctx, void** out, size_t bytes) {
   bytes = std::max<size_t>(bytes, 256);
   int best = -1;
@@ -183,6 +191,11 @@ void pool_release(rp_ctx* ctx, void* p) {
     if (ctx->pool_live[k].first == p) {
       ctx->pool_free.push_back(ctx->pool_live[k]);
       ctx->pool_live.erase(ctx->pool_live.begin() + k);
+      // keep the cache bounded: beyond 64 buffers or 8 GB the oldest entries go back to the driver
+      while (ctx->pool_free.size() > 64 || pool_cached_bytes(ctx) > ((size_t)8 << 30)) {
+        cudaFree(ctx->pool_free.front().first);
+        ctx->pool_free.erase(ctx->pool_free.begin());
+      }
       return;
     }
   cudaFree(p);
@@ -200,7 +213,7 @@ int grid_for(const rp_ctx* ctx, int nprob, size_t slot_bytes, int minb) {
   // milliseconds: not asked when the workspace the context already holds is large enough.
   size_t free_b = 0, total_b = 0;
   if ((size_t)g * slot_bytes > ctx->ws_bytes && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-    size_t budget = (free_b + ctx->ws_bytes) / 10 * 7;
+    size_t budget = (free_b + ctx->ws_bytes + pool_cached_bytes(ctx)) / 10 * 7;   // cached buffers are freed on demand
     while (g > 1 && (size_t)g * slot_bytes > budget) g--;
   }
   return g;
@@ -387,12 +400,6 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
   if (const char* e = std::getenv("RP_MCC_WIDE")) ctx->mcc_wide = std::atoi(e);
   ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads, 2, ctx->mcc_wide);
   ctx->ctas_per_sm1 = rp::mcc_max_ctas_per_sm(ctx->threads, 1, ctx->mcc_wide);
-  if (const char* e = std::getenv("RP_LS_THREADS")) {
-    int t = std::atoi(e) / 32 * 32;
-    if (t >= 32 && t <= RP_LS_THREADS) ctx->ls_threads = t;
-  }
-  if (const char* e = std::getenv("RP_LOCKSTEP")) ctx->lockstep = std::atoi(e) != 0;
-  ctx->ls_ctas_per_sm = rp::lockstep_max_ctas_per_sm(ctx->ls_threads);
   if (ctx->ctas_per_sm < 1)
     return bail(RP_ERR_CUDA, "rp_create: kernel image not loadable on this device (built for sm_100a)");
   *out = ctx;
@@ -401,12 +408,17 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
 
 int rp_destroy(rp_ctx* ctx) {
   if (!ctx) return RP_OK;
+  if (ctx->live_batches > 0) {   // batches still point into this context: the last rp_batch_destroy finishes the job
+    ctx->closing = true;
+    return RP_OK;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->ws) cudaFree(ctx->ws);
   for (auto& f : ctx->pool_free) cudaFree(f.first);
   for (auto& f : ctx->pool_live) cudaFree(f.first);
   if (ctx->d_model) cudaFree(ctx->d_model);
+  if (ctx->d_prof) cudaFree(ctx->d_prof);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
@@ -440,13 +452,19 @@ int rp_batch_destroy(rp_batch* b) {
   if (!b) return RP_OK;
   if (b->ctx) {
     cudaSetDevice(b->ctx->device);
+    if (b->last_stream && b->last_stream != b->ctx->stream) cudaStreamSynchronize(b->last_stream);
     cudaStreamSynchronize(b->ctx->stream);
   }
   if (b->ctx) {
     rp_ctx* ctx = b->ctx;
     for (void* p : {(void*)b->d_seq, (void*)b->d_probs, (void*)b->d_order, (void*)b->d_counter, (void*)b->d_dense,
-                    (void*)b->d_logz, (void*)b->d_groups, (void*)b->d_gseq, (void*)b->d_gcounter, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
+                    (void*)b->d_logz, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
       pool_release(ctx, p);
+    ctx->live_batches--;
+    if (ctx->closing && ctx->live_batches == 0) {
+      delete b;
+      return rp_destroy(ctx);
+    }
   }
   delete b;
   return RP_OK;
@@ -463,6 +481,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   CU(cudaSetDevice(ctx->device));
   rp_batch* b = new rp_batch;
   b->ctx = ctx;
+  ctx->live_batches++;
   b->n_pairs = n_pairs;
   b->opts = *opts;
   b->layout.resize(n_pairs);
@@ -503,6 +522,15 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     a.which = 1; a.seq_off = off2; a.n = pr.n2;
     a.out_bp = (long long)L.bp2; a.out_up = w > 0 ? (long long)L.up2 : -1;
     b->probs.push_back(a);
+    if (pr.n2 == 0) {   // a lone sequence (RactIP::rnafold on its own, src/ractip.cpp:1599-1601): no second fold, no hybridization
+      Problem none = q;
+      none.kind = rp::KIND_LINEAR; none.which = 2; none.n = 0;
+      b->probs.push_back(none);
+      b->maxn = std::max(b->maxn, pr.n1);
+      b->alg_flops += rp_alg_flops_mcc(pr.n1);
+      b->has_single = true;
+      continue;
+    }
     // rnaduplex(fa1, fa2, hp_)  src/ractip.cpp:548
     Problem c = q;
     c.which = 2; c.seq_off = off12; c.out_hp = (long long)L.hp;
@@ -519,9 +547,6 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     b->maxn = std::max(b->maxn, std::max(pr.n1, pr.n2));
     b->alg_flops += rp_alg_flops_mcc(pr.n1) + rp_alg_flops_mcc(pr.n2);
   }
-  // Same-shape problems go to the lockstep kernel in groups of RP_LS_G: the shuffles of a z-score
-  // batch all share the lengths of the original pair.  Everything else (ragged batches, leftovers
-  // of a shape with fewer than RP_LS_G problems, --duplex) goes to the general kernel.
   // LPT cost.  Band-kernel lengths (measured, profiles/r01b_phase_ablation.txt): ~30 k cycles per unit of
   // length for the two wavefronts (fixed cost per diagonal) + ~160 n^2 for the unpaired-window pass.
   auto cost = [&](const Problem& q) {
@@ -530,50 +555,9 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
       return 3.0e4 * q.n + ((q.kind == rp::KIND_LINEAR && q.max_w > 0) ? 160.0 * q.n * q.n : 0.0);
     return (double)q.n * q.n * (q.n + 1500.0);
   };
-  std::vector<char> in_group(b->probs.size(), 0);
-  std::vector<uint8_t> gseq;
-  if (ctx->lockstep && ctx->ls_ctas_per_sm > 0) {
-    std::vector<int> idx(b->probs.size());
-    std::iota(idx.begin(), idx.end(), 0);
-    auto key_less = [&](int x, int y) {
-      const Problem &p = b->probs[x], &q = b->probs[y];
-      if (p.kind != q.kind) return p.kind < q.kind;
-      if (p.n != q.n) return p.n > q.n;
-      if (p.cp != q.cp) return p.cp < q.cp;
-      return x < y;
-    };
-    std::stable_sort(idx.begin(), idx.end(), key_less);
-    size_t a = 0;
-    while (a < idx.size()) {
-      size_t e2 = a;
-      const Problem& p0 = b->probs[idx[a]];
-      while (e2 < idx.size() && b->probs[idx[e2]].kind == p0.kind && b->probs[idx[e2]].n == p0.n && b->probs[idx[e2]].cp == p0.cp) e2++;
-      if (p0.kind != rp::KIND_DUPLEX && e2 - a >= (size_t)RP_LS_G && p0.n >= 5) {
-        for (size_t g0 = a; g0 < e2; g0 += RP_LS_G) {
-          rp::GroupDev grp;
-          grp.n = p0.n;
-          grp.seq_off = (long long)gseq.size();
-          gseq.resize(gseq.size() + (size_t)(p0.n + 2) * RP_LS_G, 0);
-          for (int g = 0; g < RP_LS_G; g++) {
-            const bool live = g0 + g < e2;
-            const int pi = idx[live ? g0 + g : e2 - 1];
-            grp.prob[g] = live ? pi : -1;
-            if (live) in_group[pi] = 1;
-            const Problem& q = b->probs[pi];
-            for (int i = 1; i <= q.n; i++) gseq[grp.seq_off + (size_t)i * RP_LS_G + g] = seq[q.seq_off + i - 1];
-          }
-          b->groups.push_back(grp);
-          b->ls_maxn = std::max(b->ls_maxn, p0.n);
-        }
-      }
-      a = e2;
-    }
-    // groups are already ordered by decreasing n within a kind; put the costliest first overall
-    std::stable_sort(b->groups.begin(), b->groups.end(), [](const rp::GroupDev& x, const rp::GroupDev& y) { return x.n > y.n; });
-  }
   // general queue: most expensive first (LPT), ties by index for determinism
   for (size_t k = 0; k < b->probs.size(); k++)
-    if (!in_group[k]) b->order.push_back((int)k);
+    if (b->probs[k].n > 0) b->order.push_back((int)k);
   std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) { return cost(b->probs[x]) > cost(b->probs[y]); });
   if (ctx->band) {
     // class of a problem: 0 = L (512 threads, ring needs more than half an SM), 1 = S (256 threads, 2 CTAs/SM), -1 = general
@@ -606,7 +590,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   // everything the long class wrote can cross PCIe meanwhile.  Needs a uniform batch (the z-score shuffle batch:
   // every pair has the lengths of the original pair) so that the sections are strided 2-D copies.
   b->split_fetch = false;
-  if (ctx->band && n_pairs >= 2 && b->n_band[0] > 0 && b->n_band[1] > 0 && b->n_general == 0 && b->groups.empty() &&
+  if (ctx->band && n_pairs >= 2 && b->n_band[0] > 0 && b->n_band[1] > 0 && b->n_general == 0 &&
       !std::getenv("RP_NO_SPLIT_FETCH")) {
     bool uniform = true;
     for (int p = 1; p < n_pairs && uniform; p++) uniform = pairs[p].n1 == pairs[0].n1 && pairs[p].n2 == pairs[0].n2;
@@ -638,9 +622,6 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   if ((e = pool_alloc(ctx, &b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
   if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
   if ((e = pool_alloc(ctx, &b->d_counter, 4 * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
-  if ((e = pool_alloc(ctx, &b->d_gcounter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc gcounter");
-  if ((e = pool_alloc(ctx, &b->d_groups, std::max<size_t>(1, b->groups.size()) * sizeof(rp::GroupDev))) != cudaSuccess) return bail(e, "cudaMalloc groups");
-  if ((e = pool_alloc(ctx, &b->d_gseq, gseq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc gseq");
   if ((e = pool_alloc(ctx, &b->d_dense, std::max<size_t>(1, b->total_floats) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense");
   if ((e = pool_alloc(ctx, &b->d_logz, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logz");
   cudaStream_t st = ctx->stream;
@@ -649,10 +630,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     if ((e = cudaMemcpyAsync(b->d_probs, b->probs.data(), np * sizeof(Problem), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D probs");
     if (!b->order.empty() && (e = cudaMemcpyAsync(b->d_order, b->order.data(), b->order.size() * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D order");
   }
-  if (!b->groups.empty()) {
-    if ((e = cudaMemcpyAsync(b->d_groups, b->groups.data(), b->groups.size() * sizeof(rp::GroupDev), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D groups");
-    if ((e = cudaMemcpyAsync(b->d_gseq, gseq.data(), gseq.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "H2D gseq");
-  }
+  if (b->has_single && (e = cudaMemsetAsync(b->d_dense, 0, std::max<size_t>(1, b->total_floats) * sizeof(float), st)) != cudaSuccess) return bail(e, "memset dense");
   if ((e = cudaMemsetAsync(b->d_logz, 0, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double), st)) != cudaSuccess) return bail(e, "memset logz");
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "sync");  // host vectors go out of scope
   *out = b;
@@ -670,23 +648,6 @@ int rp_batch_run(rp_batch* b) {
   const size_t slot_bytes = b->slot_doubles * sizeof(double);
   if (b->grid_cached < 0) b->grid_cached = b->n_general > 0 ? grid_for(ctx, b->n_general, std::max<size_t>(slot_bytes, 8), b->mcc_minb) : 0;
   const int grid = b->grid_cached;
-  // lockstep: one CTA slot holds RP_LS_G problem workspaces
-  const int ngroups = (int)b->groups.size();
-  const size_t ls_slot_doubles = ngroups ? rp::slot_doubles(b->ls_maxn) * RP_LS_G : 0;
-  int ls_grid = b->ls_grid_cached < 0 ? 0 : b->ls_grid_cached;
-  if (ngroups && b->ls_grid_cached < 0) {
-    ls_grid = std::min(ngroups, ctx->sm_count * std::max(1, ctx->ls_ctas_per_sm));
-    if (const char* e = std::getenv("RP_GRID")) {
-      int v = std::atoi(e);
-      if (v >= 1 && v < ls_grid) ls_grid = v;
-    }
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      size_t budget = (free_b + ctx->ws_bytes) / 10 * 7;
-      while (ls_grid > 1 && (size_t)ls_grid * ls_slot_doubles * sizeof(double) > budget) ls_grid--;
-    }
-  }
-  b->ls_grid_cached = ls_grid;
   // the two kernels run one after the other on the stream and share the workspace
   // band classes: grid = resident CTAs, one workspace slot each, placed after the general kernel's slots
   const int band_threads[2] = {512, 256};
@@ -705,7 +666,7 @@ int rp_batch_run(rp_batch* b) {
       }
     }
   }
-  const size_t gen_bytes = std::max((size_t)grid * slot_bytes, (size_t)ls_grid * ls_slot_doubles * sizeof(double));
+  const size_t gen_bytes = (size_t)grid * slot_bytes;
   const size_t bandL_bytes = (size_t)b->band_grid[0] * band_slot[0] * sizeof(double);
   const size_t bandS_bytes = (size_t)b->band_grid[1] * band_slot[1] * sizeof(double);
   int rc = ensure_workspace(ctx, gen_bytes + bandL_bytes + bandS_bytes);
@@ -714,12 +675,10 @@ int rp_batch_run(rp_batch* b) {
   rp::BatchDev d;
   d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order + n_bandall; d.nprob = b->n_general;
   d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = std::max(grid, 1);
-  d.dense = b->dense_out ? b->dense_out : b->d_dense; d.logz = b->d_logz;
-  d.groups = b->d_groups; d.ngroups = ngroups; d.gcounter = b->d_gcounter; d.gseq = b->d_gseq;
-  d.ls_slot_stride = ls_slot_doubles;
+  d.dense = b->d_dense; d.logz = b->d_logz;
   d.prof = nullptr;
   d.dbg = std::getenv("RP_DEBUG_SKIP") ? std::atoi(std::getenv("RP_DEBUG_SKIP")) : 0;
-  static long long* d_prof = nullptr;
+  long long*& d_prof = ctx->d_prof;
   const bool profile = std::getenv("RP_PROFILE") != nullptr;
   if (profile) {
     if (!d_prof) CU(cudaMalloc(&d_prof, 64 * sizeof(long long)));
@@ -727,8 +686,9 @@ int rp_batch_run(rp_batch* b) {
     d.prof = d_prof;
   }
   cudaStream_t st = ctx->stream;
+  b->last_stream = st;
+  ctx->ws_stream = st;
   CU(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), st));
-  CU(cudaMemsetAsync(b->d_gcounter, 0, sizeof(int), st));
   CU(cudaEventRecord(ctx->ev[0], st));
   int launches = 0;
   {
@@ -757,10 +717,6 @@ int rp_batch_run(rp_batch* b) {
       ws_off += (size_t)b->band_grid[k] * band_slot[k];
       ord_off += b->n_band[k];
     }
-  }
-  if (ngroups > 0) {
-    CU(rp::launch_lockstep(d, ls_grid, ctx->ls_threads, st));
-    launches++;
   }
   if (b->n_mcc > 0) {
     // Few long problems (a single long pair, not a shuffle batch): one problem per thread-block cluster, so
@@ -967,27 +923,8 @@ int rp_run_dense(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opts* 
     rp_batch_destroy(b);
     return fail(ctx, RP_ERR_CAPACITY, "rp_run_dense: buffer too small");
   }
-  // RP_ZERO_COPY=1: a pinned (page-locked, mapped) host buffer is written by the kernels themselves,
-  // every finished problem streaming its fp32 matrices over PCIe while the others still compute.
-  // OFF by default: measured on B200 (1000 MicA x ompA shuffles, 102 MB of outputs) the output phases
-  // of a CTA then run at PCIe store latency and the step takes 60.2 ms against 57.2 ms for the
-  // staged copy (kernels 54.3 ms + one 2 ms D2H).
-  cudaPointerAttributes attr;
-  const bool zero_copy = b->total_floats > 0 && std::getenv("RP_ZERO_COPY") &&
-                         cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-                         attr.devicePointer != nullptr;
-  cudaGetLastError();
-  if (zero_copy) b->dense_out = static_cast<float*>(attr.devicePointer);
   rc = rp_batch_run(b);
-  if (!rc && zero_copy) {
-    cudaEventRecord(ctx->ev[2], ctx->stream);
-    cudaEventRecord(ctx->ev[3], ctx->stream);
-    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = fail(ctx, RP_ERR_CUDA, std::string("rp_run_dense: ") + cudaGetErrorString(e));
-    ctx->timed_copies = true;
-  } else if (!rc) {
-    rc = rp_batch_fetch_dense(b, out, out_floats);
-  }
+  if (!rc) rc = rp_batch_fetch_dense(b, out, out_floats);
   rp_timing t;
   if (!rc) rp_last_timing(ctx, &t);
   rp_batch_destroy(b);

@@ -157,52 +157,6 @@ __global__ void __launch_bounds__(T, MINB) mcc_band_kernel(BatchDev b) {
   }
 }
 
-// lockstep_kernel: one CTA per GROUP of RP_LS_G problems of identical shape (the shuffles of a
-// z-score batch all have the lengths of the original pair).  Lane = problem: thread tid works
-// for problem tid % G and computes whole cells of it, so there are no partial sums, no cell
-// compaction and a single barrier per anti-diagonal; the group's tables are interleaved element
-// by element, which makes every load of a warp (4 neighbouring cells x 8 problems) one
-// contiguous 256-byte run.  Persistent CTAs pull groups from a cost-ordered queue.
-template <int G>
-__global__ void __launch_bounds__(RP_LS_THREADS, RP_LS_MIN_CTAS) lockstep_kernel(BatchDev b) {
-  extern __shared__ double smem_raw[];
-  __shared__ int s_next;
-  __shared__ Problem s_prob[G];
-  CtaExec ex;
-  ex.prof = b.prof;
-  Shared sh;
-  carve_shared(sh, smem_raw, blockDim.x);
-  const int g = threadIdx.x % G;
-  for (;;) {
-    if (threadIdx.x == 0) s_next = atomicAdd(b.gcounter, 1);
-    __syncthreads();
-    const int q = s_next;
-    if (q >= b.ngroups) break;
-    const GroupDev& grp = b.groups[q];
-    if (threadIdx.x < G) {
-      int src = grp.prob[threadIdx.x];
-      Problem p;
-      if (src >= 0) {
-        p = b.probs[src];
-      } else {  // padding lane: recompute the last real problem, write nothing
-        int last = 0;
-        for (int k = 0; k < G; k++)
-          if (grp.prob[k] >= 0) last = grp.prob[k];
-        p = b.probs[last];
-        p.pair = -1;
-        p.out_bp = p.out_up = p.out_hp = -1;
-      }
-      s_prob[threadIdx.x] = p;
-    }
-    __syncthreads();
-    LCtx<G> c;
-    bind_lctx<G>(c, b.model, b.gseq + grp.seq_off, s_prob[g], b.ws + (size_t)blockIdx.x * b.ls_slot_stride, g);
-    c.dbg = b.dbg;
-    solve_lockstep<G>(ex, [&](int) -> LCtx<G>& { return c; }, s_prob, b.gseq + grp.seq_off, b.dense, b.logz, sh);
-    __syncthreads();
-  }
-}
-
 // ---------------------------------------------------------------------------
 // pf_duplex (--duplex): log-space forward/backward over pure duplexes.
 // Restates reference src/pf_duplex.c:128-164 (fw), :166-206 (bk), :97-103 (pr)
@@ -538,20 +492,6 @@ cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, c
   MccKernel k = band_kernel(threads);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<grid, threads, smem, st>>>(b);
-  return cudaGetLastError();
-}
-
-int lockstep_max_ctas_per_sm(int threads) {
-  int n = 0;
-  size_t smem = shared_bytes(threads);
-  cudaFuncSetAttribute(lockstep_kernel<RP_LS_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lockstep_kernel<RP_LS_G>, threads, smem) != cudaSuccess) return 0;
-  return n;
-}
-
-cudaError_t launch_lockstep(const BatchDev& b, int grid, int threads, cudaStream_t st) {
-  size_t smem = shared_bytes(threads);
-  lockstep_kernel<RP_LS_G><<<grid, threads, smem, st>>>(b);
   return cudaGetLastError();
 }
 

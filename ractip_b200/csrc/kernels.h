@@ -15,25 +15,7 @@
 #ifndef RP_MCC_MIN_CTAS
 #define RP_MCC_MIN_CTAS 2
 #endif
-// batch-lockstep kernel: RP_LS_G same-shape problems per CTA
-#ifndef RP_LS_G
-#define RP_LS_G 8
-#endif
-#ifndef RP_LS_THREADS
-#define RP_LS_THREADS 512
-#endif
-#ifndef RP_LS_MIN_CTAS
-#define RP_LS_MIN_CTAS 2
-#endif
-
 namespace rp {
-
-// one lockstep group: RP_LS_G problems of identical (kind, n, cp, max_w, n1, n2)
-struct GroupDev {
-  int n;
-  long long seq_off;        // offset of the group's interleaved sequences S[i*G+g] in BatchDev::gseq
-  int prob[RP_LS_G];        // problem indices; -1 = padding lane (repeats the last real problem, writes nothing)
-};
 
 struct BatchDev {
   const DevModel* model;
@@ -47,12 +29,6 @@ struct BatchDev {
   int nslots;
   float* dense;            // dense fp32 outputs (reference layouts)
   double* logz;            // 3 per pair, may be null
-  // lockstep part of the batch
-  const GroupDev* groups;
-  int ngroups;
-  int* gcounter;           // group-queue head
-  const uint8_t* gseq;     // interleaved sequences of all groups
-  size_t ls_slot_stride;   // doubles per lockstep CTA slot (RP_LS_G problem workspaces)
   long long* prof;         // 64 counters (cycles, calls per phase id) or null
   int dbg;                 // RP_DEBUG_SKIP bits (tuning aid; results are wrong when set)
 };
@@ -85,8 +61,6 @@ cudaError_t launch_mcc(const BatchDev& b, int grid, int threads, int minb, int w
 cudaError_t launch_mcc_cluster(const BatchDev& b, int nclusters, int ctas, int threads, cudaStream_t st);
 int band_max_ctas_per_sm(int threads, size_t smem);   // threads = 256 (2 CTAs/SM) or 512 (1 CTA/SM)
 cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, cudaStream_t st);
-int lockstep_max_ctas_per_sm(int threads);
-cudaError_t launch_lockstep(const BatchDev& b, int grid, int threads, cudaStream_t st);
 cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st);
 cudaError_t launch_sparse(const SparseDev& s, int n_pairs, bool with_ups, cudaStream_t st);
 cudaError_t launch_peak_fp64(double* out, int grid, int iters, cudaStream_t st);

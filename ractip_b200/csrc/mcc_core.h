@@ -18,13 +18,6 @@
 //   sum_k A(i,k-1)*B(k,j)  ->  sum_a A[a][i] * B[d-1-a][i+1+a]
 //   interior rows          ->  sum_u2 g[u1][u2] * B[d-2-u1-u2][i+1+u1]
 //
-// Two ways of laying problems out, behind the same code (the context type C):
-//   Ctx      one problem per CTA, elements contiguous; work of a cell is SLICED
-//            over threads (general kernel: any mix of lengths).
-//   LCtx<G>  G problems of identical shape interleaved element by element
-//            (element e of problem g at e*G+g): lane = problem, a thread does
-//            WHOLE cells of its own problem (batch-lockstep kernel: the shuffle
-//            batch, where every problem has the same lengths).
 #ifndef RP_MCC_CORE_H
 #define RP_MCC_CORE_H
 
@@ -92,7 +85,7 @@ RP_HD size_t table_elems(int n) { return (size_t)n * (size_t)(n + 1) + 8; }
 RP_HD size_t vector_elems(int n) { return (size_t)n + 8; }
 RP_HD size_t slot_doubles(int n) { return T_COUNT * table_elems(n) + V_COUNT * vector_elems(n); }
 
-// one problem, contiguous elements
+// one problem per CTA (or cluster), elements contiguous; the work of a cell is sliced over threads
 struct Ctx {
   const DevModel* M;
   const uint8_t* S;   // S[1..n]; low 3 bits base code 0..4, bit 3 = "letter is not A/C/G/U"
@@ -119,25 +112,6 @@ struct Ctx {
   RP_HD int sraw(int i) const { return S[i]; }
 };
 
-// G problems of identical (n, cp), interleaved: element e of lane g at e*G+g
-template <int G>
-struct LCtx {
-  const DevModel* M;
-  const uint8_t* S;   // S[i*G] of this lane (pointer already offset by the lane)
-  int n, cp, ld, kind, max_w;
-  double* ws;         // group workspace, already offset by the lane
-  size_t te, ve;
-  double invZ;
-  int dbg;
-  long long* prof;
-  RP_HD double& tb(int t, int d, int i) const { return ws[((size_t)t * te + (size_t)d * ld + i) * G]; }
-  RP_HD double* ptr(int t, int d, int i) const { return ws + ((size_t)t * te + (size_t)d * ld + i) * G; }
-  RP_HD double& v(int vv, int k) const { return ws[((size_t)T_COUNT * te + (size_t)vv * ve + k) * G]; }
-  RP_HD int dstep() const { return ld * G; }
-  RP_HD int pstep() const { return G; }
-  RP_HD int sraw(int i) const { return S[(size_t)i * G]; }
-};
-
 RP_HD void bind_ctx(Ctx& c, const DevModel* M, const uint8_t* S, const Problem& p, double* ws) {
   c.M = M; c.S = S; c.n = p.n; c.cp = p.cp; c.ld = p.n + 1; c.kind = p.kind; c.max_w = p.max_w;
   c.ws = ws; c.te = (unsigned)table_elems(p.n); c.ve = (unsigned)vector_elems(p.n);
@@ -145,15 +119,6 @@ RP_HD void bind_ctx(Ctx& c, const DevModel* M, const uint8_t* S, const Problem& 
   c.dbg = 0;
   c.prof = nullptr;
 }
-template <int G>
-RP_HD void bind_lctx(LCtx<G>& c, const DevModel* M, const uint8_t* S_group, const Problem& p, double* ws_group, int g) {
-  c.M = M; c.S = S_group + g; c.n = p.n; c.cp = p.cp; c.ld = p.n + 1; c.kind = p.kind; c.max_w = p.max_w;
-  c.ws = ws_group + g; c.te = table_elems(p.n); c.ve = vector_elems(p.n);
-  c.invZ = 0;
-  c.dbg = 0;
-  c.prof = nullptr;
-}
-
 #define TB(c, t, d, i) ((c).tb(t, d, i))
 // store of a value that is not read again soon (qb, out, class tables, outputs): evict-first, so that
 // it does not displace the history tables in L2
@@ -179,7 +144,7 @@ constexpr int BAND = TURN + 2;
 constexpr int WIDE_MAX = 15;
 
 // CTA-shared scratch (CUDA shared memory; a heap block in the host emulation)
-constexpr int RP_SMEM_SEQ = 4096;  // sequence bytes staged in shared memory (n+2 general, (n+2)*G lockstep)
+constexpr int RP_SMEM_SEQ = 4096;  // sequence bytes staged in shared memory (n+2)
 struct Shared {
   int T;
   double* part;     // [2*W][T] partial sums of the current phase (general kernel; W = width of its bands)
@@ -480,8 +445,7 @@ RP_HD ISplit make_isplit(const Ctx& c, int d, int i0, int C, int T) {
 }
 
 // ---------------------------------------------------------------------------
-// prologue.  (ct, nct) = index and number of the threads that share one problem:
-// (tid, T) in the general kernel, (tid/G, T/G) in the lockstep kernel.
+// prologue.  (ct, nct) = index and number of the threads that share one problem.
 // ---------------------------------------------------------------------------
 RP_HD void load_shared_model(const DevModel& M, const Shared& sh, int tid) {
   for (int x = tid; x < (MAXLOOP + 1) * GROW_LD; x += sh.T) sh.grow[x] = M.grow[x / GROW_LD][x % GROW_LD];
@@ -796,20 +760,6 @@ RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   }
   inside_finish(c, d, i, type, sI, sM, sQ);
 }
-// lockstep kernel: a thread does whole cells of its own problem
-template <class C>
-RP_HD void inside_cells(C& c, const Shared& sh, int d, int ct, int nct) {
-  const int cells = c.n - d;
-  for (int cell = ct; cell < cells; cell += nct) {
-    const int i = 1 + cell;
-    const int type = pair_type(base(c, i), base(c, i + d));
-    const double sI = type ? inside_interior(c, sh, d, i, type, 0, 1) : 0.;
-    double sM, sQ;
-    inside_splits(c, d, i, 0, 1, sM, sQ);
-    inside_finish(c, d, i, type, sI, sM, sQ);
-  }
-}
-
 // ---------------------------------------------------------------------------
 // outside pass, diagonal d from n-1 down to TURN+1.
 // out(k,l) = Z_outside(k,l)/Z  (ViennaRNA's probs[] before the final *qb).
@@ -1126,20 +1076,6 @@ RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   }
   outside_finish(c, d, k, type, sI, sP, sL);
 }
-template <class C>
-RP_HD void outside_cells(C& c, const Shared& sh, int d, int ct, int nct) {
-  const int cells = c.n - d;
-  for (int cell = ct; cell < cells; cell += nct) {
-    const int k = 1 + cell;
-    const int type = pair_type(base(c, k), base(c, k + d));
-    const double sI = type ? outside_interior(c, sh, d, k, 0, 1) : 0.;
-    double sP, sL;
-    outside_splits(c, d, k, type != 0, 0, 1, sP, sL);
-    if (c.kind == KIND_LINEAR && c.max_w > 0) TB(c, T_XX, d, k) = sP;
-    outside_finish(c, d, k, type, sI, sP, sL);
-  }
-}
-
 // ---------------------------------------------------------------------------
 // Wide bands (general kernel, long problems).  With BAND = TURN+2 diagonals per pass every operand of
 // the split sums is final when the pass runs, but each pass streams the whole history of the tables

@@ -3,9 +3,8 @@
 // synchronises them.  kernels.cu instantiates them with a CTA executor
 // (threadIdx.x + __syncthreads); tests/emul with a serial one.
 //
-//   solve_mcc       one problem per CTA, work of a cell sliced over threads (any lengths)
-//   solve_lockstep  G same-shape problems per CTA, lane = problem, a thread does whole
-//                   cells of its own problem; one barrier per anti-diagonal
+//   solve_mcc / solve_mcc_wide / solve_mcc_cluster   one problem per CTA (cluster), tables in HBM (any length)
+//   solve_band                                       one problem per CTA, interior-loop operands in shared memory
 #ifndef RP_MCC_DRIVER_H
 #define RP_MCC_DRIVER_H
 
@@ -24,32 +23,28 @@ enum {
   PH_WRITE_HP, PH_LOGZ, PH_BAND_A, PH_BAND_B, PH_CFAC, PH_COUNT
 };
 
-// outputs of finished problems; probs[g] is lane g's problem (G = 1 in the general kernel)
+// outputs of a finished problem
 // `SM`: the model the table-driven gap loops read (DevModel, or the band kernel's shared-memory copy);
 // `gfull`: DevModel::gfull or a shared-memory copy of it
-template <class Exec, class Get, class MT>
-RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* dense, const MT& SM, const double* gfull) {
-  const int nct = ex.nthreads() / G;
-  if (probs[0].kind == KIND_LINEAR) {
-    ex.phase(PH_WRITE_BP, [&](int tid) {
-      const Problem& p = probs[tid % G];
-      if (p.out_bp >= 0) write_bp(get(tid % G), dense + p.out_bp, tid / G, nct);
-    });
-    ex.phase(PH_WRITE_BP, [&](int tid) {
-      const Problem& p = probs[tid % G];
-      if (p.out_bp >= 0) write_bp2(get(tid % G), dense + p.out_bp, tid / G, nct);
-    });
-    if (probs[0].max_w > 0) {
+template <class Exec, class MT>
+RP_HD void emit_outputs(Exec& ex, Ctx& c, const Problem& p, float* dense, const MT& SM, const double* gfull) {
+  const int nct = ex.nthreads();
+  if (p.kind == KIND_LINEAR) {
+    if (p.out_bp >= 0) {
+      ex.phase(PH_WRITE_BP, [&](int tid) { write_bp(c, dense + p.out_bp, tid, nct); });
+      ex.phase(PH_WRITE_BP, [&](int tid) { write_bp2(c, dense + p.out_bp, tid, nct); });
+    }
+    if (p.max_w > 0) {
       ex.phase(PH_UN_HAIRPIN, [&](int tid) {
 #ifdef __CUDA_ARCH__
-        long long* prof = RP_PROF(get(tid % G));
+        long long* prof = RP_PROF(c);
         const long long t0 = (prof && tid == 0) ? clock64() : 0;
 #endif
-        unstru_hairpin(get(tid % G), tid / G, nct);
+        unstru_hairpin(c, tid, nct);
 #ifdef __CUDA_ARCH__
         const long long t1 = (prof && tid == 0) ? clock64() : 0;
 #endif
-        unstru_gap_specials(get(tid % G), SM, tid / G, nct);
+        unstru_gap_specials(c, SM, tid, nct);
 #ifdef __CUDA_ARCH__
         if (prof && tid == 0) {   // RP_PROFILE probes of thread 0: the two halves of the phase
           atomicAdd(reinterpret_cast<unsigned long long*>(prof + 22), (unsigned long long)(t1 - t0));
@@ -59,21 +54,16 @@ RP_HD void emit_outputs(Exec& ex, Get get, const Problem* probs, int G, float* d
         }
 #endif
       });
-      ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(get(tid % G), gfull, 0, tid / G, nct); });
-      ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(get(tid % G), gfull, 1, tid / G, nct); });
-      ex.phase(PH_UN_DOMROWS, [&](int tid) { unstru_dom_rows(get(tid % G), tid / G, nct); });
-      ex.phase(PH_UN_DOMCOLS, [&](int tid) { unstru_dom_cols(get(tid % G), tid / G, nct); });
-      ex.phase(PH_UN_MLTAB, [&](int tid) { unstru_ml_tables(get(tid % G), tid / G, nct); });
-      ex.phase(PH_UN_WINDOWS, [&](int tid) {
-        const Problem& p = probs[tid % G];
-        if (p.out_up >= 0) unstru_windows(get(tid % G), dense + p.out_up, tid / G, nct);
-      });
+      ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(c, gfull, 0, tid, nct); });
+      ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(c, gfull, 1, tid, nct); });
+      ex.phase(PH_UN_DOMROWS, [&](int tid) { unstru_dom_rows(c, tid, nct); });
+      ex.phase(PH_UN_DOMCOLS, [&](int tid) { unstru_dom_cols(c, tid, nct); });
+      ex.phase(PH_UN_MLTAB, [&](int tid) { unstru_ml_tables(c, tid, nct); });
+      if (p.out_up >= 0) ex.phase(PH_UN_WINDOWS, [&](int tid) { unstru_windows(c, dense + p.out_up, tid, nct); });
     }
-  } else if (probs[0].kind == KIND_COFOLD) {
-    ex.phase(PH_WRITE_HP, [&](int tid) {
-      const Problem& p = probs[tid % G];
-      if (p.out_hp >= 0) write_hp(get(tid % G), dense + p.out_hp, p.n1, p.n2, p.th_hy, tid / G, nct);
-    });
+  } else if (p.kind == KIND_COFOLD) {
+    if (p.out_hp >= 0)
+      ex.phase(PH_WRITE_HP, [&](int tid) { write_hp(c, dense + p.out_hp, p.n1, p.n2, p.th_hy, tid, nct); });
   }
 }
 
@@ -175,7 +165,7 @@ RP_HD void solve_mcc(Exec& ex, Ctx& c, const Problem& p, float* dense, double* l
       ex.phase(PH_OUTSIDE_B, [&](int tid) { outside_B(c, sh, d, i0, C, tid); });
     }
   }
-  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M, &c.M->gfull[0][0]);
+  emit_outputs(ex, c, p, dense, *c.M, &c.M->gfull[0][0]);
 }
 
 // ---------------------------------------------------------------------------
@@ -275,7 +265,7 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
       ex.phase(PH_OUTSIDE_B, [&](int tid) { wide_outside_finish<W>(c, sh, d, i0, C, tid); });
     }
   }
-  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *c.M, &c.M->gfull[0][0]);
+  emit_outputs(ex, c, p, dense, *c.M, &c.M->gfull[0][0]);
 }
 
 #ifdef __CUDACC__
@@ -534,51 +524,7 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     });
     gfull = bs.TI;
   }
-  emit_outputs(ex, [&](int) -> Ctx& { return c; }, &p, 1, dense, *bs.sm, gfull);
-}
-
-// ---------------------------------------------------------------------------
-// lockstep kernel: G problems of identical (kind, n, cp, max_w) per CTA.
-// Thread tid serves lane g = tid % G with cell-thread index ct = tid / G.
-// `get(g)` returns the lane's context (the calling thread's own on the GPU).
-// probs[g].pair < 0 marks a padding lane (computed, never written out).
-// gS: the group's interleaved sequences, S[i*G+g], i = 0..n+1.
-// ---------------------------------------------------------------------------
-template <int G, class Exec, class Get>
-RP_HD void solve_lockstep(Exec& ex, Get get, const Problem* probs, const uint8_t* gS, float* dense, double* logz,
-                          const Shared& sh) {
-  const int T = sh.T, nct = T / G;
-  const int n = probs[0].n, cp = probs[0].cp;
-  if ((size_t)(n + 2) * G <= RP_SMEM_SEQ) {
-    ex.phase(PH_STAGE, [&](int tid) {
-      for (int x = tid; x < (n + 2) * G; x += T) sh.S[x] = gS[x];
-    });
-    ex.phase(PH_STAGE, [&](int tid) { get(tid % G).S = sh.S + (tid % G); });
-  }
-  ex.phase(PH_PROLOGUE, [&](int tid) {
-    load_shared_model(*get(tid % G).M, sh, tid);
-    prologue_vectors(get(tid % G), tid / G, nct);
-  });
-  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(get(tid % G), tid / G, nct); });
-
-  for (int d = TURN + 1; d <= n - 1; d++)
-    ex.phase(PH_INSIDE_A, [&](int tid) { inside_cells(get(tid % G), sh, d, tid / G, nct); });
-  ex.phase(PH_LOGZ, [&](int tid) {
-    auto& c = get(tid % G);
-    inside_end(c);
-    const Problem& p = probs[tid % G];
-    if (logz && tid / G == 0 && p.pair >= 0)
-      logz[(size_t)p.pair * 3 + p.which] = log(TB(c, T_Q, n - 1, 1)) + n * log(c.M->pf_scale);
-  });
-
-  for (int d = n - 1; d >= TURN + 1; d--) {
-    if (cp > 0) {
-      ex.phase(PH_NICK1, [&](int tid) { outside_nick1(get(tid % G), *get(tid % G).M, sh.red + (tid % G), G, 1, d, tid / G, nct); });
-      ex.phase(PH_NICK2, [&](int tid) { outside_nick2(get(tid % G), sh.red + (tid % G), G, 1, d, tid / G, nct); });
-    }
-    ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_cells(get(tid % G), sh, d, tid / G, nct); });
-  }
-  emit_outputs(ex, get, probs, G, dense, *get(0).M, &get(0).M->gfull[0][0]);
+  emit_outputs(ex, c, p, dense, *bs.sm, gfull);
 }
 
 }  // namespace rp

@@ -228,7 +228,7 @@ class ProbabilityStage:
     def run_dense(self, pairs: Sequence[Tuple[str, str]], opts: Optional[RpOpts] = None,
                   pinned: bool = False) -> List[PairProbabilities]:
         """rp_run_dense: host buffers in, host buffers out.  pinned=True hands the library a page-locked
-        buffer (rp_host_alloc), which the kernels write directly instead of a staged device-to-host copy."""
+        buffer (rp_host_alloc) as the target of its device-to-host copy."""
         opts = opts if opts is not None else default_opts()
         arr, keep = _make_pairs(pairs)
         n = len(pairs)
@@ -276,9 +276,9 @@ class ProbabilityStage:
         return self.run_dense([(s1, s2)], opts)[0]
 
     def rnafold(self, seq: str, max_w: int = 15):
-        """RactIP::rnafold (src/ractip.cpp:308-382): (bp, offset, up).  The C ABI
-        works on pairs, so this pays for one redundant two-strand problem."""
-        r = self.run_dense([(seq, seq)], default_opts(max_w=max(1, max_w)))[0]
+        """RactIP::rnafold (src/ractip.cpp:308-382): (bp, offset, up).  A pair with an empty second
+        sequence computes s1's sections only."""
+        r = self.run_dense([(seq, "")], default_opts(max_w=max(1, max_w)))[0]
         return r.bp1, r.offset1, r.up1
 
     def rnaduplex(self, s1: str, s2: str, th_hy: float = 0.1, use_pf_duplex: bool = False) -> np.ndarray:

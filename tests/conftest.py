@@ -60,9 +60,6 @@ def emul(model):
     em.emul_band_problem.restype = C.c_int
     em.emul_wide_problem.argtypes = [C.c_int] + em.emul_problem.argtypes
     em.emul_wide_problem.restype = C.c_int
-    em.emul_lockstep.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    em.emul_lockstep.restype = C.c_int
 
     class Emul:
         @staticmethod
@@ -92,26 +89,6 @@ def emul(model):
                                  None, None, hp.ctypes.data, C.byref(lz))
             assert rc == 0
             return hp, lz.value
-
-        def lockstep_linear(self, seqs, w, G=8, T=64):
-            """Batch-lockstep schedule: len(seqs) <= G same-length sequences, lane = sequence."""
-            n, cnt = len(seqs[0]), len(seqs)
-            bp = np.zeros((cnt, (n + 1) * (n + 2) // 2), dtype=np.float32)
-            up = np.zeros((cnt, n, w), dtype=np.float32)
-            lz = np.zeros(cnt)
-            rc = em.emul_lockstep(C.addressof(model), G, "".join(seqs).encode(), cnt, n, 0, 0, w, 0, 0, 0.0, T,
-                                  bp.ctypes.data, up.ctypes.data, None, lz.ctypes.data)
-            assert rc == 0
-            return bp, up, lz
-
-        def lockstep_cofold(self, pairs, th=0.1, G=8, T=64):
-            n1, n2, cnt = len(pairs[0][0]), len(pairs[0][1]), len(pairs)
-            hp = np.zeros((cnt, n1 + 1, n2 + 1), dtype=np.float32)
-            lz = np.zeros(cnt)
-            rc = em.emul_lockstep(C.addressof(model), G, "".join(a + b for a, b in pairs).encode(), cnt, n1 + n2, n1 + 1, 1,
-                                  0, n1, n2, th, T, None, None, hp.ctypes.data, lz.ctypes.data)
-            assert rc == 0
-            return hp, lz
 
     return Emul()
 

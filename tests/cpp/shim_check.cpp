@@ -1,7 +1,10 @@
 // Compiles and exercises the C++ shim (include/ractip_prob.hpp) the way a RactIP build would.
 //   shim_check host          : host-only entry points; the stage must refuse to exist without a GPU
 //   shim_check gpu S1 S2     : fills RactIP's members for one pair and prints a few numbers
+//   shim_check multi S1 S2 N : the z-score shuffle batch (N shuffles) on every visible GPU through rp_multi_*, compared
+//                              with the same batch on one GPU
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -24,6 +27,26 @@ int main(int argc, char** argv) {
     return 0;
   }
   if (argc < 4) return 4;
+  if (mode == "multi") {
+    const int num = argc > 4 ? std::atoi(argv[4]) : 16;
+    std::vector<std::pair<std::string, std::string> > batch;
+    rp::zscore_shuffles(argv[2], argv[3], 12, 1, num, batch);
+    std::vector<rp::PairProbabilities> one, all;
+    {
+      rp::ProbabilityStage single;
+      single.solve_batch(batch, one);
+    }
+    rp::ProbabilityStage many(nullptr, 0, 0);
+    many.solve_batch(batch, all);
+    std::printf("devices %d pairs %d\n", many.devices(), num);
+    if (one.size() != all.size()) return 7;
+    for (size_t k = 0; k < one.size(); k++)
+      if (one[k].bp1 != all[k].bp1 || one[k].bp2 != all[k].bp2 || one[k].up1 != all[k].up1 || one[k].up2 != all[k].up2 ||
+          one[k].hp != all[k].hp || one[k].offset2 != all[k].offset2)
+        return 8;
+    std::printf("multi == single\n");
+    return 0;
+  }
   rp::ProbabilityStage st;
   rp::PairProbabilities r;
   st.solve_probabilities(argv[2], argv[3], r);

@@ -97,55 +97,3 @@ extern "C" int emul_band_problem(const rp_model* m, const char* seq, int n, int 
                                  float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
   return run_problem(1, m, seq, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
 }
-
-// lockstep kernel: `count` (<= G) same-shape problems; seqs = count*n letters, outputs count blocks
-template <int G>
-static int lockstep_run(const char* seqs, int count, int n, int cp, int kind, int max_w, int n1, int n2, float th_hy,
-                        int T, float* bp, float* up, float* hp, double* logz) {
-  size_t nbp, nup, nhp;
-  layout(n, max_w, n1, n2, nbp, nup, nhp);
-  const size_t per = nbp + nup + nhp;
-  std::vector<float> dense(per * G + 8, 0.f);
-  std::vector<uint8_t> S((size_t)(n + 2) * G + 16, 0);
-  std::vector<rp::Problem> probs(G);
-  for (int g = 0; g < G; g++) {
-    const int src = g < count ? g : count - 1;
-    for (int i = 1; i <= n; i++) S[(size_t)i * G + g] = rp::encode_base(seqs[(size_t)src * n + i - 1]);
-    rp::Problem& p = probs[g];
-    std::memset(&p, 0, sizeof p);
-    p.n = n; p.cp = cp; p.kind = kind; p.pair = g < count ? g : -1; p.which = 0; p.max_w = max_w;
-    p.n1 = n1; p.n2 = n2; p.th_hy = th_hy;
-    const bool live = g < count;
-    p.out_bp = (live && kind == rp::KIND_LINEAR && bp) ? (long long)(per * g) : -1;
-    p.out_up = (live && kind == rp::KIND_LINEAR && up && max_w > 0) ? (long long)(per * g + nbp) : -1;
-    p.out_hp = (live && kind == rp::KIND_COFOLD && hp) ? (long long)(per * g + nbp + nup) : -1;
-  }
-  std::vector<double> ws(rp::slot_doubles(n) * G, 1e300);
-  std::vector<double> smem(rp::shared_bytes(T) / sizeof(double) + 2, 0.0);
-  rp::Shared sh;
-  rp::carve_shared(sh, smem.data(), T);
-  std::vector<double> lz((size_t)G * 3, 0.0);
-  std::vector<rp::LCtx<G> > cs(G);
-  for (int g = 0; g < G; g++) rp::bind_lctx<G>(cs[g], &g_model, S.data(), probs[g], ws.data(), g);
-  SerialExec ex{T};
-  rp::solve_lockstep<G>(ex, [&](int g) -> rp::LCtx<G>& { return cs[g]; }, probs.data(), S.data(), dense.data(), lz.data(), sh);
-  for (int g = 0; g < count; g++) {
-    if (probs[g].out_bp >= 0) std::memcpy(bp + nbp * g, dense.data() + per * g, nbp * sizeof(float));
-    if (probs[g].out_up >= 0) std::memcpy(up + nup * g, dense.data() + per * g + nbp, nup * sizeof(float));
-    if (probs[g].out_hp >= 0) std::memcpy(hp + nhp * g, dense.data() + per * g + nbp + nup, nhp * sizeof(float));
-    if (logz) logz[g] = lz[(size_t)g * 3];
-  }
-  return 0;
-}
-
-extern "C" int emul_lockstep(const rp_model* m, int G, const char* seqs, int count, int n, int cp, int kind, int max_w,
-                             int n1, int n2, float th_hy, int T, float* bp, float* up, float* hp, double* logz) {
-  int rc = rp::build_dev_model(*m, &g_model);
-  if (rc) return rc;
-  if (count < 1 || count > G || T % G) return 1;
-  switch (G) {
-    case 8: return lockstep_run<8>(seqs, count, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
-    case 4: return lockstep_run<4>(seqs, count, n, cp, kind, max_w, n1, n2, th_hy, T, bp, up, hp, logz);
-    default: return 1;
-  }
-}

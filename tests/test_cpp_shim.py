@@ -44,3 +44,15 @@ def test_shim_fills_ractip_members(lib, stage, bundled, tmp_path):
     assert abs(float(vals["sum_bp1"]) - float(py.bp1.astype(np.float64).sum())) < 1e-4
     assert abs(float(vals["sum_up1"]) - float(py.up1.astype(np.float64).sum())) < 1e-3
     assert abs(float(vals["sum_hp"]) - float(py.hp.astype(np.float64).sum())) < 1e-4
+
+
+@pytest.mark.gpu
+def test_shim_multi_gpu_batch_equals_single_gpu(lib, bundled, tmp_path):
+    """rp_multi_*: the shuffle batch cut into one contiguous block per visible GPU (host threads), results written
+    into the caller's one buffer -- bit-identical to the one-GPU run.  (On a one-GPU box: one block.)"""
+    import torch
+    exe = _build(lib, tmp_path)
+    r = subprocess.run([str(exe), "multi", bundled["sequences"]["MicA"], bundled["sequences"]["ompA"], "37"],
+                       stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout
+    assert f"devices {torch.cuda.device_count()} pairs 37" in r.stdout and "multi == single" in r.stdout

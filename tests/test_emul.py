@@ -47,31 +47,6 @@ def test_emulated_bundled_pair(emul, oracle, bundled):
     assert np.array_equal(hp, oracle.rnaduplex(s1, s2, 0.1))
 
 
-@pytest.mark.parametrize("G,T,count", [(8, 64, 8), (8, 256, 5), (4, 32, 4)])
-def test_emulated_lockstep_linear_matches_oracle(emul, oracle, G, T, count):
-    """Batch-lockstep schedule (lane = problem, whole cells per thread): same numbers as the oracle."""
-    rng = np.random.default_rng(G * 1000 + T)
-    for n in [5, 12, 37, 72]:
-        seqs = [rand_seq(rng, n) for _ in range(count)]
-        bp, up, lz = emul.lockstep_linear(seqs, 15, G, T)
-        for g, s in enumerate(seqs):
-            obp, oup = oracle.rnafold(s, 15)
-            assert np.array_equal(bp[g], obp), (n, g)
-            assert np.abs(up[g] - oup).max() <= 2e-7, (n, g)
-            assert abs(lz[g] - oracle.fold(s)[2]) < 1e-10
-
-
-@pytest.mark.parametrize("G,T,count", [(8, 128, 8), (8, 64, 3)])
-def test_emulated_lockstep_two_strand_matches_oracle(emul, oracle, G, T, count):
-    rng = np.random.default_rng(G + T)
-    for n1, n2 in [(3, 9), (12, 9), (30, 41)]:
-        pairs = [(rand_seq(rng, n1), rand_seq(rng, n2)) for _ in range(count)]
-        hp, lz = emul.lockstep_cofold(pairs, 0.0, G, T)
-        for g, (a, b) in enumerate(pairs):
-            assert np.abs(hp[g] - oracle.rnaduplex(a, b, 0.0)).max() <= 2e-7, (n1, n2, g)
-            assert abs(lz[g] - oracle.fold(a + b, n1 + 1)[2]) < 1e-10
-
-
 # ---- shared-memory band kernel (mcc_band.h): dense register-tiled interior sums, ring of 32 diagonals
 @pytest.mark.parametrize("T", [64, 256, 512])
 def test_emulated_band_linear_matches_oracle(emul, oracle, T):

@@ -509,3 +509,25 @@ def test_random_sweep_of_lengths_nick_positions_and_letters(stage, oracle):
             pairs.append((rand_seq(rng, n1, al), rand_seq(rng, tot - n1, al)))
         for (s1, s2), r in zip(pairs, stage.run_dense(pairs, opts)):
             _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"sweep {len(s1)}x{len(s2)}")
+
+
+def test_single_sequence_request_and_context_lifetime(oracle, model, bundled):
+    """A pair with an empty second sequence computes s1's sections only (RactIP::rnafold on its own,
+    src/ractip.cpp:308-382); closing the stage while a batch is alive is safe (the last batch tears it down)."""
+    from ractip_b200 import ProbabilityStage, default_opts
+    st = ProbabilityStage(model)
+    s = bundled["sequences"]["MicA"]
+    bp, off, up = st.rnafold(s, 15)
+    obp, oup = oracle.rnafold(s, 15)
+    assert np.abs(bp.astype(np.float64) - obp).max() <= TOL and np.abs(up.astype(np.float64) - oup).max() <= TOL
+    assert st.last_timing().kernel_launches == 1
+    mixed = st.run_dense([(s, ""), (bundled["sequences"]["DIS"], bundled["sequences"]["DIS"])], default_opts())
+    assert mixed[0].hp.shape == (len(s) + 1, 1) and not mixed[0].hp.any() and mixed[0].up2.shape == (0, 15)
+    assert np.abs(mixed[0].bp1.astype(np.float64) - obp).max() <= TOL
+    assert mixed[1].hp.max() > 0.9
+    b = st.batch([(s, s)], default_opts())
+    b.run()
+    st.close()          # the context stays alive underneath until its last batch goes
+    flat = b.fetch_dense()
+    assert np.abs(b.split_dense(flat)[0].bp1.astype(np.float64) - obp).max() <= TOL
+    b.close()
