@@ -117,11 +117,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+    path = Path(os.environ.get("RP_LIB", LIB_PATH))   # RP_LIB: e.g. the tuning build (RP_BUILD_TUNE=1, profile probes compiled in)
+    if not path.exists():
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m ractip_b200.build` "
+            f"{path} is missing: build it with `python -m ractip_b200.build` "
             "(there is no CPU/Python fallback for the probability stage)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
     P = C.POINTER
     sig = {

@@ -58,6 +58,7 @@ struct rp_ctx {
   std::vector<std::pair<void*, size_t>> pool_live;
   // lifetime: batches hold a reference; rp_destroy with batches alive only marks the context closed, the last
   // rp_batch_destroy tears it down (a batch handle never outlives the memory it points into)
+  int up_ctas_per_sm = 0;             // unstru_kernel occupancy
   int live_batches = 0;
   bool closing = false;
   cudaStream_t ws_stream = nullptr;   // stream of the last launch that used the workspace / a pooled buffer
@@ -99,6 +100,12 @@ struct rp_batch {
   // sparse
   std::vector<rp_sparse_layout> slayout;
   size_t total_recs = 0, total_upf = 0;
+  // deferred unpaired-window passes (unstru_kernel): queue entries appended to `order`, private workspaces
+  int n_defer = 0;
+  size_t defer_slot = 0;      // doubles per private workspace
+  int defer_maxn = 0;
+  double* d_ws_up = nullptr;
+  int up_grid = -1;
   bool has_single = false;              // some pair has n2 == 0: its unused output sections are zero-filled once
   cudaStream_t last_stream = nullptr;   // stream the batch last ran on (rp_set_stream may have moved the context on)
   rp::SparsePair* d_spairs = nullptr;
@@ -400,6 +407,7 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
   if (const char* e = std::getenv("RP_MCC_WIDE")) ctx->mcc_wide = std::atoi(e);
   ctx->ctas_per_sm = rp::mcc_max_ctas_per_sm(ctx->threads, 2, ctx->mcc_wide);
   ctx->ctas_per_sm1 = rp::mcc_max_ctas_per_sm(ctx->threads, 1, ctx->mcc_wide);
+  ctx->up_ctas_per_sm = rp::unstru_max_ctas_per_sm();
   if (ctx->ctas_per_sm < 1)
     return bail(RP_ERR_CUDA, "rp_create: kernel image not loadable on this device (built for sm_100a)");
   *out = ctx;
@@ -458,7 +466,7 @@ int rp_batch_destroy(rp_batch* b) {
   if (b->ctx) {
     rp_ctx* ctx = b->ctx;
     for (void* p : {(void*)b->d_seq, (void*)b->d_probs, (void*)b->d_order, (void*)b->d_counter, (void*)b->d_dense,
-                    (void*)b->d_logz, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
+                    (void*)b->d_logz, (void*)b->d_ws_up, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
       pool_release(ctx, p);
     ctx->live_batches--;
     if (ctx->closing && ctx->live_batches == 0) {
@@ -514,6 +522,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     std::memset(&q, 0, sizeof q);
     q.pair = p; q.max_w = w; q.n1 = pr.n1; q.n2 = pr.n2; q.th_hy = opts->th_hy;
     q.out_bp = q.out_up = q.out_hp = -1;
+    q.ws_off = -1;
     // rnafold(fa1, ...), rnafold(fa2, ...)  src/ractip.cpp:546-547
     Problem a = q;
     a.kind = rp::KIND_LINEAR; a.which = 0; a.seq_off = off1; a.n = pr.n1; a.cp = 0;
@@ -578,8 +587,34 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     for (auto& v : part) b->order.insert(b->order.end(), v.begin(), v.end());
   }
   b->n_general = (int)b->order.size() - b->n_band[0] - b->n_band[1];
+  // Unpaired-window passes of the band classes run in a launch of their own (unstru_kernel: small CTAs, several per
+  // SM -- the pass is latency-bound and needs no shared-memory ring).  Their problems keep their tables in private
+  // workspaces; when those would not fit a sane budget the pass stays fused with the wavefronts (RP_DEFER_UP=0: off).
+  {
+    const char* e = std::getenv("RP_DEFER_UP");
+    const bool want = ctx->band && ctx->up_ctas_per_sm > 0 && !(e && std::atoi(e) == 0);
+    int maxn = 0;
+    std::vector<int> up;
+    for (int x = 0; want && x < b->n_band[0] + b->n_band[1]; x++) {
+      const Problem& q = b->probs[b->order[x]];
+      if (q.kind == rp::KIND_LINEAR && q.max_w > 0 && q.out_up >= 0) { up.push_back(b->order[x]); maxn = std::max(maxn, q.n); }
+    }
+    const size_t slot = up.empty() ? 0 : rp::slot_doubles(maxn);
+    if (!up.empty() && (double)slot * sizeof(double) * up.size() <= 24e9) {
+      b->n_defer = (int)up.size();
+      b->defer_slot = slot;
+      b->defer_maxn = maxn;
+      for (size_t k = 0; k < up.size(); k++) {
+        b->probs[up[k]].defer_up = 1;
+        b->probs[up[k]].ws_off = (long long)(k * slot);
+      }
+      // queue of the deferred passes: costliest (longest) first, appended after the wavefront queues
+      std::stable_sort(up.begin(), up.end(), [&](int x, int y) { return b->probs[x].n > b->probs[y].n; });
+      b->order.insert(b->order.end(), up.begin(), up.end());
+    }
+  }
   int gen_maxn = 0, gen_mcc = 0;
-  for (size_t x = (size_t)b->n_band[0] + b->n_band[1]; x < b->order.size(); x++) {
+  for (size_t x = (size_t)b->n_band[0] + b->n_band[1]; x < (size_t)(b->n_band[0] + b->n_band[1] + b->n_general); x++) {
     const int k = b->order[x];
     if (b->probs[k].kind != rp::KIND_DUPLEX) { gen_maxn = std::max(gen_maxn, b->probs[k].n); gen_mcc++; }
   }
@@ -600,7 +635,8 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
       auto is_short = [&](int n) { return rp_kernel_plan(n, ctx->smem_optin, nullptr) == RP_KERNEL_BAND_2CTA; };
       const bool s1 = is_short(pairs[0].n1), s2 = is_short(pairs[0].n2), s12 = is_short(pairs[0].n1 + pairs[0].n2);
       struct Sec { size_t off, len; bool sh; };
-      const Sec secs[5] = {{L.bp1, L.n_bp1, s1}, {L.bp2, L.n_bp2, s2}, {L.up1, L.n_up1, s1}, {L.up2, L.n_up2, s2}, {L.hp, L.n_hp, s12}};
+      const bool late = b->n_defer > 0;   // deferred unpaired-window passes write the up sections last
+      const Sec secs[5] = {{L.bp1, L.n_bp1, s1}, {L.bp2, L.n_bp2, s2}, {L.up1, L.n_up1, s1 || late}, {L.up2, L.n_up2, s2 || late}, {L.hp, L.n_hp, s12}};
       b->sect_long.clear(); b->sect_short.clear();
       for (const Sec& x : secs) {   // sections are in layout order: merge neighbours of the same class
         if (!x.len) continue;
@@ -620,7 +656,15 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   const size_t np = b->probs.size();
   if ((e = pool_alloc(ctx, &b->d_seq, seq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc seq");
   if ((e = pool_alloc(ctx, &b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
-  if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
+  if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, b->order.size()) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
+  if (b->n_defer && pool_alloc(ctx, &b->d_ws_up, b->defer_slot * sizeof(double) * (size_t)b->n_defer) != cudaSuccess) {
+    // no room for the private workspaces: keep the pass fused with the wavefronts
+    cudaGetLastError();
+    b->d_ws_up = nullptr;
+    for (auto& q : b->probs) { q.defer_up = 0; q.ws_off = -1; }
+    b->order.resize(b->order.size() - (size_t)b->n_defer);
+    b->n_defer = 0;
+  }
   if ((e = pool_alloc(ctx, &b->d_counter, 4 * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
   if ((e = pool_alloc(ctx, &b->d_dense, std::max<size_t>(1, b->total_floats) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense");
   if ((e = pool_alloc(ctx, &b->d_logz, std::max<size_t>(1, (size_t)n_pairs * 3) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc logz");
@@ -676,6 +720,7 @@ int rp_batch_run(rp_batch* b) {
   d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order + n_bandall; d.nprob = b->n_general;
   d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = std::max(grid, 1);
   d.dense = b->d_dense; d.logz = b->d_logz;
+  d.ws_up = b->d_ws_up;
   d.prof = nullptr;
   d.dbg = std::getenv("RP_DEBUG_SKIP") ? std::atoi(std::getenv("RP_DEBUG_SKIP")) : 0;
   long long*& d_prof = ctx->d_prof;
@@ -717,6 +762,14 @@ int rp_batch_run(rp_batch* b) {
       ws_off += (size_t)b->band_grid[k] * band_slot[k];
       ord_off += b->n_band[k];
     }
+  }
+  if (b->n_defer > 0) {   // the unpaired-window passes of the band classes, after both of their launches (the streams have joined)
+    rp::BatchDev du = d;
+    du.order = b->d_order + n_bandall + b->n_general; du.nprob = b->n_defer;
+    du.counter = b->d_counter + 3;
+    if (b->up_grid < 0) b->up_grid = std::min(b->n_defer, ctx->sm_count * std::max(1, ctx->up_ctas_per_sm));
+    CU(rp::launch_unstru(du, b->up_grid, st));
+    launches++;
   }
   if (b->n_mcc > 0) {
     // Few long problems (a single long pair, not a shuffle batch): one problem per thread-block cluster, so

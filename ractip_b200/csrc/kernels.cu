@@ -150,10 +150,55 @@ __global__ void __launch_bounds__(T, MINB) mcc_band_kernel(BatchDev b) {
     if (q >= b.nprob) break;
     const Problem p = b.probs[b.order[q]];
     Ctx c;
-    bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws + (size_t)blockIdx.x * b.slot_stride);
+    bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, p.ws_off >= 0 ? b.ws_up + p.ws_off : b.ws + (size_t)blockIdx.x * b.slot_stride);
     c.dbg = b.dbg;
     c.prof = b.prof;
     solve_band(ex, c, p, b.dense, b.logz, smem_raw);
+  }
+}
+
+// unstru_kernel: the unpaired-window pass (pf_unstru, src/ractip.cpp:371-375) of the single-strand problems the
+// band kernel has finished, as a launch of its own.  The pass needs no shared-memory ring and is bound by the
+// latency of its table walks through L2, so it runs with small CTAs, several per SM (the band kernel's shape --
+// one 512-thread CTA per SM because of the ring -- keeps only 16 warps in flight).  Each problem's tables sit in
+// its private workspace (Problem::ws_off).
+constexpr int RP_UP_THREADS = 256;
+__global__ void __launch_bounds__(RP_UP_THREADS, 3) unstru_kernel(BatchDev b) {
+  __shared__ int s_next;
+  __shared__ double s_gfull[(MAXLOOP + 1) * GROW_LD];
+  __shared__ uint8_t s_seq[RP_SMEM_SEQ + 8];
+  CtaExec ex;
+  ex.prof = b.prof;
+  const int T = blockDim.x;
+  for (int x = threadIdx.x; x < (MAXLOOP + 1) * GROW_LD; x += T) s_gfull[x] = (&b.model->gfull[0][0])[x];
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(b.counter, 1);
+    __syncthreads();
+    const int q = s_next;
+    __syncthreads();
+    if (q >= b.nprob) break;
+    const Problem p = b.probs[b.order[q]];
+    Ctx c;
+    bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, b.ws_up + p.ws_off);
+    c.dbg = b.dbg;
+    c.prof = b.prof;
+    if (p.n + 2 <= RP_SMEM_SEQ) {
+      for (int x = threadIdx.x; x <= p.n + 1; x += T) s_seq[x] = c.S[x];
+      __syncthreads();
+      c.S = s_seq;
+    }
+    inside_end(c);   // 1/Z from the finished inside table
+    // the phases of emit_unpaired (mcc_driver.h)
+    ex.phase(PH_UN_HAIRPIN, [&](int tid) {
+      unstru_hairpin(c, tid, T);
+      unstru_gap_specials(c, *b.model, tid, T);
+    });
+    ex.phase(PH_UN_GAPS0, [&](int tid) { unstru_gaps(c, s_gfull, 0, tid, T); });
+    ex.phase(PH_UN_GAPS1, [&](int tid) { unstru_gaps(c, s_gfull, 1, tid, T); });
+    ex.phase(PH_UN_DOMROWS, [&](int tid) { unstru_dom_rows(c, tid, T); });
+    ex.phase(PH_UN_DOMCOLS, [&](int tid) { unstru_dom_cols(c, tid, T); });
+    ex.phase(PH_UN_MLTAB, [&](int tid) { unstru_ml_tables(c, tid, T); });
+    if (p.out_up >= 0) ex.phase(PH_UN_WINDOWS, [&](int tid) { unstru_windows(c, b.dense + p.out_up, tid, T); });
   }
 }
 
@@ -492,6 +537,16 @@ cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, c
   MccKernel k = band_kernel(threads);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<grid, threads, smem, st>>>(b);
+  return cudaGetLastError();
+}
+
+int unstru_max_ctas_per_sm() {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, unstru_kernel, RP_UP_THREADS, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+cudaError_t launch_unstru(const BatchDev& b, int grid, cudaStream_t st) {
+  unstru_kernel<<<grid, RP_UP_THREADS, 0, st>>>(b);
   return cudaGetLastError();
 }
 

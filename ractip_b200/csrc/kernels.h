@@ -27,6 +27,7 @@ struct BatchDev {
   double* ws;              // nslots workspace slots
   size_t slot_stride;      // doubles per slot
   int nslots;
+  double* ws_up;           // per-problem workspaces of the problems whose unpaired-window pass is deferred (Problem::ws_off)
   float* dense;            // dense fp32 outputs (reference layouts)
   double* logz;            // 3 per pair, may be null
   long long* prof;         // 64 counters (cycles, calls per phase id) or null
@@ -62,6 +63,8 @@ cudaError_t launch_mcc_cluster(const BatchDev& b, int nclusters, int ctas, int t
 int band_max_ctas_per_sm(int threads, size_t smem);   // threads = 256 (2 CTAs/SM) or 512 (1 CTA/SM)
 cudaError_t launch_band(const BatchDev& b, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st);
+int unstru_max_ctas_per_sm();
+cudaError_t launch_unstru(const BatchDev& b, int grid, cudaStream_t st);   // deferred unpaired-window passes: b.order/nprob = their queue
 cudaError_t launch_sparse(const SparseDev& s, int n_pairs, bool with_ups, cudaStream_t st);
 cudaError_t launch_peak_fp64(double* out, int grid, int iters, cudaStream_t st);
 cudaError_t launch_peak_smem(double* out, int grid, int iters, cudaStream_t st);

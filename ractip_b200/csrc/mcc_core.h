@@ -62,7 +62,8 @@ struct Problem {
   long long out_up;
   long long out_hp;
   float th_hy;
-  int pad;
+  int defer_up;       // 1: the unpaired-window pass runs later in its own kernel (unstru_kernel) on the tables left in ws_off
+  long long ws_off;   // >= 0: private workspace (doubles from BatchDev::ws_up) that outlives the wavefront kernel; -1: the CTA's slot
 };
 
 enum {

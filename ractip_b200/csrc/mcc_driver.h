@@ -23,6 +23,9 @@ enum {
   PH_WRITE_HP, PH_LOGZ, PH_BAND_A, PH_BAND_B, PH_CFAC, PH_COUNT
 };
 
+template <class Exec, class MT>
+RP_HD void emit_unpaired(Exec& ex, Ctx& c, const Problem& p, float* dense, const MT& SM, const double* gfull);
+
 // outputs of a finished problem
 // `SM`: the model the table-driven gap loops read (DevModel, or the band kernel's shared-memory copy);
 // `gfull`: DevModel::gfull or a shared-memory copy of it
@@ -34,7 +37,21 @@ RP_HD void emit_outputs(Exec& ex, Ctx& c, const Problem& p, float* dense, const 
       ex.phase(PH_WRITE_BP, [&](int tid) { write_bp(c, dense + p.out_bp, tid, nct); });
       ex.phase(PH_WRITE_BP, [&](int tid) { write_bp2(c, dense + p.out_bp, tid, nct); });
     }
-    if (p.max_w > 0) {
+    if (p.max_w > 0 && !p.defer_up) emit_unpaired(ex, c, p, dense, SM, gfull);
+  } else if (p.kind == KIND_COFOLD) {
+    if (p.out_hp >= 0)
+      ex.phase(PH_WRITE_HP, [&](int tid) { write_hp(c, dense + p.out_hp, p.n1, p.n2, p.th_hy, tid, nct); });
+  }
+}
+
+// the unpaired-window pass of a finished single-strand problem (pf_unstru, src/ractip.cpp:371-375): reads the tables
+// the two wavefronts left in the problem's workspace.  Run right after them (emit_outputs) or, for the band-kernel
+// classes, later by unstru_kernel with its own launch shape.
+template <class Exec, class MT>
+RP_HD void emit_unpaired(Exec& ex, Ctx& c, const Problem& p, float* dense, const MT& SM, const double* gfull) {
+  const int nct = ex.nthreads();
+  {
+    {
       ex.phase(PH_UN_HAIRPIN, [&](int tid) {
 #ifdef __CUDA_ARCH__
         long long* prof = RP_PROF(c);
@@ -61,9 +78,6 @@ RP_HD void emit_outputs(Exec& ex, Ctx& c, const Problem& p, float* dense, const 
       ex.phase(PH_UN_MLTAB, [&](int tid) { unstru_ml_tables(c, tid, nct); });
       if (p.out_up >= 0) ex.phase(PH_UN_WINDOWS, [&](int tid) { unstru_windows(c, dense + p.out_up, tid, nct); });
     }
-  } else if (p.kind == KIND_COFOLD) {
-    if (p.out_hp >= 0)
-      ex.phase(PH_WRITE_HP, [&](int tid) { write_hp(c, dense + p.out_hp, p.n1, p.n2, p.th_hy, tid, nct); });
   }
 }
 
@@ -478,7 +492,6 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
   for (int d = n - 1; d >= TURN; d--) {
     const int dfin = d + 1 <= n - 1 ? d + 1 : -1;
     const int dnew = d >= TURN + 1 ? d : -1;
-    const bool nick = false;   // (only inter-strand cells are finished: the nicked-loop context never applies)
     // split sums of diagonals d .. d-BAND+1: operands on diagonals >= d+2, complete after the previous step
     if (dnew >= 0 && (n - 1 - d) % BAND == 0) {
       const int rows = n - d + BAND - 1;
@@ -506,19 +519,17 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
     }
     ex.phase(PH_OUTSIDE_A, [&](int tid) {
       if (dfin >= 0) band_outside_B(c, sh, bs, dfin, wide, tid);
-      if (nick && tid < 128 && !(RP_DBG(c) & 64)) outside_nick1(c, *bs.sm, sh.red, 1, 32, dfin, tid, 128);
       if (dnew >= 0) band_interior_A<-1>(c, bs, dnew, tid, T);
       if (tid == T - 1 && d - 1 >= TURN + 1) band_make_desc(bs.desc[(d - 1) & (NDESC - 1)], n, c.cp, d - 1, T, true);
     });
     if (dnew < 0) break;
     ex.phase(PH_CFAC, [&](int tid) {
       band_collect<-1>(c, bs, dnew, d - 1 >= TURN + 1 ? d - 1 : -1, tid, T);
-      if (nick) outside_nick2(c, sh.red, 1, 32, dfin, tid, T);
     });
   }
   // the ring is free now: it takes a copy of the gap-sum weights
   const double* gfull = &c.M->gfull[0][0];
-  if (wide && (size_t)3 * BSLOTS * bs.LDB >= (size_t)(MAXLOOP + 1) * GROW_LD) {
+  if (wide && !p.defer_up && (size_t)3 * BSLOTS * bs.LDB >= (size_t)(MAXLOOP + 1) * GROW_LD) {
     ex.phase(PH_STAGE, [&](int tid) {
       for (int x = tid; x < (MAXLOOP + 1) * GROW_LD; x += T) bs.TI[x] = (&c.M->gfull[0][0])[x];
     });

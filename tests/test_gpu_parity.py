@@ -520,7 +520,7 @@ def test_single_sequence_request_and_context_lifetime(oracle, model, bundled):
     bp, off, up = st.rnafold(s, 15)
     obp, oup = oracle.rnafold(s, 15)
     assert np.abs(bp.astype(np.float64) - obp).max() <= TOL and np.abs(up.astype(np.float64) - oup).max() <= TOL
-    assert st.last_timing().kernel_launches == 1
+    assert 1 <= st.last_timing().kernel_launches <= 2   # the band kernel (+ the deferred unpaired-window kernel)
     mixed = st.run_dense([(s, ""), (bundled["sequences"]["DIS"], bundled["sequences"]["DIS"])], default_opts())
     assert mixed[0].hp.shape == (len(s) + 1, 1) and not mixed[0].hp.any() and mixed[0].up2.shape == (0, 15)
     assert np.abs(mixed[0].bp1.astype(np.float64) - obp).max() <= TOL
