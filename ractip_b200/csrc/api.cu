@@ -600,7 +600,10 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
       if (q.kind == rp::KIND_LINEAR && q.max_w > 0 && q.out_up >= 0) { up.push_back(b->order[x]); maxn = std::max(maxn, q.n); }
     }
     const size_t slot = up.empty() ? 0 : rp::slot_doubles(maxn);
-    if (!up.empty() && (double)slot * sizeof(double) * up.size() <= 24e9) {
+    // Worth it for large batches only: the extra launch ends with its own tail, and with few waves of problems the
+    // fused pass is faster (measured, MicA x ompA shuffles: 125 pairs 5.15 ms fused / 5.90 deferred, 500 pairs
+    // 19.5 / 19.8, 1000 pairs 39.0 / 38.1).
+    if ((int)up.size() >= 10 * ctx->sm_count && (double)slot * sizeof(double) * up.size() <= 24e9) {
       b->n_defer = (int)up.size();
       b->defer_slot = slot;
       b->defer_maxn = maxn;
