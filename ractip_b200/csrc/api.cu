@@ -105,6 +105,8 @@ struct rp_batch {
   size_t defer_slot = 0;      // doubles per private workspace
   int defer_maxn = 0;
   double* d_ws_up = nullptr;
+  int* d_done = nullptr;      // completion flags of the deferred problems (indexed by problem)
+  int up_mode = 0;            // 0: pass fused with the wavefronts, 1: unstru_kernel after them, 2: jobs of their own inside the band kernel
   int up_grid = -1;
   bool has_single = false;              // some pair has n2 == 0: its unused output sections are zero-filled once
   cudaStream_t last_stream = nullptr;   // stream the batch last ran on (rp_set_stream may have moved the context on)
@@ -466,7 +468,7 @@ int rp_batch_destroy(rp_batch* b) {
   if (b->ctx) {
     rp_ctx* ctx = b->ctx;
     for (void* p : {(void*)b->d_seq, (void*)b->d_probs, (void*)b->d_order, (void*)b->d_counter, (void*)b->d_dense,
-                    (void*)b->d_logz, (void*)b->d_ws_up, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
+                    (void*)b->d_logz, (void*)b->d_ws_up, (void*)b->d_done, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
       pool_release(ctx, p);
     ctx->live_batches--;
     if (ctx->closing && ctx->live_batches == 0) {
@@ -587,23 +589,32 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     for (auto& v : part) b->order.insert(b->order.end(), v.begin(), v.end());
   }
   b->n_general = (int)b->order.size() - b->n_band[0] - b->n_band[1];
-  // Unpaired-window passes of the band classes run in a launch of their own (unstru_kernel: small CTAs, several per
-  // SM -- the pass is latency-bound and needs no shared-memory ring).  Their problems keep their tables in private
-  // workspaces; when those would not fit a sane budget the pass stays fused with the wavefronts (RP_DEFER_UP=0: off).
+  // Unpaired-window passes of the band classes, three ways:
+  //   mode 1 (large batches, >= 10 problems per SM): a launch of their own after the wavefront kernels (unstru_kernel:
+  //           small CTAs, three per SM -- the pass needs no shared-memory ring);
+  //   mode 2 (batches with at least four problems per SM): JOBS of their own in the band kernel's queue, after all
+  //           wavefront jobs, each waiting for its problem's completion flag -- finer jobs shorten the tail when there are
+  //           few problems per SM (125 MicA x ompA pairs: the per-GPU share at 8 GPUs);
+  //   mode 0 (a handful of problems, or no room for private workspaces): fused with the wavefronts.
+  // Modes 1 and 2 keep a deferred problem's tables in a private workspace.  RP_DEFER_UP=0/1/2 forces a mode.
   {
     const char* e = std::getenv("RP_DEFER_UP");
-    const bool want = ctx->band && ctx->up_ctas_per_sm > 0 && !(e && std::atoi(e) == 0);
     int maxn = 0;
     std::vector<int> up;
-    for (int x = 0; want && x < b->n_band[0] + b->n_band[1]; x++) {
+    for (int x = 0; ctx->band && x < b->n_band[0] + b->n_band[1]; x++) {
       const Problem& q = b->probs[b->order[x]];
       if (q.kind == rp::KIND_LINEAR && q.max_w > 0 && q.out_up >= 0) { up.push_back(b->order[x]); maxn = std::max(maxn, q.n); }
     }
     const size_t slot = up.empty() ? 0 : rp::slot_doubles(maxn);
-    // Worth it for large batches only: the extra launch ends with its own tail, and with few waves of problems the
-    // fused pass is faster (measured, MicA x ompA shuffles: 125 pairs 5.15 ms fused / 5.90 deferred, 500 pairs
-    // 19.5 / 19.8, 1000 pairs 39.0 / 38.1).
-    if ((int)up.size() >= 10 * ctx->sm_count && (double)slot * sizeof(double) * up.size() <= 24e9) {
+    int mode = 0;
+    if (!up.empty() && (double)slot * sizeof(double) * up.size() <= 24e9) {
+      // (measured, MicA x ompA shuffles, fused / own launch: 125 pairs 5.15 / 5.90 ms, 500 pairs 19.5 / 19.8, 1000 pairs 39.0 / 38.1)
+      if ((int)up.size() >= 10 * ctx->sm_count && ctx->up_ctas_per_sm > 0) mode = 1;
+      else if (b->n_band[0] + b->n_band[1] >= 4 * ctx->sm_count) mode = 2;   // (jobs of their own / fused: 125 pairs 5.34 / 5.15 ms, 250 pairs 9.85 / 10.27, 500 pairs 19.2 / 19.6)
+      if (e) mode = std::atoi(e);
+    }
+    b->up_mode = mode;
+    if (mode) {
       b->n_defer = (int)up.size();
       b->defer_slot = slot;
       b->defer_maxn = maxn;
@@ -611,9 +622,31 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
         b->probs[up[k]].defer_up = 1;
         b->probs[up[k]].ws_off = (long long)(k * slot);
       }
-      // queue of the deferred passes: costliest (longest) first, appended after the wavefront queues
+      // the deferred passes, costliest (longest) first
       std::stable_sort(up.begin(), up.end(), [&](int x, int y) { return b->probs[x].n > b->probs[y].n; });
-      b->order.insert(b->order.end(), up.begin(), up.end());
+      if (mode == 1) {
+        b->order.insert(b->order.end(), up.begin(), up.end());   // queue of unstru_kernel, after the wavefront queues
+      } else {
+        // per band class: wavefront jobs with a dependent job first (their successor should start early), then the
+        // others, then the unpaired-window jobs
+        std::vector<int> q2;
+        int off = 0;
+        for (int cl = 0; cl < 2; cl++) {
+          std::vector<int> dep, oth, ups;
+          for (int x = off; x < off + b->n_band[cl]; x++) (b->probs[b->order[x]].defer_up ? dep : oth).push_back(b->order[x]);
+          const int maxn_cl = b->band_maxn[cl];
+          for (int k : up)
+            if (rp_kernel_plan(b->probs[k].n, ctx->smem_optin, nullptr) == cl) ups.push_back(k | rp::RP_JOB_UNPAIRED);
+          (void)maxn_cl;
+          off += b->n_band[cl];
+          q2.insert(q2.end(), dep.begin(), dep.end());
+          q2.insert(q2.end(), oth.begin(), oth.end());
+          q2.insert(q2.end(), ups.begin(), ups.end());
+          b->n_band[cl] = (int)(dep.size() + oth.size() + ups.size());
+        }
+        q2.insert(q2.end(), b->order.begin() + off, b->order.end());   // the general queue
+        b->order.swap(q2);
+      }
     }
   }
   int gen_maxn = 0, gen_mcc = 0;
@@ -638,7 +671,7 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
       auto is_short = [&](int n) { return rp_kernel_plan(n, ctx->smem_optin, nullptr) == RP_KERNEL_BAND_2CTA; };
       const bool s1 = is_short(pairs[0].n1), s2 = is_short(pairs[0].n2), s12 = is_short(pairs[0].n1 + pairs[0].n2);
       struct Sec { size_t off, len; bool sh; };
-      const bool late = b->n_defer > 0;   // deferred unpaired-window passes write the up sections last
+      const bool late = b->up_mode == 1;   // the deferred unpaired-window launch writes the up sections last
       const Sec secs[5] = {{L.bp1, L.n_bp1, s1}, {L.bp2, L.n_bp2, s2}, {L.up1, L.n_up1, s1 || late}, {L.up2, L.n_up2, s2 || late}, {L.hp, L.n_hp, s12}};
       b->sect_long.clear(); b->sect_short.clear();
       for (const Sec& x : secs) {   // sections are in layout order: merge neighbours of the same class
@@ -660,13 +693,28 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   if ((e = pool_alloc(ctx, &b->d_seq, seq.size() + 16)) != cudaSuccess) return bail(e, "cudaMalloc seq");
   if ((e = pool_alloc(ctx, &b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
   if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, b->order.size()) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
+  if ((e = pool_alloc(ctx, &b->d_done, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc done");
   if (b->n_defer && pool_alloc(ctx, &b->d_ws_up, b->defer_slot * sizeof(double) * (size_t)b->n_defer) != cudaSuccess) {
     // no room for the private workspaces: keep the pass fused with the wavefronts
     cudaGetLastError();
     b->d_ws_up = nullptr;
     for (auto& q : b->probs) { q.defer_up = 0; q.ws_off = -1; }
-    b->order.resize(b->order.size() - (size_t)b->n_defer);
+    if (b->up_mode == 1) b->order.resize(b->order.size() - (size_t)b->n_defer);
+    else {   // drop the unpaired-window jobs from the band queues
+      std::vector<int> q2;
+      int off = 0;
+      for (int cl = 0; cl < 2; cl++) {
+        int kept = 0;
+        for (int x = off; x < off + b->n_band[cl]; x++)
+          if (!(b->order[x] & rp::RP_JOB_UNPAIRED)) { q2.push_back(b->order[x]); kept++; }
+        off += b->n_band[cl];
+        b->n_band[cl] = kept;
+      }
+      q2.insert(q2.end(), b->order.begin() + off, b->order.end());
+      b->order.swap(q2);
+    }
     b->n_defer = 0;
+    b->up_mode = 0;
   }
   if ((e = pool_alloc(ctx, &b->d_counter, 4 * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc counter");
   if ((e = pool_alloc(ctx, &b->d_dense, std::max<size_t>(1, b->total_floats) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense");
@@ -723,7 +771,7 @@ int rp_batch_run(rp_batch* b) {
   d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order + n_bandall; d.nprob = b->n_general;
   d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = std::max(grid, 1);
   d.dense = b->d_dense; d.logz = b->d_logz;
-  d.ws_up = b->d_ws_up;
+  d.ws_up = b->d_ws_up; d.done = b->d_done;
   d.prof = nullptr;
   d.dbg = std::getenv("RP_DEBUG_SKIP") ? std::atoi(std::getenv("RP_DEBUG_SKIP")) : 0;
   long long*& d_prof = ctx->d_prof;
@@ -737,6 +785,7 @@ int rp_batch_run(rp_batch* b) {
   b->last_stream = st;
   ctx->ws_stream = st;
   CU(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(int), st));
+  if (b->n_defer) CU(cudaMemsetAsync(b->d_done, 0, b->probs.size() * sizeof(int), st));
   CU(cudaEventRecord(ctx->ev[0], st));
   int launches = 0;
   {
@@ -766,7 +815,7 @@ int rp_batch_run(rp_batch* b) {
       ord_off += b->n_band[k];
     }
   }
-  if (b->n_defer > 0) {   // the unpaired-window passes of the band classes, after both of their launches (the streams have joined)
+  if (b->up_mode == 1) {   // the unpaired-window passes of the band classes, after both of their launches (the streams have joined)
     rp::BatchDev du = d;
     du.order = b->d_order + n_bandall + b->n_general; du.nprob = b->n_defer;
     du.counter = b->d_counter + 3;

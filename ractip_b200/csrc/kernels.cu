@@ -148,12 +148,30 @@ __global__ void __launch_bounds__(T, MINB) mcc_band_kernel(BatchDev b) {
     const int q = s_next;
     __syncthreads();
     if (q >= b.nprob) break;
-    const Problem p = b.probs[b.order[q]];
+    const int job = b.order[q], pi = job & (RP_JOB_UNPAIRED - 1);
+    const Problem p = b.probs[pi];
     Ctx c;
     bind_ctx(c, b.model, b.seq + p.seq_off - 1, p, p.ws_off >= 0 ? b.ws_up + p.ws_off : b.ws + (size_t)blockIdx.x * b.slot_stride);
     c.dbg = b.dbg;
     c.prof = b.prof;
+    if (job & RP_JOB_UNPAIRED) {
+      // The unpaired-window pass of a problem whose wavefronts ran as an earlier job (maybe on another SM; its tables sit
+      // in the problem's private workspace).  Such jobs come after ALL wavefront jobs in the queue, so the job waited for
+      // is running or done: no deadlock.  Finer jobs = a shorter tail when there are few problems per SM.
+      if (threadIdx.x == 0) {
+        while (atomicAdd(b.done + pi, 0) == 0) __nanosleep(500);
+        __threadfence();
+      }
+      __syncthreads();
+      solve_band_unpaired(ex, c, p, b.dense, smem_raw);
+      continue;
+    }
     solve_band(ex, c, p, b.dense, b.logz, smem_raw);
+    if (p.defer_up) {   // publish: the tables are complete (release; the unpaired-window job acquires)
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(b.done + pi, 1);
+    }
   }
 }
 

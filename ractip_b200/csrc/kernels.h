@@ -17,6 +17,9 @@
 #endif
 namespace rp {
 
+// queue entries: problem index, + RP_JOB_UNPAIRED for the unpaired-window pass of a deferred problem as a job of its own
+constexpr int RP_JOB_UNPAIRED = 0x40000000;
+
 struct BatchDev {
   const DevModel* model;
   const uint8_t* seq;      // encoded sequences, one zero byte of padding around each
@@ -27,6 +30,7 @@ struct BatchDev {
   double* ws;              // nslots workspace slots
   size_t slot_stride;      // doubles per slot
   int nslots;
+  int* done;               // per problem: set when a deferred problem's wavefronts are complete (its unpaired-window job waits on it)
   double* ws_up;           // per-problem workspaces of the problems whose unpaired-window pass is deferred (Problem::ws_off)
   float* dense;            // dense fp32 outputs (reference layouts)
   double* logz;            // 3 per pair, may be null

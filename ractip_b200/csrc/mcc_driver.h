@@ -538,5 +538,29 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
   emit_outputs(ex, c, p, dense, *bs.sm, gfull);
 }
 
+// the unpaired-window pass of a problem the band kernel finished earlier, run as a job of its own inside that kernel
+template <class Exec>
+RP_HD void solve_band_unpaired(Exec& ex, Ctx& c, const Problem& p, float* dense, void* smem) {
+  const int T = ex.nthreads(), n = c.n;
+  Shared sh;
+  BandShared bs;
+  carve_band(sh, bs, smem, n, T);
+  const uint8_t* gS = c.S;
+  ex.phase(PH_STAGE, [&](int tid) {
+    for (int x = tid; x <= n + 1; x += T) sh.S[x] = gS[x];
+    load_band_weights(*c.M, bs, tid, T);
+  });
+  c.S = sh.S;
+  inside_end(c);
+  const double* gfull = &c.M->gfull[0][0];
+  if ((size_t)3 * BSLOTS * bs.LDB >= (size_t)(MAXLOOP + 1) * GROW_LD) {
+    ex.phase(PH_STAGE, [&](int tid) {
+      for (int x = tid; x < (MAXLOOP + 1) * GROW_LD; x += T) bs.TI[x] = (&c.M->gfull[0][0])[x];
+    });
+    gfull = bs.TI;
+  }
+  emit_unpaired(ex, c, p, dense, *bs.sm, gfull);
+}
+
 }  // namespace rp
 #endif
