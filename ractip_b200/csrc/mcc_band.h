@@ -678,13 +678,7 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     const double prp = ldg_if(mll, c.ptr(T_PR, d + 1, mll ? k - 1 : 1), safe, 0.);
     const double q5 = ldg_if(k > 1, c.ptr(T_Q, k > 1 ? k - 2 : 0, 1), safe, 1.0);
     const double q3 = ldg_if(l < n, c.ptr(T_Q, l < n ? n - l - 1 : 0, l < n ? l + 1 : 1), safe, 1.0);
-    double qo = 0., qn = 1.0;
-    const bool s2 = c.cp > 0 && k >= c.cp, s1 = c.cp > 0 && !s2 && l < c.cp;
-    if (c.cp > 0) {
-      qo = ldg_if(s1 || s2, s2 ? &VEC(c, V_QROUT, l) : &VEC(c, V_QLOUT, k), safe, 0.);
-      const bool hn = s2 ? (k > c.cp) : (s1 && l + 1 <= c.cp - 1);
-      qn = ldg_if(hn, s2 ? c.ptr(T_Q, hn ? k - 1 - c.cp : 0, c.cp) : c.ptr(T_Q, hn ? c.cp - 2 - l : 0, hn ? l + 1 : 1), safe, 1.0);
-    }
+    // (two strands: only inter-strand cells are finished here, and those never sit in the nicked loop)
     // ---- (2) sequence-only factors
     const int type = pair_type(base(c, k), base(c, l));
     const bool tz = type != 0;
@@ -694,13 +688,11 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     const double scale2 = M.scale_small[2];
     const double kx = ext_stem_bf(M, type, mll ? skm : -1, mlr ? slp : -1);                     // stem in the exterior loop
     const double km = (mlr && mll) ? ml_stem_bf(M, type, skm, slp) * scale2 : 0.;              // stem in a multiloop
-    // stem in the nicked loop: strand 2 (5' neighbour missing when k == cp), strand 1 (3' neighbour missing when l+1 == cp)
-    const double kn = s2 ? ext_stem_bf(M, type, k > c.cp ? skm : -1, slp) : (s1 ? ext_stem_bf(M, type, skm, l + 1 < c.cp ? slp : -1) : 0.);
     const double gI = tz ? M.mmI[type][si1][sj1] : 0., g1 = tz ? M.mm1n[type][si1][sj1] : 0., gA = tz ? au : 0.;
     const double gM = (tz && ss(c, k, k + 1) && ss(c, l - 1, l)) ? M.expMLclosing * ml_stem_bf(M, rt, sj1, si1) : 0.;
     const double sIraw = bs.sIv[k];
     const size_t ro = (size_t)(d & (BSLOTS - 1)) * bs.LDB + bidx(bs, k);
-    if (RP_DBG(c) & 128) { bs.sIv[k] = sP + sL + qbv + plp + mcp + pmp + prp + q5 + q3 + qo + qn; continue; }
+    if (RP_DBG(c) & 128) { bs.sIv[k] = sP + sL + qbv + plp + mcp + pmp + prp + q5 + q3; continue; }
     // ---- (3) combine
     const bool live = tz && qbv != 0.;
     const double PL = mlr ? plp * M.mlb1 + mcp : 0.;
@@ -709,7 +701,6 @@ RP_HD void band_outside_B(C& c, const Shared& sh, const BandShared& bs, int d, b
     double out = q5 * q3 * c.invZ * kx;
     out += sIraw;
     out += (PMLB + sL) * km;
-    out += qo * qn * kn;
     out = live ? out : 0.;
     TB(c, T_PL, d, k) = PL;
     TB(c, T_PR, d, k) = PR;

@@ -71,12 +71,12 @@ enum {
   T_OUT, T_OUTI, T_OUT1N, T_OUTAU, T_MC, T_PR, T_PRML, T_PMLB, T_PL,
   T_DG, T_RR, T_LL, T_XX,
   T_QS, T_PRB, T_MLB,   // band-bulk split sums of the general kernel (see inside_band_A / outside_band_A)
+  T_QMR, T_PRMLR,       // wide schedule: ROW-major copies of qm and PRML (element (i,j) at (i-1)*ld + j), see Ctx::rptr
   T_LIST,   // not doubles: per-diagonal lists of pairable cells (uint16), general kernel only
   T_COUNT
 };
 enum {
   V_SCALE = 0, V_MLB, V_HPW, V_SP3, V_SP4, V_SP6, V_U0, V_U1,
-  V_QR, V_QROUT, V_QL, V_QLOUT,
   V_COUNT
 };
 
@@ -107,6 +107,10 @@ struct Ctx {
   RP_HD unsigned off(int t, int d, int i) const { return (unsigned)t * te + ((unsigned)d & ring_mask(t)) * (unsigned)ld + (unsigned)i; }
   RP_HD double& tb(int t, int d, int i) const { return ws[off(t, d, i)]; }
   RP_HD double* ptr(int t, int d, int i) const { return ws + off(t, d, i); }
+  // The ML sum of the outside far pass walks COLUMNS (PRML(i,l), qm(i+1,k-1) over i, lanes = neighbouring l): in the
+  // diagonal-major tables neighbouring lanes are a whole row apart (one 32-byte sector per 8-byte operand), in the
+  // row-major copies they are neighbours.
+  RP_HD double* rptr(int t, int i, int j) const { return ws + ((unsigned)t * te + (unsigned)(i - 1) * (unsigned)ld + (unsigned)j); }
   RP_HD double& v(int vv, int k) const { return ws[(unsigned)T_COUNT * te + (unsigned)vv * ve + (unsigned)k]; }
   RP_HD int dstep() const { return ld; }   // one diagonal up, same position
   RP_HD int pstep() const { return 1; }    // same diagonal, next position
@@ -154,14 +158,33 @@ struct Shared {
   double* ghead_1;  // [GROW_LD]
   double* red;      // [128] small reductions (nick sums)
   uint8_t* S;       // [RP_SMEM_SEQ + 8] staged sequence(s)
+  double* gtile;    // wide builds: staged generic-class rows of a chunk (see "Staged generic interior sums"); aliases part
+  double* gpart;    // wide builds: partial generic sums [bin][cell]; aliases part
 };
+// Staged generic interior sums (wide builds of the general kernel, long problems).  The generic-class taps of the
+// interior-loop sum (375 of the 496 terms of a cell) are summed DENSELY out of a shared-memory tile: the rows
+// s = 6..30 of the generic class table (diagonals d -/+ (2+s)) over the positions a chunk of cells can reach are
+// copied into shared memory once per chunk, zero where a position is invalid, and a thread walks a row for 8
+// neighbouring cells with a sliding register window (one shared load per 8 FMAs, no predicates) -- the band
+// kernel's scheme, per chunk instead of per problem.  The ends (bulge, 1xn) and the table-driven shapes stay with
+// the per-cell code (inside_interior / outside_interior with generic = false).
+constexpr int GS_ROW0 = 6, GS_NROWS = MAXLOOP - GS_ROW0 + 1;             // rows 6..30
+RP_HD int gs_lt(int T) { return (T + MAXLOOP + 8 + 7) / 8 * 8; }          // elements per tile row (multiple of 8)
+constexpr int GS_KINDS = 5;   // ends_items: bulge row, 1xn row, bulge heads, 1xn heads, table-driven shapes
+RP_HD size_t gs_doubles(int T) { return (size_t)GS_KINDS * T + (size_t)GS_NROWS * gs_lt(T) + 8 * (size_t)T; }   // ends partials + tile + [bin][cell]
+RP_HD size_t part_doubles(int T, int W) {
+  const size_t far = 2 * (size_t)W * T;
+  return (W > BAND && gs_doubles(T) > far) ? gs_doubles(T) : far;
+}
 RP_HD size_t shared_bytes(int T, int W = BAND) {
-  return sizeof(double) * (2 * W * (size_t)T + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
+  return sizeof(double) * (part_doubles(T, W) + (MAXLOOP + 1) * GROW_LD + 2 * GROW_LD + 128) + RP_SMEM_SEQ + 16;
 }
 RP_HD void carve_shared(Shared& sh, void* base, int T, int W = BAND) {
   sh.T = T;
   double* p = static_cast<double*>(base);
-  sh.part = p; p += 2 * W * (size_t)T;
+  sh.part = p; p += part_doubles(T, W);
+  sh.gtile = sh.part + (size_t)GS_KINDS * T;
+  sh.gpart = sh.gtile + (size_t)GS_NROWS * gs_lt(T);
   sh.grow = p; p += (MAXLOOP + 1) * GROW_LD;
   sh.ghead_b = p; p += GROW_LD;
   sh.ghead_1 = p; p += GROW_LD;
@@ -300,7 +323,7 @@ RP_HD double row_sum(const double* g, const double* p, int step, int lo, int hi)
 // u2 <= u2cap, u1+u2+2 <= ddmax; every element touched is a valid cell.
 template <int SIGN>
 RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, const double* TA, int ds, int ps,
-                         int u1max, int u2cap, int ddmax, int sl, int SI, double& sI, double& s1, double& sA) {
+                         int u1max, int u2cap, int ddmax, int sl, int SI, double& sI, double& s1, double& sA, bool generic = true) {
   const int step = -SIGN * ds;
   for (int q = sl; q <= MAXLOOP / 2; q += SI) {
     for (int h = 0; h < 2; h++) {
@@ -320,7 +343,7 @@ RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, c
       } else {
         sA += sh.ghead_b[u1] * TA[o0];
         if (u2hi >= 1) s1 += sh.ghead_1[u1] * T1[o0 + step];
-        if (u2hi >= 2) sI += row_sum(g, TI + o0, step, 2, u2hi);
+        if (generic && u2hi >= 2) sI += row_sum(g, TI + o0, step, 2, u2hi);
       }
     }
   }
@@ -529,7 +552,6 @@ RP_HD void prologue2(C& c, int ct, int nct) {
     }
     VEC(c, V_SP3, i) = s3; VEC(c, V_SP4, i) = s4; VEC(c, V_SP6, i) = s6;
     VEC(c, V_U0, i) = 0.; VEC(c, V_U1, i) = 0.;
-    VEC(c, V_QR, i) = 0.; VEC(c, V_QROUT, i) = 0.; VEC(c, V_QL, i) = 0.; VEC(c, V_QLOUT, i) = 0.;
   }
   // diagonals 0..TURN: q = scale[d+1], everything else 0
   const int dmax = TURN < n - 1 ? TURN : n - 1;
@@ -551,7 +573,7 @@ RP_HD void prologue2(C& c, int ct, int nct) {
 // ---------------------------------------------------------------------------
 // slice sl of SI of the interior-loop sum of a cell that can pair
 template <class C>
-RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int type, int sl, int SI) {
+RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int type, int sl, int SI, bool generic = true) {
   const DevModel& M = *c.M;
   const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
   if (ddmax < 2) return 0.;
@@ -565,7 +587,7 @@ RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int typ
   double sI = 0., s1 = 0., sA = 0.;
   if (!(RP_DBG(c) & 1))
     interior_rows<1>(sh, c.ptr(T_QBI, d, i), c.ptr(T_QB1N, d, i), c.ptr(T_QBAU, d, i), c.dstep(), c.pstep(), u1max, maxu2,
-                     ddmax, sl, SI, sI, s1, sA);
+                     ddmax, sl, SI, sI, s1, sA, generic);
   double accI = M.mmI[type][si1][sj1] * sI + M.mm1n[type][si1][sj1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
   // table-driven small loops
   for (int s = sl; s < RP_N_SPECIAL; s += SI) {
@@ -732,14 +754,14 @@ RP_HD void inside_band_B(Ctx& c, const Shared& sh, int d0, int i0, int C, int ti
   }
 }
 // per diagonal, phase A: interior-loop work items (pairable cell, slice), partials to sh.part[tid]
-RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid, bool generic = true) {
   const int T = sh.T;
   if (d - (TURN + 1) < 2) return;
   const ISplit is = make_isplit(c, d, i0, C, T);
   const int r = tid % is.cntp, sl = tid / is.cntp;
   if (sl < is.SI && r < is.cnt) {
     const int i = listp(c)[(size_t)d * c.ld + is.lo + r];
-    sh.part[tid] = inside_interior(c, sh, d, i, pair_type(base(c, i), base(c, i + d)), sl, is.SI);
+    sh.part[tid] = inside_interior(c, sh, d, i, pair_type(base(c, i), base(c, i + d)), sl, is.SI, generic);
   }
 }
 // per diagonal, phase B: one thread per cell
@@ -765,83 +787,12 @@ RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
 // outside pass, diagonal d from n-1 down to TURN+1.
 // out(k,l) = Z_outside(k,l)/Z  (ViennaRNA's probs[] before the final *qb).
 // ---------------------------------------------------------------------------
-// two-strand only, twice per diagonal before the cells: the closing pairs that
-// straddle the nick feed the stems sitting directly in the nicked loop.
-//   Qr(r)    = sum_{p<cp} out(p,r) ExtClose(p,r) scale[2] q(p+1,cp-1)        complete after diag r-cp+1
-//   Qrout(l) = sum_{r>l} Qr(r) q(l+1,r-1)
-//   Ql(p)    = sum_{r>=cp} out(p,r) ExtClose(p,r) scale[2] q(cp,r-1)         complete after diag cp-p
-//   Qlout(k) = sum_{p<k} Ql(p) q(p+1,k-1)
-// Step d finalises Qr(d+cp), Qrout(d+cp-1), Ql(cp-1-d), Qlout(cp-d).  Each of the
-// four sums is split over `np` threads (fixed partition => deterministic);
-// partial (job, lane) goes to red[(job*np+lane)*rs].
-template <class C, class MT>
-RP_HD double nick_close(const C& c, const MT& M, int p, int r) {
-  const int tp = pair_type(base(c, p), base(c, r));
-  if (!tp || r - p <= TURN) return 0.;
-  const double o = TB(c, T_OUT, r - p, p);
-  if (o == 0.) return 0.;
-  return o * VEC(c, V_SCALE, 2) *
-         ext_stem(M, rtype(tp), ss(c, r - 1, r) ? base(c, r - 1) : -1, ss(c, p, p + 1) ? base(c, p + 1) : -1);
-}
-// (M: the model ext_stem reads -- DevModel, or the band kernel's shared-memory copy)
-template <class C, class MT>
-RP_HD void outside_nick1(C& c, const MT& M, double* red, int rs, int np, int d, int ct, int nct) {
-  if (c.cp <= 0) return;
-  const int n = c.n, cp = c.cp;
-  for (int w = ct; w < 4 * np; w += nct) {
-    const int lane = w % np, job = w / np;
-    double s = 0.;
-    if (job == 0) {          // Qr(r), r = d+cp: closing pairs (p,r), all of diag >= d+1
-      const int r = d + cp;
-      if (r >= cp && r <= n)
-        for (int p = 1 + lane; p < cp; p += np) {
-          const double v = nick_close(c, M, p, r);
-          if (v != 0.) s += v * (p + 1 <= cp - 1 ? TB(c, T_Q, cp - 2 - p, p + 1) : 1.0);
-        }
-    } else if (job == 1) {   // Ql(p), p = cp-1-d
-      const int p = cp - 1 - d;
-      if (p >= 1 && p < cp)
-        for (int rr = cp + lane; rr <= n; rr += np) {
-          const double v = nick_close(c, M, p, rr);
-          if (v != 0.) s += v * (cp <= rr - 1 ? TB(c, T_Q, rr - 1 - cp, cp) : 1.0);
-        }
-    } else if (job == 2) {   // part of Qrout(l), l = d+cp-1, that uses Qr(r), r >= l+2 (earlier steps)
-      const int l = d + cp - 1;
-      if (l >= cp && l < n)
-        for (int r = l + 2 + lane; r <= n; r += np) s += VEC(c, V_QR, r) * TB(c, T_Q, r - 2 - l, l + 1);
-    } else {                 // part of Qlout(k), k = cp-d, that uses Ql(p), p <= k-2 (earlier steps)
-      const int k = cp - d;
-      if (k >= 2 && k < cp)
-        for (int p = 1 + lane; p <= k - 2; p += np) s += VEC(c, V_QL, p) * TB(c, T_Q, k - 2 - p, p + 1);
-    }
-    red[(size_t)w * rs] = s;
-  }
-}
-template <class C>
-RP_HD void outside_nick2(C& c, const double* red, int rs, int np, int d, int ct, int nct) {
-  if (c.cp <= 0) return;
-  const int n = c.n, cp = c.cp;
-  const int second = nct > np ? np : (nct > 1 ? 1 : 0);  // a thread of another warp when there is one
-  if (ct == 0) {
-    double qr = 0., rest = 0.;
-    for (int t = 0; t < np; t++) { qr += red[(size_t)t * rs]; rest += red[(size_t)(2 * np + t) * rs]; }
-    const int r = d + cp, l = d + cp - 1;
-    if (r >= cp && r <= n) VEC(c, V_QR, r) = qr;
-    // Qrout(l) = Qr(l+1)*q(l+1,l) + rest, q of the empty segment is 1
-    if (l >= cp && l < n) VEC(c, V_QROUT, l) = qr + rest;
-  }
-  if (ct == second) {
-    double ql = 0., rest = 0.;
-    for (int t = 0; t < np; t++) { ql += red[(size_t)(np + t) * rs]; rest += red[(size_t)(3 * np + t) * rs]; }
-    const int p = cp - 1 - d, k = cp - d;
-    if (p >= 1 && p < cp) VEC(c, V_QL, p) = ql;
-    if (k >= 2 && k < cp) VEC(c, V_QLOUT, k) = ql + rest;
-  }
-}
+// (Two strands: only the inter-strand cells are finished -- cross_lo / cross_hi -- and a cell that joins the strands
+// never sits in the loop that holds the nick, so the outside pass needs no nick sums.)
 
 // slice sl of SI of the interior-loop sum seen from the inner pair (k,l) (which can pair)
 template <class C>
-RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl, int SI) {
+RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl, int SI, bool generic = true) {
   const DevModel& M = *c.M;
   const int n = c.n, l = k + d;
   const int ddmax = n - 1 - d < MAXLOOP + 2 ? n - 1 - d : MAXLOOP + 2;
@@ -860,7 +811,7 @@ RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl
   double sI = 0., s1 = 0., sA = 0.;
   if (!(RP_DBG(c) & 1))
     interior_rows<-1>(sh, c.ptr(T_OUTI, d, k), c.ptr(T_OUT1N, d, k), c.ptr(T_OUTAU, d, k), c.dstep(), c.pstep(), u1max,
-                      maxu2, ddmax, sl, SI, sI, s1, sA);
+                      maxu2, ddmax, sl, SI, sI, s1, sA, generic);
   double accI = M.mmI[t2][sq1][sp1] * sI + M.mm1n[t2][sq1][sp1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
   for (int s = sl; s < RP_N_SPECIAL; s += SI) {
     int u1, u2;
@@ -922,19 +873,6 @@ RP_HD void outside_finish(C& c, int d, int k, int type, double sI, double sP, do
           ext_stem(M, type, (k > 1 && ss(c, k - 1, k)) ? base(c, k - 1) : -1, (l < n && ss(c, l, l + 1)) ? base(c, l + 1) : -1);
     out += sI;
     if (mlr && k > 1 && ss(c, k - 1, k)) out += (PMLB + sL) * ml_stem(M, type, base(c, k - 1), base(c, l + 1)) * scale2;
-    if (c.cp > 0) {
-      if (k >= c.cp) {
-        const double qo = VEC(c, V_QROUT, l);
-        if (qo != 0.)
-          out += qo * (k > c.cp ? TB(c, T_Q, k - 1 - c.cp, c.cp) : 1.0) *
-                 ext_stem(M, type, k > c.cp ? base(c, k - 1) : -1, base(c, l + 1));
-      } else if (l < c.cp) {
-        const double qo = VEC(c, V_QLOUT, k);
-        if (qo != 0.)
-          out += qo * (l + 1 <= c.cp - 1 ? TB(c, T_Q, c.cp - 2 - l, l + 1) : 1.0) *
-                 ext_stem(M, type, base(c, k - 1), l + 1 < c.cp ? base(c, l + 1) : -1);
-      }
-    }
   }
   TB(c, T_OUT, d, k) = out;
   double fI = 0., f1 = 0., fA = 0., mc = 0.;
@@ -1053,14 +991,14 @@ RP_HD void outside_band_B(Ctx& c, const Shared& sh, int d0, int r0, int C, int t
   }
 }
 // per diagonal, phase A: interior-loop items, partials to sh.part[tid]
-RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid, bool generic = true) {
   const int T = sh.T;
   if (c.n - 1 - d < 2) return;
   const ISplit is = make_isplit(c, d, i0, C, T);
   const int r = tid % is.cntp, sl = tid / is.cntp;
   if (sl < is.SI && r < is.cnt) {
     const int k = listp(c)[(size_t)d * c.ld + is.lo + r];
-    sh.part[tid] = outside_interior(c, sh, d, k, sl, is.SI);
+    sh.part[tid] = outside_interior(c, sh, d, k, sl, is.SI, generic);
   }
 }
 RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
@@ -1089,6 +1027,13 @@ RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
 //   outside, band d0 .. d0-W+1, cell of diagonal d0-e: term b (operand Mc or PRML on diagonal d+2+b)
 //     is far iff b >= e (diagonals >= d0+2 are final when the pass runs)
 // ---------------------------------------------------------------------------
+// prologue of the wide schedule: the row-major copy of qm vanishes on diagonals <= TURN like the table itself
+RP_HD void prologue_rowmajor(const Ctx& c, int ct, int nct) {
+  for (int x = ct; x < (TURN + 1) * c.n; x += nct) {
+    const int d = x / c.n, i = 1 + x % c.n;
+    if (i + d <= c.n) *c.rptr(T_QMR, i, i + d) = 0.;
+  }
+}
 template <int W>
 RP_HD int wide_start_inside(int d) { return TURN + 1 + (d - TURN - 1) / W * W; }
 template <int W>
@@ -1202,11 +1147,11 @@ RP_HD void wide_outside_A(const Ctx& c, const Shared& sh, int d0, int r0, int C,
         if (need) {
           const int ifar = k0 - 2;
           for (int i = 1 + slice; i <= ifar; i += S) {
-            const double A = TB(c, T_PRML, l - i, i);
-            const double* B = c.ptr(T_QM, 0, i + 1) + (long)(k0 - 2 - i) * ds;   // qm(i+1, k0-1); per e one diagonal up
+            const double A = *c.rptr(T_PRMLR, i, l);
+            const double* B = c.rptr(T_QMR, i + 1, k0 - 1);   // qm(i+1, k0-1+e)
             const int emin = i - k0 + TURN + 3;
             for (int e = 0; e < W; e++)
-              if (e >= emin && ((need >> e) & 1)) ml[e] += A * B[(long)e * ds];
+              if (e >= emin && ((need >> e) & 1)) ml[e] += A * B[e];
           }
         }
       }
@@ -1236,8 +1181,182 @@ RP_HD void wide_outside_B(Ctx& c, const Shared& sh, int d0, int r0, int C, int t
   }
 }
 // per diagonal, phase B of the wide schedule: as inside_B, plus the near terms
+// how generic_items deals a chunk of C cells out over the warps (the finishes read the partials back the same way)
+struct GSplit {
+  int NG, nb, wpb, cap;   // groups of 8 cells, blocks of 32 groups, warps (= bins) per block, cells per bin row
+};
+RP_HD GSplit make_gsplit(int C, int T) {
+  GSplit g;
+  g.NG = (C + 7) / 8;
+  g.nb = (g.NG + 31) / 32;
+  g.wpb = (T / 32) / g.nb;
+  if (g.wpb < 1) g.wpb = 1;
+  g.cap = g.nb * 256;
+  return g;
+}
+RP_HD double generic_partials(const Shared& sh, int C, int cell) {
+  const GSplit gs = make_gsplit(C, sh.T);
+  double t = 0.;
+  for (int b = 0; b < gs.wpb; b++) t += sh.gpart[(size_t)b * gs.cap + cell];
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+// The rest of a staged chunk's interior sums: per pairable cell five items, each one batched strided walk
+// (kind-major, so the lanes of a warp run the same walk for neighbouring cells):
+//   0  bulges on the 5' side of the inner pair   u1 = 0, u2 = 2..      2  bulges on the 3' side      u2 = 0, u1 = 2..
+//   1  1xn loops, single base 5'                 u1 = 1, u2 = 3..      3  1xn loops, single base 3'  u2 = 1, u1 = 2..
+//   4  the table-driven small shapes
+// Partial (kind, cell r) goes to sh.part[kind * cntp + r], closing factor included.
+// ---------------------------------------------------------------------------
+RP_HD double row_sum8(const double* g, const double* p, long step, int lo, int hi) {
+  double a[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) a[u] = 0.;
+  const double* q = p + (long)lo * step;
+  g += lo;
+  int cnt = hi - lo + 1;
+#pragma unroll 1
+  for (; cnt >= 8; cnt -= 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = q[u * step];
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[u] += g[u] * v[u];
+    g += 8;
+    q += 8 * step;
+  }
+  {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 7; u++) v[u] = u < cnt ? q[u * step] : 0.;
+#pragma unroll
+    for (int u = 0; u < 7; u++) a[u] += (u < cnt ? g[u] : 0.) * v[u];
+  }
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+// the four walks.  TA / T1 point at the cell's own entry of the bulge / 1xn class tables (see interior_rows for
+// SIGN, the strides and the bounds).
+template <int SIGN>
+RP_HD double ends_walk(const Shared& sh, int kind, const double* TA, const double* T1, int ds, int ps, int u1max, int u2cap,
+                       int ddmax) {
+  const long step = -(long)SIGN * ds, across = -(long)SIGN * (ds - ps);
+  const long o0 = -(long)SIGN * (2L * ds - ps);   // element (u1 = 0, u2 = 0); (u1, u2) at o0 + u1*across + u2*step
+  if (u1max < 0 || u2cap < 0) return 0.;
+  if (kind == 0) {
+    int hi = MAXLOOP;
+    if (u2cap < hi) hi = u2cap;
+    if (ddmax - 2 < hi) hi = ddmax - 2;
+    return hi >= 2 ? row_sum8(sh.grow, TA + o0, step, 2, hi) : 0.;
+  }
+  if (kind == 1) {
+    if (u1max < 1) return 0.;
+    int hi = MAXLOOP - 1;
+    if (u2cap < hi) hi = u2cap;
+    if (ddmax - 3 < hi) hi = ddmax - 3;
+    return hi >= 3 ? row_sum8(sh.grow + GROW_LD, T1 + o0 + across, step, 3, hi) : 0.;
+  }
+  if (kind == 2) return u1max >= 2 ? row_sum8(sh.ghead_b, TA + o0, across, 2, u1max) : 0.;
+  int hi = u1max;
+  if (MAXLOOP - 1 < hi) hi = MAXLOOP - 1;
+  if (ddmax - 3 < hi) hi = ddmax - 3;
+  return (u2cap >= 1 && hi >= 2) ? row_sum8(sh.ghead_1, T1 + o0 + step, across, 2, hi) : 0.;
+}
+RP_HD double inside_ends_item(const Ctx& c, const Shared& sh, int d, int i, int kind) {
+  const DevModel& M = *c.M;
+  const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
+  if (ddmax < 2) return 0.;
+  const int j = i + d, type = pair_type(base(c, i), base(c, j));
+  const int maxpo = (c.cp > 0 && i < c.cp) ? c.cp - 1 - i : 1000;
+  const int maxu2 = (c.cp > 0 && j >= c.cp) ? j - 1 - c.cp : 1000;
+  const int si1 = base(c, i + 1), sj1 = base(c, j - 1);
+  if (kind < 4) {
+    int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
+    if (maxpo - 1 < u1max) u1max = maxpo - 1;
+    const double w = ends_walk<1>(sh, kind, c.ptr(T_QBAU, d, i), c.ptr(T_QB1N, d, i), c.dstep(), c.pstep(), u1max, maxu2, ddmax);
+    return w * ((kind & 1) ? M.mm1n[type][si1][sj1] : (type > 2 ? M.expTermAU : 1.0));
+  }
+  // all nine inner pairs fetched before any is used
+  double qv[RP_N_SPECIAL];
+  int t2v[RP_N_SPECIAL];
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) {
+    int u1, u2;
+    special_uv(s, u1, u2);
+    const int dd = u1 + u2 + 2;
+    const bool ok = dd <= ddmax && u1 + 1 <= maxpo && u2 <= maxu2;
+    const int k = i + 1 + u1, l = j - 1 - u2;
+    t2v[s] = ok ? pair_type(base(c, k), base(c, l)) : 0;
+    qv[s] = t2v[s] ? TB(c, T_QB, d - dd, k) : 0.;
+  }
+  double acc = 0.;
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) {
+    if (!t2v[s]) continue;
+    int u1, u2;
+    special_uv(s, u1, u2);
+    const int k = i + 1 + u1, l = j - 1 - u2;
+    acc += qv[s] * special_loop(M, s, type, rtype(t2v[s]), si1, sj1, base(c, k - 1), base(c, l + 1));
+  }
+  return acc;
+}
+RP_HD double outside_ends_item(const Ctx& c, const Shared& sh, int d, int k, int kind) {
+  const DevModel& M = *c.M;
+  const int n = c.n, l = k + d;
+  const int ddmax = n - 1 - d < MAXLOOP + 2 ? n - 1 - d : MAXLOOP + 2;
+  if (ddmax < 2) return 0.;
+  int maxpo = k - 1, maxu2 = n - l - 1;
+  if (c.cp > 0) {
+    if (k >= c.cp && k - c.cp < maxpo) maxpo = k - c.cp;
+    if (l < c.cp && c.cp - 2 - l < maxu2) maxu2 = c.cp - 2 - l;
+  }
+  if (maxpo < 1 || maxu2 < 0 || TB(c, T_QB, d, k) == 0.) return 0.;
+  const int type = pair_type(base(c, k), base(c, l));
+  const int t2 = rtype(type), sp1 = base(c, k - 1), sq1 = base(c, l + 1);
+  if (kind < 4) {
+    int u1max = ddmax - 2 < MAXLOOP ? ddmax - 2 : MAXLOOP;
+    if (maxpo - 1 < u1max) u1max = maxpo - 1;
+    const double w = ends_walk<-1>(sh, kind, c.ptr(T_OUTAU, d, k), c.ptr(T_OUT1N, d, k), c.dstep(), c.pstep(), u1max, maxu2, ddmax);
+    return w * ((kind & 1) ? M.mm1n[t2][sq1][sp1] : (type > 2 ? M.expTermAU : 1.0));
+  }
+  double ov[RP_N_SPECIAL];
+  int t1v[RP_N_SPECIAL];
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) {
+    int u1, u2;
+    special_uv(s, u1, u2);
+    const int dd = u1 + u2 + 2;
+    const bool ok = dd <= ddmax && u1 + 1 <= maxpo && u2 <= maxu2;
+    const int i = k - 1 - u1, j = l + 1 + u2;
+    t1v[s] = ok ? pair_type(base(c, i), base(c, j)) : 0;
+    ov[s] = t1v[s] ? TB(c, T_OUT, d + dd, i) : 0.;
+  }
+  double acc = 0.;
+#pragma unroll
+  for (int s = 0; s < RP_N_SPECIAL; s++) {
+    if (!t1v[s] || ov[s] == 0.) continue;
+    int u1, u2;
+    special_uv(s, u1, u2);
+    const int i = k - 1 - u1, j = l + 1 + u2;
+    acc += ov[s] * special_loop(M, s, t1v[s], t2, base(c, i + 1), base(c, j - 1), sp1, sq1);
+  }
+  return acc;
+}
+template <int SIGN>
+RP_HD void ends_items(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T;
+  if ((SIGN > 0 ? d - (TURN + 1) : c.n - 1 - d) < 2) return;
+  const ISplit is = make_isplit(c, d, i0, C, T);
+  const uint16_t* L = listp(c) + (size_t)d * c.ld + is.lo;
+  for (int x = tid; x < GS_KINDS * is.cntp; x += T) {
+    const int kind = x / is.cntp, r = x - kind * is.cntp;
+    if (r >= is.cnt) continue;
+    sh.part[x] = SIGN > 0 ? inside_ends_item(c, sh, d, L[r], kind) : outside_ends_item(c, sh, d, L[r], kind);
+  }
+}
+
 template <int W>
-RP_HD void wide_inside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+RP_HD void wide_inside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, int tid, bool staged = false) {
   const int T = sh.T;
   if (tid >= C) return;
   const int i = i0 + tid;
@@ -1248,10 +1367,14 @@ RP_HD void wide_inside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, in
   if (type && d - (TURN + 1) >= 2) {
     const ISplit is = make_isplit(c, d, i0, C, T);
     const int r = (int)posp(c)[(size_t)d * c.ld + i] - is.lo;
-    for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+    const int NS = staged ? GS_KINDS : is.SI;
+    for (int s = 0; s < NS; s++) sI += sh.part[s * is.cntp + r];
+    if (staged)   // the generic-class taps, summed densely out of the staged tile (generic_items)
+      sI += c.M->mmI[type][base(c, i + 1)][base(c, i + d - 1)] * generic_partials(sh, C, i - i0);
   }
   TB(c, T_QM2, d, i) = sM;   // complete now: the closing sum of (i-1,i+d+1) and the unpaired-window pass read it
   inside_finish(c, d, i, type, sI, sM, sQ);
+  *c.rptr(T_QMR, i, i + d) = TB(c, T_QM, d, i);
 }
 // near terms of cell (k, k+d): Mc / PRML on diagonals d+2+b < d0+2, i.e. b < e = d0-d
 template <int W>
@@ -1262,7 +1385,7 @@ RP_HD void outside_near(const Ctx& c, int d, int k, bool pairs, double& sP, doub
     for (int cc = TURN + 1; cc < e && cc <= k - 3; cc++) sL += TB(c, T_PRML, d + 2 + cc, k - 2 - cc) * TB(c, T_QM, cc, k - 1 - cc);
 }
 template <int W>
-RP_HD void wide_outside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+RP_HD void wide_outside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, int tid, bool staged = false) {
   const int T = sh.T;
   if (tid >= C) return;
   const int k = i0 + tid, l = k + d;
@@ -1274,10 +1397,108 @@ RP_HD void wide_outside_finish(Ctx& c, const Shared& sh, int d, int i0, int C, i
   if (pairs && c.n - 1 - d >= 2) {
     const ISplit is = make_isplit(c, d, i0, C, T);
     const int r = (int)posp(c)[(size_t)d * c.ld + k] - is.lo;
-    for (int s = 0; s < is.SI; s++) sI += sh.part[s * is.cntp + r];
+    const int NS = staged ? GS_KINDS : is.SI;
+    for (int s = 0; s < NS; s++) sI += sh.part[s * is.cntp + r];
+    if (staged && k > 1 && l < c.n)
+      sI += c.M->mmI[rtype(type)][base(c, l + 1)][base(c, k - 1)] * generic_partials(sh, C, k - i0);
   }
   if (c.kind == KIND_LINEAR && c.max_w > 0) RP_ST_STREAM(TB(c, T_XX, d, k), sP);   // PR for the unpaired-window pass
   outside_finish(c, d, k, type, sI, sP, sL);
+  *c.rptr(T_PRMLR, k, l) = TB(c, T_PRML, d, k);
+}
+
+// ---------------------------------------------------------------------------
+// Staged generic interior sums (see the note at struct Shared).  Chunk = cells i0 .. i0+C-1 of diagonal d (one strand
+// segment: `crossing` says the cells join the strands, which confines their inner pairs to inter-strand cells too).
+// Tile row s (6 <= s <= smax) holds the class row of diagonal d -/+ (2+s) from position P(s) on, P(s) = i0+1 inside,
+// i0-1-s outside; element e of a row at ((e & 7) * LT/8 + (e >> 3)), so that the 32 lanes of a warp, which own 32
+// consecutive groups of 8 cells, read 32 consecutive doubles.  Cell r of group g, tap t reads element 8g + r + t.
+// ---------------------------------------------------------------------------
+RP_HD int gs_smax(int n, int d, int SIGN) {
+  const int m = SIGN > 0 ? d - 6 : n - 3 - d;
+  return m < MAXLOOP ? m : MAXLOOP;
+}
+template <int SIGN>
+RP_HD void stage_generic_tile(const Ctx& c, const Shared& sh, int d, int i0, int C, bool crossing, int tid) {
+  const int T = sh.T, n = c.n, LT = gs_lt(T), L8 = LT / 8;
+  const int smax = gs_smax(n, d, SIGN);
+  const int nrows = smax - GS_ROW0 + 1;
+  if (nrows <= 0) return;
+  const int len = ((C + 7) & ~7) + MAXLOOP + 8;   // elements any group of the chunk can reach (<= LT)
+  const int total = nrows * len;
+  constexpr int NL = 8;                            // loads in flight per thread
+  for (int x0 = tid; x0 < total; x0 += NL * T) {
+    double v[NL];
+    int dst[NL];
+#pragma unroll
+    for (int u = 0; u < NL; u++) {
+      const int x = x0 + u * T;
+      v[u] = 0.; dst[u] = -1;
+      if (x < total) {
+        const int row = x / len, e = x - row * len, sdiag = GS_ROW0 + row;
+        const int dr = d - SIGN * (2 + sdiag);
+        const int pos = (SIGN > 0 ? i0 + 1 : i0 - 1 - sdiag) + e;
+        int plo = 1, phi = n - dr;
+        if (crossing) { if (c.cp - dr > plo) plo = c.cp - dr; if (c.cp - 1 < phi) phi = c.cp - 1; }
+        if (pos >= plo && pos <= phi) v[u] = TB(c, SIGN > 0 ? T_QBI : T_OUTI, dr, pos);
+        dst[u] = row * LT + (e & 7) * L8 + (e >> 3);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NL; u++)
+      if (dst[u] >= 0) sh.gtile[dst[u]] = v[u];
+  }
+}
+// one warp: the rows of its bin for the 32 groups of its block; lane = group; partial sums to gpart[bin][cell]
+template <int SIGN>
+RP_HD void generic_items(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
+  const int T = sh.T, LT = gs_lt(T), L8 = LT / 8;
+  const GSplit gs = make_gsplit(C, T);
+  const int warp = tid >> 5, lane = tid & 31;
+  const int blk = warp / gs.wpb, bin = warp - blk * gs.wpb;
+  if (blk >= gs.nb) return;
+  const int g = blk * 32 + lane;
+  const int smax = gs_smax(c.n, d, SIGN), nrows = smax - GS_ROW0 + 1;
+  double tot[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) tot[r] = 0.;
+  if (g < gs.NG) {
+    // rows dealt out long / short alternately, so that every bin gets about the same number of taps
+    for (int idx = bin; idx < nrows; idx += gs.wpb) {
+      const int s = (idx & 1) ? GS_ROW0 + (idx >> 1) : smax - (idx >> 1);
+      const double* row = sh.gtile + (size_t)(s - GS_ROW0) * LT + g;   // element 8g + c at row[(c & 7) * L8 + (c >> 3)]
+#define RP_GX(cc) (((cc) & 7) * L8 + ((cc) >> 3))
+      double win[8];
+#pragma unroll
+      for (int r = 0; r < 7; r++) win[r] = row[RP_GX(2 + r)];
+      win[7] = 0.;
+      const int nst = s - 3;   // taps t = 2 .. s-2; step x loads element 9 + x, weight g(2+x, s-2-x)
+      int x = 0;
+#pragma unroll 1
+      for (; x + 8 <= nst; x += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          win[(u + 7) & 7] = row[RP_GX(9 + u) + (x >> 3)];
+          const double gv = sh.grow[(2 + x + u) * GROW_LD + (s - 2 - x - u)];
+#pragma unroll
+          for (int r = 0; r < 8; r++) tot[r] += gv * win[(u + r) & 7];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 7; u++) {
+        if (x + u < nst) {
+          win[(u + 7) & 7] = row[RP_GX(9 + u) + (x >> 3)];
+          const double gv = sh.grow[(2 + x + u) * GROW_LD + (s - 2 - x - u)];
+#pragma unroll
+          for (int r = 0; r < 8; r++) tot[r] += gv * win[(u + r) & 7];
+        }
+      }
+#undef RP_GX
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+    if (8 * g + r < gs.cap) sh.gpart[(size_t)bin * gs.cap + 8 * g + r] = tot[r];
 }
 
 // ---------------------------------------------------------------------------

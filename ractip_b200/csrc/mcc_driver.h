@@ -18,7 +18,7 @@
 namespace rp {
 
 enum {
-  PH_STAGE = 0, PH_PROLOGUE, PH_PROLOGUE2, PH_INSIDE_A, PH_INSIDE_B, PH_NICK1, PH_NICK2, PH_OUTSIDE_A, PH_OUTSIDE_B,
+  PH_STAGE = 0, PH_PROLOGUE, PH_PROLOGUE2, PH_INSIDE_A, PH_INSIDE_B, PH_GENERIC_IN, PH_GENERIC_OUT, PH_OUTSIDE_A, PH_OUTSIDE_B,
   PH_WRITE_BP, PH_UN_HAIRPIN, PH_UN_GAPS0, PH_UN_GAPS1, PH_UN_DOMROWS, PH_UN_DOMCOLS, PH_UN_MLTAB, PH_UN_WINDOWS,
   PH_WRITE_HP, PH_LOGZ, PH_BAND_A, PH_BAND_B, PH_CFAC, PH_COUNT
 };
@@ -204,7 +204,10 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
     prologue_vectors(c, tid, T);
     prologue_lists(c, tid, T);
   });
-  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, tid, T); });
+  ex.phase(PH_PROLOGUE2, [&](int tid) {
+    prologue2(c, tid, T);
+    prologue_rowmajor(c, tid, T);
+  });
 
   for (int d = TURN + 1; d <= n - 1; d++) {
     if (d == wide_start_inside<W>(d)) {
@@ -231,12 +234,35 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
         });
       }
     }
+    // Chunks of up to T cells that do not straddle a strand segment (both ends on strand 1 / joining the strands /
+    // both on strand 2): the generic-class taps of a chunk are summed densely out of a shared-memory tile
+    // (stage_generic_tile + generic_items), the ends and the table-driven shapes per cell (inside_A).
     const int cells = n - d;
-    const int chunk = cells < T ? cells : T;
-    for (int i0 = 1; i0 <= cells; i0 += chunk) {
-      const int C = cells - i0 + 1 < chunk ? cells - i0 + 1 : chunk;
-      ex.phase(PH_INSIDE_A, [&](int tid) { inside_A(c, sh, d, i0, C, tid); });
-      ex.phase(PH_INSIDE_B, [&](int tid) { wide_inside_finish<W>(c, sh, d, i0, C, tid); });
+    int sb[4] = {1, cells + 1, cells + 1, cells + 1};
+    if (c.cp > 0) {
+      int b1 = c.cp - d, b2 = c.cp;
+      if (b1 < 1) b1 = 1;
+      if (b1 > cells + 1) b1 = cells + 1;
+      if (b2 > cells + 1) b2 = cells + 1;
+      if (b2 < b1) b2 = b1;
+      sb[1] = b1; sb[2] = b2;
+    }
+    const bool staged = W > BAND && gs_smax(n, d, 1) >= GS_ROW0;   // (the tile lives in the wide builds' partial-sum buffer)
+    for (int sgm = 0; sgm < 3; sgm++) {
+      for (int i0 = sb[sgm]; i0 < sb[sgm + 1]; i0 += T) {
+        const int C = sb[sgm + 1] - i0 < T ? sb[sgm + 1] - i0 : T;
+        const bool crossing = c.cp > 0 && sgm == 1;
+        ex.phase(PH_INSIDE_A, [&](int tid) {
+          if (staged) {
+            stage_generic_tile<1>(c, sh, d, i0, C, crossing, tid);
+            ends_items<1>(c, sh, d, i0, C, tid);
+          } else {
+            inside_A(c, sh, d, i0, C, tid);
+          }
+        });
+        if (staged) ex.phase(PH_GENERIC_IN, [&](int tid) { generic_items<1>(c, sh, d, i0, C, tid); });
+        ex.phase(PH_INSIDE_B, [&](int tid) { wide_inside_finish<W>(c, sh, d, i0, C, tid, staged); });
+      }
     }
   }
   inside_end(c);
@@ -273,10 +299,19 @@ RP_HD void solve_mcc_wide(Exec& ex, Ctx& c, const Problem& p, float* dense, doub
     }
     const int lo = cross_lo(c, d), hi = cross_hi(c, d), cells = hi - lo + 1;
     const int chunk = cells < T ? cells : T;
+    const bool staged = W > BAND && gs_smax(n, d, -1) >= GS_ROW0;
     for (int i0 = lo; i0 <= hi; i0 += chunk) {
       const int C = hi - i0 + 1 < chunk ? hi - i0 + 1 : chunk;
-      ex.phase(PH_OUTSIDE_A, [&](int tid) { outside_A(c, sh, d, i0, C, tid); });
-      ex.phase(PH_OUTSIDE_B, [&](int tid) { wide_outside_finish<W>(c, sh, d, i0, C, tid); });
+      ex.phase(PH_OUTSIDE_A, [&](int tid) {
+        if (staged) {
+          stage_generic_tile<-1>(c, sh, d, i0, C, false, tid);   // (enclosing pairs of inter-strand cells join the strands anyway)
+          ends_items<-1>(c, sh, d, i0, C, tid);
+        } else {
+          outside_A(c, sh, d, i0, C, tid);
+        }
+      });
+      if (staged) ex.phase(PH_GENERIC_OUT, [&](int tid) { generic_items<-1>(c, sh, d, i0, C, tid); });
+      ex.phase(PH_OUTSIDE_B, [&](int tid) { wide_outside_finish<W>(c, sh, d, i0, C, tid, staged); });
     }
   }
   emit_outputs(ex, c, p, dense, *c.M, &c.M->gfull[0][0]);
@@ -317,7 +352,10 @@ __device__ void solve_mcc_cluster(Exec& ex, Ctx& c, const Problem& p, float* den
     prologue_lists(c, R * T + tid, GT);
   });
   ex.csync();
-  ex.phase(PH_PROLOGUE2, [&](int tid) { prologue2(c, R * T + tid, GT); });
+  ex.phase(PH_PROLOGUE2, [&](int tid) {
+    prologue2(c, R * T + tid, GT);
+    prologue_rowmajor(c, R * T + tid, GT);
+  });
   ex.csync();
 
   for (int d = TURN + 1; d <= n - 1; d++) {
@@ -483,9 +521,6 @@ RP_HD void solve_band(Exec& ex, Ctx& c, const Problem& p, float* dense, double* 
   }
 
   // ---- outside: diagonals n-1 .. TURN+1; step d completes diagonal d+1 and runs the items of d.
-  // Nick sums of diagonal x (outside_nick1/2, they need out of every diagonal > x) ride along one
-  // step late as well: first half in the long phase of step x-1, second half in the quick phase
-  // after it; their results are first read when diagonal x-1 is completed, in step x-2.
   if (n - 1 >= TURN + 1)
     ex.phase(PH_CFAC, [&](int tid) { if (tid == 0) band_make_desc(bs.desc[(n - 1) & (NDESC - 1)], n, c.cp, n - 1, T, true); });
   ex.phase(PH_CFAC, [&](int tid) { band_collect<-1>(c, bs, -1, n - 1 >= TURN + 1 ? n - 1 : -1, tid, T); });

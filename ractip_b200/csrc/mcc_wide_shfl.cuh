@@ -221,8 +221,8 @@ __device__ __forceinline__ void wide_outside_A_shfl(const Ctx& c, const Shared& 
         for (int u = 0; u < NB; u++) {
           const int iu = i + u * S;
           const int row0 = k0 - 2 - iu;   // diagonal of this lane's e = 0 element
-          A[u] = (need != 0 && iu <= ifar) ? ld_stream(c.ptr(T_PRML, l - iu, iu)) : 0.;
-          b0[u] = (iu <= ifar_hi && row0 >= 0 && k0 - 1 <= n) ? ld_stream(c.ptr(T_QM, 0, iu + 1) + (long)row0 * ds) : 0.;   // qm(iu+1, k0-1)
+          A[u] = (need != 0 && iu <= ifar) ? ld_stream(c.rptr(T_PRMLR, iu, l)) : 0.;   // (row-major copies: lanes are neighbours)
+          b0[u] = (iu <= ifar_hi && row0 >= 0 && k0 - 1 <= n) ? ld_stream(c.rptr(T_QMR, iu + 1, k0 - 1)) : 0.;
         }
 #pragma unroll
         for (int u = 0; u < NB; u++) {
