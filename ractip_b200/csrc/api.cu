@@ -104,7 +104,6 @@ struct rp_batch {
   int n_defer = 0;
   size_t defer_slot = 0;      // doubles per private workspace
   int defer_maxn = 0;
-  double* d_ws_up = nullptr;
   int* d_done = nullptr;      // completion flags of the deferred problems (indexed by problem)
   int up_mode = 0;            // 0: pass fused with the wavefronts, 1: unstru_kernel after them, 2: jobs of their own inside the band kernel
   int up_grid = -1;
@@ -468,7 +467,7 @@ int rp_batch_destroy(rp_batch* b) {
   if (b->ctx) {
     rp_ctx* ctx = b->ctx;
     for (void* p : {(void*)b->d_seq, (void*)b->d_probs, (void*)b->d_order, (void*)b->d_counter, (void*)b->d_dense,
-                    (void*)b->d_logz, (void*)b->d_ws_up, (void*)b->d_done, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
+                    (void*)b->d_logz, (void*)b->d_done, (void*)b->d_spairs, (void*)b->d_recs, (void*)b->d_ups, (void*)b->d_counts})
       pool_release(ctx, p);
     ctx->live_batches--;
     if (ctx->closing && ctx->live_batches == 0) {
@@ -694,10 +693,16 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   if ((e = pool_alloc(ctx, &b->d_probs, std::max<size_t>(1, np) * sizeof(Problem))) != cudaSuccess) return bail(e, "cudaMalloc probs");
   if ((e = pool_alloc(ctx, &b->d_order, std::max<size_t>(1, b->order.size()) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc order");
   if ((e = pool_alloc(ctx, &b->d_done, std::max<size_t>(1, np) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc done");
-  if (b->n_defer && pool_alloc(ctx, &b->d_ws_up, b->defer_slot * sizeof(double) * (size_t)b->n_defer) != cudaSuccess) {
-    // no room for the private workspaces: keep the pass fused with the wavefronts
-    cudaGetLastError();
-    b->d_ws_up = nullptr;
+  // The private workspaces of the deferred passes are part of the context's workspace (grown on demand by rp_batch_run,
+  // kept between calls).  If the device cannot hold them, the pass stays fused with the wavefronts.
+  bool up_fits = true;
+  if (b->n_defer) {
+    const size_t need = b->defer_slot * sizeof(double) * (size_t)b->n_defer;
+    size_t free_b = 0, total_b = 0;
+    if (need > ctx->ws_bytes && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+      up_fits = need <= (free_b + ctx->ws_bytes + pool_cached_bytes(ctx)) / 10 * 6;
+  }
+  if (b->n_defer && !up_fits) {
     for (auto& q : b->probs) { q.defer_up = 0; q.ws_off = -1; }
     if (b->up_mode == 1) b->order.resize(b->order.size() - (size_t)b->n_defer);
     else {   // drop the unpaired-window jobs from the band queues
@@ -764,14 +769,15 @@ int rp_batch_run(rp_batch* b) {
   const size_t gen_bytes = (size_t)grid * slot_bytes;
   const size_t bandL_bytes = (size_t)b->band_grid[0] * band_slot[0] * sizeof(double);
   const size_t bandS_bytes = (size_t)b->band_grid[1] * band_slot[1] * sizeof(double);
-  int rc = ensure_workspace(ctx, gen_bytes + bandL_bytes + bandS_bytes);
+  const size_t up_bytes = b->n_defer ? b->defer_slot * sizeof(double) * (size_t)b->n_defer : 0;
+  int rc = ensure_workspace(ctx, gen_bytes + bandL_bytes + bandS_bytes + up_bytes);
   if (rc) return rc;
   const int n_bandall = b->n_band[0] + b->n_band[1];
   rp::BatchDev d;
   d.model = ctx->d_model; d.seq = b->d_seq; d.probs = b->d_probs; d.order = b->d_order + n_bandall; d.nprob = b->n_general;
   d.counter = b->d_counter; d.ws = ctx->ws; d.slot_stride = b->slot_doubles; d.nslots = std::max(grid, 1);
   d.dense = b->d_dense; d.logz = b->d_logz;
-  d.ws_up = b->d_ws_up; d.done = b->d_done;
+  d.ws_up = ctx->ws + (gen_bytes + bandL_bytes + bandS_bytes) / sizeof(double); d.done = b->d_done;
   d.prof = nullptr;
   d.dbg = std::getenv("RP_DEBUG_SKIP") ? std::atoi(std::getenv("RP_DEBUG_SKIP")) : 0;
   long long*& d_prof = ctx->d_prof;

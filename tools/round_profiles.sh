@@ -1,0 +1,12 @@
+#!/bin/bash
+# One GPU-box pass for a round: bench (both arms), the ncu launch list of the bench command, and --set full captures of
+# the dominant kernels.  Run as: gpurun -- "bash tools/round_profiles.sh"; outputs land in gpurun_out/.
+set -x
+cd $GRAFT_REPO_ROOT
+O=gpurun_out; mkdir -p $O
+timeout 900 python bench.py --impl reference > $O/${TAG:-r02j}_bench_reference.json 2> $O/${TAG:-r02j}_bench_reference.err
+timeout 900 python bench.py > $O/${TAG:-r02j}_bench.json 2> $O/${TAG:-r02j}_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG:-r02j}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${TAG:-r02j}_launches.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mcc_band_kernel|unstru_kernel" -c 3 -o $O/${TAG:-r02j}_band python tools/perf_probe.py --workload mica_ompa --num 1000 --reps 1 > $O/${TAG:-r02j}_ncu_band.log 2>&1
+timeout 800 ncu --set full --clock-control none --import-source on -k regex:mcc_persistent -c 1 -o $O/${TAG:-r02j}_general python tools/perf_probe.py --workload synthetic --num 148 --reps 1 > $O/${TAG:-r02j}_ncu_general.log 2>&1
+for f in $O/${TAG:-r02j}_bench.json $O/${TAG:-r02j}_bench_reference.json; do tail -n 2 $f; done
