@@ -1425,28 +1425,29 @@ RP_HD void stage_generic_tile(const Ctx& c, const Shared& sh, int d, int i0, int
   const int nrows = smax - GS_ROW0 + 1;
   if (nrows <= 0) return;
   const int len = ((C + 7) & ~7) + MAXLOOP + 8;   // elements any group of the chunk can reach (<= LT)
-  const int total = nrows * len;
+  // a warp takes (row, NL interleaved segments of 32 elements) items: consecutive lanes load consecutive positions
   constexpr int NL = 8;                            // loads in flight per thread
-  for (int x0 = tid; x0 < total; x0 += NL * T) {
+  const int nblk = (len + 32 * NL - 1) / (32 * NL);
+  const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5;
+  for (int it = warp; it < nrows * nblk; it += nwarp) {
+    const int row = it / nblk, blk = it - row * nblk, sdiag = GS_ROW0 + row;
+    const int dr = d - SIGN * (2 + sdiag);
+    const int pos0 = (SIGN > 0 ? i0 + 1 : i0 - 1 - sdiag);
+    int plo = 1, phi = n - dr;
+    if (crossing) { if (c.cp - dr > plo) plo = c.cp - dr; if (c.cp - 1 < phi) phi = c.cp - 1; }
+    const double* src = c.ptr(SIGN > 0 ? T_QBI : T_OUTI, dr, 0);
+    double* dstrow = sh.gtile + (size_t)row * LT;
     double v[NL];
-    int dst[NL];
 #pragma unroll
     for (int u = 0; u < NL; u++) {
-      const int x = x0 + u * T;
-      v[u] = 0.; dst[u] = -1;
-      if (x < total) {
-        const int row = x / len, e = x - row * len, sdiag = GS_ROW0 + row;
-        const int dr = d - SIGN * (2 + sdiag);
-        const int pos = (SIGN > 0 ? i0 + 1 : i0 - 1 - sdiag) + e;
-        int plo = 1, phi = n - dr;
-        if (crossing) { if (c.cp - dr > plo) plo = c.cp - dr; if (c.cp - 1 < phi) phi = c.cp - 1; }
-        if (pos >= plo && pos <= phi) v[u] = TB(c, SIGN > 0 ? T_QBI : T_OUTI, dr, pos);
-        dst[u] = row * LT + (e & 7) * L8 + (e >> 3);
-      }
+      const int e = (u * nblk + blk) * 32 + lane, pos = pos0 + e;
+      v[u] = (e < len && pos >= plo && pos <= phi) ? src[pos] : 0.;
     }
 #pragma unroll
-    for (int u = 0; u < NL; u++)
-      if (dst[u] >= 0) sh.gtile[dst[u]] = v[u];
+    for (int u = 0; u < NL; u++) {
+      const int e = (u * nblk + blk) * 32 + lane;
+      if (e < len) dstrow[(e & 7) * L8 + (e >> 3)] = v[u];
+    }
   }
 }
 // one warp: the rows of its bin for the 32 groups of its block; lane = group; partial sums to gpart[bin][cell]

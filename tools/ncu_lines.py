@@ -2,6 +2,7 @@
 """Aggregate an ncu report's per-instruction samples by CUDA source line.
 
     python tools/ncu_lines.py gpurun_out/prof.ncu-rep [kernel_substring] [top]
+    NCU_KERNEL=<name> ...   picks that kernel's launch out of a report that holds several (ncu --kernel-name)
 
 kernel_substring selects the SASS section by its MANGLED name: give enough of it to single out one template
 instance (mcc_band_kernelILi512ELi1, mcc_persistentILi1ELi10), or the line map of another instance is used.
@@ -42,7 +43,9 @@ for cubin in tmp.glob("*.cubin"):
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*?);", l)
         if m:
             addr2line[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+import os  # noqa: E402
+sel = ["--kernel-name", os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+out = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                      text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
