@@ -166,8 +166,8 @@ struct Shared {
 // s = 6..30 of the generic class table (diagonals d -/+ (2+s)) over the positions a chunk of cells can reach are
 // copied into shared memory once per chunk, zero where a position is invalid, and a thread walks a row for 8
 // neighbouring cells with a sliding register window (one shared load per 8 FMAs, no predicates) -- the band
-// kernel's scheme, per chunk instead of per problem.  The ends (bulge, 1xn) and the table-driven shapes stay with
-// the per-cell code (inside_interior / outside_interior with generic = false).
+// kernel's scheme, per chunk instead of per problem.  The ends (bulge, 1xn) and the table-driven shapes are five
+// batched items per pairable cell (ends_items).
 constexpr int GS_ROW0 = 6, GS_NROWS = MAXLOOP - GS_ROW0 + 1;             // rows 6..30
 RP_HD int gs_lt(int T) { return (T + MAXLOOP + 8 + 7) / 8 * 8; }          // elements per tile row (multiple of 8)
 constexpr int GS_KINDS = 5;   // ends_items: bulge row, 1xn row, bulge heads, 1xn heads, table-driven shapes
@@ -323,7 +323,7 @@ RP_HD double row_sum(const double* g, const double* p, int step, int lo, int hi)
 // u2 <= u2cap, u1+u2+2 <= ddmax; every element touched is a valid cell.
 template <int SIGN>
 RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, const double* TA, int ds, int ps,
-                         int u1max, int u2cap, int ddmax, int sl, int SI, double& sI, double& s1, double& sA, bool generic = true) {
+                         int u1max, int u2cap, int ddmax, int sl, int SI, double& sI, double& s1, double& sA) {
   const int step = -SIGN * ds;
   for (int q = sl; q <= MAXLOOP / 2; q += SI) {
     for (int h = 0; h < 2; h++) {
@@ -343,7 +343,7 @@ RP_HD void interior_rows(const Shared& sh, const double* TI, const double* T1, c
       } else {
         sA += sh.ghead_b[u1] * TA[o0];
         if (u2hi >= 1) s1 += sh.ghead_1[u1] * T1[o0 + step];
-        if (generic && u2hi >= 2) sI += row_sum(g, TI + o0, step, 2, u2hi);
+        if (u2hi >= 2) sI += row_sum(g, TI + o0, step, 2, u2hi);
       }
     }
   }
@@ -573,7 +573,7 @@ RP_HD void prologue2(C& c, int ct, int nct) {
 // ---------------------------------------------------------------------------
 // slice sl of SI of the interior-loop sum of a cell that can pair
 template <class C>
-RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int type, int sl, int SI, bool generic = true) {
+RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int type, int sl, int SI) {
   const DevModel& M = *c.M;
   const int ddmax = d - (TURN + 1) < MAXLOOP + 2 ? d - (TURN + 1) : MAXLOOP + 2;
   if (ddmax < 2) return 0.;
@@ -587,7 +587,7 @@ RP_HD double inside_interior(const C& c, const Shared& sh, int d, int i, int typ
   double sI = 0., s1 = 0., sA = 0.;
   if (!(RP_DBG(c) & 1))
     interior_rows<1>(sh, c.ptr(T_QBI, d, i), c.ptr(T_QB1N, d, i), c.ptr(T_QBAU, d, i), c.dstep(), c.pstep(), u1max, maxu2,
-                     ddmax, sl, SI, sI, s1, sA, generic);
+                     ddmax, sl, SI, sI, s1, sA);
   double accI = M.mmI[type][si1][sj1] * sI + M.mm1n[type][si1][sj1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
   // table-driven small loops
   for (int s = sl; s < RP_N_SPECIAL; s += SI) {
@@ -754,14 +754,14 @@ RP_HD void inside_band_B(Ctx& c, const Shared& sh, int d0, int i0, int C, int ti
   }
 }
 // per diagonal, phase A: interior-loop work items (pairable cell, slice), partials to sh.part[tid]
-RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid, bool generic = true) {
+RP_HD void inside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   const int T = sh.T;
   if (d - (TURN + 1) < 2) return;
   const ISplit is = make_isplit(c, d, i0, C, T);
   const int r = tid % is.cntp, sl = tid / is.cntp;
   if (sl < is.SI && r < is.cnt) {
     const int i = listp(c)[(size_t)d * c.ld + is.lo + r];
-    sh.part[tid] = inside_interior(c, sh, d, i, pair_type(base(c, i), base(c, i + d)), sl, is.SI, generic);
+    sh.part[tid] = inside_interior(c, sh, d, i, pair_type(base(c, i), base(c, i + d)), sl, is.SI);
   }
 }
 // per diagonal, phase B: one thread per cell
@@ -792,7 +792,7 @@ RP_HD void inside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
 
 // slice sl of SI of the interior-loop sum seen from the inner pair (k,l) (which can pair)
 template <class C>
-RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl, int SI, bool generic = true) {
+RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl, int SI) {
   const DevModel& M = *c.M;
   const int n = c.n, l = k + d;
   const int ddmax = n - 1 - d < MAXLOOP + 2 ? n - 1 - d : MAXLOOP + 2;
@@ -811,7 +811,7 @@ RP_HD double outside_interior(const C& c, const Shared& sh, int d, int k, int sl
   double sI = 0., s1 = 0., sA = 0.;
   if (!(RP_DBG(c) & 1))
     interior_rows<-1>(sh, c.ptr(T_OUTI, d, k), c.ptr(T_OUT1N, d, k), c.ptr(T_OUTAU, d, k), c.dstep(), c.pstep(), u1max,
-                      maxu2, ddmax, sl, SI, sI, s1, sA, generic);
+                      maxu2, ddmax, sl, SI, sI, s1, sA);
   double accI = M.mmI[t2][sq1][sp1] * sI + M.mm1n[t2][sq1][sp1] * s1 + (type > 2 ? M.expTermAU : 1.0) * sA;
   for (int s = sl; s < RP_N_SPECIAL; s += SI) {
     int u1, u2;
@@ -991,14 +991,14 @@ RP_HD void outside_band_B(Ctx& c, const Shared& sh, int d0, int r0, int C, int t
   }
 }
 // per diagonal, phase A: interior-loop items, partials to sh.part[tid]
-RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid, bool generic = true) {
+RP_HD void outside_A(const Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
   const int T = sh.T;
   if (c.n - 1 - d < 2) return;
   const ISplit is = make_isplit(c, d, i0, C, T);
   const int r = tid % is.cntp, sl = tid / is.cntp;
   if (sl < is.SI && r < is.cnt) {
     const int k = listp(c)[(size_t)d * c.ld + is.lo + r];
-    sh.part[tid] = outside_interior(c, sh, d, k, sl, is.SI, generic);
+    sh.part[tid] = outside_interior(c, sh, d, k, sl, is.SI);
   }
 }
 RP_HD void outside_B(Ctx& c, const Shared& sh, int d, int i0, int C, int tid) {
