@@ -394,8 +394,8 @@ def measure(args, stage, workload, pairs_all, desc, data, rank, world, local_ran
         launch_ms = statistics.mean(kern_ms) if kern_ms else tt.ms_total
         achieved = alg / (launch_ms * 1e-3) / 1e12
         traffic, traffic_src = traffic_record(workload)
-        if traffic is not None and workload == "synthetic":
-            traffic = traffic / 1000.0 * len(mine)      # recorded per 1000-pair launch
+        if traffic is not None and traffic_src and traffic_src.get("pairs_per_launch"):
+            traffic = traffic / traffic_src["pairs_per_launch"] * len(mine)   # scaled to this launch's pair count
         roofline = {
             "bound": "fp64_fma", "kernel": KERNELS[workload][0], "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
             "frac": achieved / fp64_tf if fp64_tf else None, "traffic": traffic, "traffic_source": traffic_src,

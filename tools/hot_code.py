@@ -3,6 +3,7 @@
 how many distinct SASS instructions carry the executed instruction stream, and where they sit.
 
     python tools/hot_code.py <report.ncu-rep> [bucket_bytes]
+    NCU_ARGS="--launch-count 1" ...   extra `ncu -i` selection arguments for reports that hold several launches
 """
 import csv
 import subprocess
@@ -10,7 +11,8 @@ import sys
 
 rep = sys.argv[1]
 bucket = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+import os  # noqa: E402
+out = subprocess.run(["ncu", "-i", rep, *os.environ.get("NCU_ARGS", "").split(), "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 lines = out.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.DictReader(lines[start:]))
