@@ -350,6 +350,26 @@ def test_configs4_size_pair_matches_oracle(model, oracle, monkeypatch, cluster):
     _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, "1000x500")
 
 
+@pytest.mark.parametrize("n1,n2,seed", [(745, 31, 5), (513, 512, 6), (700, 333, 7)])
+def test_long_ragged_pairs_match_oracle(model, oracle, monkeypatch, n1, n2, seed):
+    """The long-problem build (wide split-sum bands, staged interior tiles, row-major copies) on shapes that put
+    the chunk and strand-segment boundaries in odd places: a nick 31 nt from the 3' end, diagonals one cell longer than
+    the CTA width, a strand-2 segment shorter than a chunk.  RP_CLUSTER=0 keeps the batch's route (one CTA per problem)."""
+    from ractip_b200 import ProbabilityStage, default_opts
+    monkeypatch.setenv("RP_CLUSTER", "0")
+    monkeypatch.setenv("RP_MCC_LONG_N", "500")   # the 513-nt strands take the long build too
+    rng = np.random.default_rng(seed)
+    s1 = "".join("ACGU"[x] for x in rng.integers(0, 4, n1))
+    s2 = "".join("ACGU"[x] for x in rng.integers(0, 4, n2))
+    opts = default_opts()
+    st = ProbabilityStage(model)
+    try:
+        r = st.run_dense([(s1, s2)], opts, pinned=True)[0]
+    finally:
+        st.close()
+    _compare(r, _oracle_pair(oracle, s1, s2, opts), s1, s2, opts, f"{n1}x{n2}")
+
+
 def test_split_fetch_of_uniform_batches(stage, bundled, monkeypatch):
     """Shuffle batches (every pair the same lengths) whose problems fall into both band classes are fetched in
     two parts -- the long class's sections while the short class still runs -- and give the same bytes as the

@@ -13,7 +13,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 rep, frag = sys.argv[1], sys.argv[2]
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+import os  # noqa: E402
+out = subprocess.run(["ncu", "-i", rep, *os.environ.get("NCU_ARGS", "").split(), "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 lines = out.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 dyn = {}
@@ -52,17 +53,27 @@ for a, (e, s) in dyn.items():
     if e > thr * n_calls:
         x[0] += 1
     x[1] += e; x[2] += s
-# aggregate per file in blocks of source lines that are contiguous
-agg = collections.defaultdict(lambda: [0, 0, 0])
+# aggregate per enclosing source function (found by scanning the source files for definitions at column 0)
+_defs = {}
+def _load(f):
+    out = []
+    for path in list((ROOT / "ractip_b200" / "csrc").glob(f)) :
+        for n, line in enumerate(path.read_text().splitlines(), 1):
+            m = re.match(r"^(?:RP_HD|__device__|__global__|inline|static)\b[^;]*?\b(\w+)\s*\(", line)
+            if m and not line.rstrip().endswith(";"):
+                out.append((n, m.group(1)))
+    return out
 def region(f, l):
-    table = {
-        "mcc_band.h": [(0,150,"band:setup/weights"),(151,204,"band:segs/ldg"),(205,225,"band:ring_ld"),(226,335,"band:interior_item"),(336,405,"band:specials"),(406,454,"band:interior_A"),(455,472,"band:interior_sum"),(473,532,"band:cfac"),(533,657,"band:finish_in"),(658,720,"band:finish_out"),(721,760,"band:collect")],
-        "mcc_core.h": [(0,130,"core:ctx/off/tb"),(131,215,"core:misc"),(216,250,"core:pair_type/ss/stems"),(251,275,"core:special_loop"),(276,345,"core:hairpin/row_sum"),(346,440,"core:dots/multi_dot"),(441,570,"core:prologue"),(571,800,"core:inside generic"),(801,880,"core:nick"),(881,1130,"core:outside generic"),(1131,1335,"core:wide"),(1336,1635,"core:unstru"),(1636,1700,"core:outputs")],
-    }
-    for lo, hi, name in table.get(f, []):
-        if lo <= l <= hi:
-            return name
-    return f
+    if f not in _defs:
+        _defs[f] = _load(f)
+    name = None
+    for n, fn in _defs[f]:
+        if n <= l:
+            name = fn
+        else:
+            break
+    return f"{f.split('.')[0]}:{name}" if name else f
+agg = collections.defaultdict(lambda: [0, 0, 0])
 for (f, l), (h, e, s) in by.items():
     x = agg[region(f, l)]
     x[0] += h; x[1] += e; x[2] += s
