@@ -15,9 +15,11 @@ Capacities come from rp_sparse_plan (a bound, not a count), so every rank's
 buffer has the same size and no size exchange is needed.  torch.distributed does
 the transport (NCCL over NVLink on GPUs, gloo in the CPU tests); the kernels
 write straight into the buffer through rp_batch_sparse_device.  Stream order:
-rp_batch_sparse_device is asynchronous on the CONTEXT's stream; either make that
-the stream the collective runs on (rp_set_stream(torch's current stream), as
-bench.py does) or call DeviceBatch.sync() before gather().
+rp_batch_sparse_device is asynchronous on the CONTEXT's stream.  gather() therefore
+synchronises the batch that fill()ed the buffer before the collective, unless the
+caller made the context's stream the one the collective runs on
+(rp_set_stream(torch's current stream), as bench.py does) and says so with
+same_stream=True.
 """
 from __future__ import annotations
 
@@ -94,6 +96,7 @@ class ShardPlan:
         base = local.data_ptr()
         batch.stage._check(batch.lib.rp_batch_sparse_device(batch.handle, C.c_void_p(base), self.capacity(),
                                                             C.c_void_p(0), 0, C.c_void_p(base + self.rec_bytes)))
+        self._filled_by = batch   # gather() waits for it unless told that the collective runs on the same stream
 
     def rec_view(self, buf: np.ndarray) -> np.ndarray:
         """The record section of one rank's buffer as a structured array."""
@@ -101,11 +104,17 @@ class ShardPlan:
         usable = self.rec_bytes // REC_DTYPE.itemsize * REC_DTYPE.itemsize
         return buf[o_rec:o_rec + usable].view(REC_DTYPE)
 
-    def gather(self, local, group=None):
-        """The single collective of the path.  `local` is a uint8 tensor of nbytes (CUDA or CPU)."""
+    def gather(self, local, group=None, same_stream: bool = False):
+        """The single collective of the path.  `local` is a uint8 tensor of nbytes (CUDA or CPU).  The kernels that
+        fill() launched run on the CONTEXT's stream: unless the caller has made that the stream the collective runs on
+        (rp_set_stream with torch's current stream -- then pass same_stream=True), the batch is synchronised first."""
         import torch
         import torch.distributed as dist
         assert local.dtype == torch.uint8 and local.numel() == self.nbytes
+        filled_by = getattr(self, "_filled_by", None)
+        if filled_by is not None and not same_stream:
+            filled_by.sync()
+        self._filled_by = None
         out = torch.empty(self.world * self.nbytes, dtype=torch.uint8, device=local.device)
         if self.world == 1:
             out.copy_(local)
