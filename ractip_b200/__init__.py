@@ -12,6 +12,9 @@ from .stage import (DeviceBatch, PairProbabilities, PairRecords, ProbabilityStag
 from .ip import (IPModel, JointPrediction, default_ip_opts, energy_of_duplex, energy_of_structure,  # noqa: E402
                  solve_joint, solve_ss, zscore_statistic)
 
-__all__ = ["IPModel", "JointPrediction", "default_ip_opts", "energy_of_duplex", "energy_of_structure",
+from .frontend import (FastaRecord, PairResult, format_result, input_pairs, load_fasta, parse_fasta,  # noqa: E402
+                       predict)
+
+__all__ = ["FastaRecord", "PairResult", "format_result", "input_pairs", "load_fasta", "parse_fasta", "predict", "IPModel", "JointPrediction", "default_ip_opts", "energy_of_duplex", "energy_of_structure",
            "solve_joint", "solve_ss", "zscore_statistic", "DeviceBatch", "PairProbabilities", "PairRecords", "ProbabilityStage", "RpError",
            "bp_offsets", "default_model", "default_opts", "zscore_shuffles"]

@@ -107,6 +107,8 @@ EXPORTS = [
     # include/ractip_ip.h (host-side consumer: integer programme, energy evaluation)
     "rp_ip_opts_default", "rp_ip_build", "rp_ip_build_sparse", "rp_ip_build_ss", "rp_ip_dims", "rp_ip_export",
     "rp_ip_decode", "rp_ip_free", "rp_energy_of_structure", "rp_energy_of_duplex",
+    # include/ractip_io.h (many-pair front end: the reference's FASTA reader)
+    "rp_fasta_load", "rp_fasta_parse", "rp_fasta_count", "rp_fasta_get", "rp_fasta_free",
 ]
 
 _lib = None
@@ -172,6 +174,11 @@ def load() -> C.CDLL:
         "rp_ip_free": (None, [vp]),
         "rp_energy_of_structure": (i, [P(RpModel), C.c_char_p, C.c_char_p, i, i, P(C.c_float)]),
         "rp_energy_of_duplex": (i, [P(RpModel), C.c_char_p, i, C.c_char_p, i, C.c_char_p, C.c_char_p, P(C.c_float)]),
+        "rp_fasta_load": (i, [C.c_char_p, P(vp)]),
+        "rp_fasta_parse": (i, [C.c_char_p, sz, P(vp)]),
+        "rp_fasta_count": (i, [vp]),
+        "rp_fasta_get": (i, [vp, i, P(C.c_char_p), P(C.c_char_p), P(C.c_char_p)]),
+        "rp_fasta_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
