@@ -227,3 +227,33 @@ def test_energy_of_duplex_and_zscore(model, bundled):
     a, b = zscore_statistic(-20.0, -9.0, [(-10.0, -6.0), (-12.0, -7.0), (-8.0, -5.0), (-10.0, -6.0)])
     assert a == pytest.approx((-20.0 + 10.0) / math.sqrt(2.0), rel=1e-5)
     assert b == pytest.approx((-11.0 + 4.0) / math.sqrt(0.5), rel=1e-5)
+
+
+def test_readme_window_does_not_hinge_on_the_recalled_tables(bundled):
+    """The one place where the README answer and this pipeline part (see the module docstring) is the accessible
+    window 11..23 of DIS: P(unpaired) = 0.0038 here, <= 0.003 in the run that made the README.  The Turner-2004 tables
+    BL* does not overwrite were recalled, not copied (params/turner2004_residual.par) -- this shows they are not the
+    reason: shifting EVERY entry of any one of them by +-0.3 kcal/mol moves the value by less than 4 %, while it would
+    have to drop by more than 21 %."""
+    import numpy as np
+    from oracle.oracle import Oracle
+    from ractip_b200 import default_model
+    s = bundled["sequences"]["DIS"]
+
+    def window(m):
+        return float(Oracle(m).rnafold(s, 15)[1][10][12])
+
+    base = window(default_model())
+    assert 0.0037 < base < 0.0039
+    worst = 0.0
+    for name in ("mismatchExt37", "mismatchM37", "mismatch1nI37", "mismatch23I37", "Triloop37", "Hexaloop37"):
+        for delta in (-30, 30):
+            m = default_model()
+            np.frombuffer(getattr(m, name), dtype=np.int32)[:] += delta
+            worst = max(worst, abs(window(m) / base - 1.0))
+    for name in ("lxc37", "DuplexInit37"):
+        for delta in (-30, 30):
+            m = default_model()
+            setattr(m, name, getattr(m, name) + delta)
+            worst = max(worst, abs(window(m) / base - 1.0))
+    assert worst < 0.04
