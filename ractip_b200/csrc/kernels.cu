@@ -366,93 +366,116 @@ __global__ void __launch_bounds__(256) duplex_kernel(BatchDev b) {
 // ---------------------------------------------------------------------------
 // thresholded records in the reference's variable-creation order
 // (src/ractip.cpp:557-567 for x/y: j ascending, i descending; :598-609 for z:
-// i ascending, j ascending).  One warp per list: ballot + popcount keeps order.
+// i ascending, j ascending; :619-628,639-648 for v/w: start ascending, length ascending).
+// One CTA per (pair, list).  The scan order of a list is a flat index k; every thread takes a contiguous range of
+// k, counts its hits (pass 1), the CTA turns the counts into offsets, and the thread writes its hits in place
+// (pass 2) -- the order is the scan order whatever the thread count, and the loads of a range are independent.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(160) sparse_kernel(SparseDev s) {
-  const int pair = blockIdx.x;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const SparsePair sp = s.pairs[pair];
-  int count = 0, overflow = 0;
-  if (warp < 2) {
-    const int L = warp == 0 ? sp.n1 : sp.n2;
-    const float* bp = s.dense + (warp == 0 ? sp.bp1 : sp.bp2);
-    rp_rec* out = s.recs + (warp == 0 ? sp.x : sp.y);
-    const int cap = warp == 0 ? sp.cap_x : sp.cap_y;
-    // scan order: j = 1..L-1 (0-based), i = j-1..0  -> linear index within column j
-    for (int j = 1; j < L; j++) {
-      for (int i0 = j - 1; i0 >= 0; i0 -= 32) {
-        const int i = i0 - lane;
-        float p = 0.f;
-        bool hit = false;
-        if (i >= 0) {
-          const int I = i + 1, J = j + 1;
-          p = bp[(size_t)I * (2 * L + 1 - I) / 2 + J];
-          hit = p > s.th_ss;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-          const int pos = count + __popc(m & ((1u << lane) - 1));
-          if (pos < cap) { out[pos].i = i; out[pos].j = j; out[pos].p = p; }
-        }
-        count += __popc(m);
-      }
-    }
-    if (count > cap) overflow = 1;
-  } else if (warp >= 3) {
-    // accessible regions (src/ractip.cpp:619-628 v, :639-648 w): start i ascending, length index j ascending
-    const int L = warp == 3 ? sp.n1 : sp.n2;
-    const float* up = s.dense + (warp == 3 ? sp.up1_src : sp.up2_src);
-    rp_rec* out = s.recs + (warp == 3 ? sp.v : sp.w);
-    const int cap = warp == 3 ? sp.cap_v : sp.cap_w;
-    const int j0 = s.min_w - 1, nj = cap > 0 ? s.max_w - j0 : 0;   // cap == 0: accessibility is off, no variables
-    const int total = nj > 0 ? L * nj : 0;
-    for (int x0 = 0; x0 < total; x0 += 32) {
-      const int x = x0 + lane;
-      float p = 0.f;
-      bool hit = false;
-      int i = 0, j = 0;
-      if (x < total) {
-        i = x / nj; j = j0 + x % nj;
-        p = up[(size_t)i * s.max_w + j];
-        hit = p > s.th_ac;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = count + __popc(m & ((1u << lane) - 1));
-        if (pos < cap) { out[pos].i = i; out[pos].j = j; out[pos].p = p; }
-      }
-      count += __popc(m);
-    }
-    if (count > cap) overflow = 1;
-  } else {
-    const float* hp = s.dense + sp.hp;
-    rp_rec* out = s.recs + sp.z;
-    const int total = sp.n1 * sp.n2;
-    for (int x0 = 0; x0 < total; x0 += 32) {
-      const int x = x0 + lane;
-      float p = 0.f;
-      bool hit = false;
-      int i = 0, j = 0;
-      if (x < total) {
-        i = x / sp.n2; j = x % sp.n2;
-        p = hp[(size_t)(i + 1) * (sp.n2 + 1) + (j + 1)];
-        hit = p > s.th_hy;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = count + __popc(m & ((1u << lane) - 1));
-        if (pos < sp.cap_z) { out[pos].i = i; out[pos].j = j; out[pos].p = p; }
-      }
-      count += __popc(m);
-    }
-    if (count > sp.cap_z) overflow = 1;
+constexpr int RP_SPARSE_THREADS = 128;
+struct SparseList {
+  int kind;            // 0 x, 1 y, 2 z, 3 v, 4 w
+  const float* src;
+  int L, n2, nj, j0, max_w;
+  float th;
+};
+// element k of the scan: (i, j) as stored in the record, and its probability
+__device__ __forceinline__ float sparse_at(const SparseList& q, int cj, int ci, int k, int& ri, int& rj) {
+  if (q.kind < 2) {          // (column cj, row ci), both 0-based, ci < cj
+    ri = ci; rj = cj;
+    const int I = ci + 1, J = cj + 1;
+    return q.src[(size_t)I * (2 * q.L + 1 - I) / 2 + J];
   }
-  if (lane == 0) {
+  if (q.kind == 2) {
+    ri = k / q.n2; rj = k - ri * q.n2;
+    return q.src[(size_t)(ri + 1) * (q.n2 + 1) + (rj + 1)];
+  }
+  ri = k / q.nj; rj = q.j0 + (k - ri * q.nj);
+  return q.src[(size_t)ri * q.max_w + rj];
+}
+__global__ void __launch_bounds__(RP_SPARSE_THREADS) sparse_kernel(SparseDev s) {
+  __shared__ int s_cnt[RP_SPARSE_THREADS];
+  const int pair = blockIdx.x, kind = blockIdx.y, tid = threadIdx.x, T = RP_SPARSE_THREADS;
+  const SparsePair sp = s.pairs[pair];
+  SparseList q;
+  q.kind = kind;
+  rp_rec* out;
+  int cap, total;
+  if (kind < 2) {
+    q.L = kind == 0 ? sp.n1 : sp.n2;
+    q.src = s.dense + (kind == 0 ? sp.bp1 : sp.bp2);
+    q.th = s.th_ss;
+    out = s.recs + (kind == 0 ? sp.x : sp.y);
+    cap = kind == 0 ? sp.cap_x : sp.cap_y;
+    total = q.L * (q.L - 1) / 2;
+  } else if (kind == 2) {
+    q.n2 = sp.n2;
+    q.src = s.dense + sp.hp;
+    q.th = s.th_hy;
+    out = s.recs + sp.z;
+    cap = sp.cap_z;
+    total = sp.n1 * sp.n2;
+  } else {
+    q.L = kind == 3 ? sp.n1 : sp.n2;
+    q.src = s.dense + (kind == 3 ? sp.up1_src : sp.up2_src);
+    q.th = s.th_ac;
+    out = s.recs + (kind == 3 ? sp.v : sp.w);
+    cap = kind == 3 ? sp.cap_v : sp.cap_w;
+    q.j0 = s.min_w - 1;
+    q.max_w = s.max_w;
+    q.nj = cap > 0 ? s.max_w - q.j0 : 0;   // cap == 0: accessibility is off, no variables
+    total = q.nj > 0 ? q.L * q.nj : 0;
+  }
+  const int per = (total + T - 1) / T;
+  const int k0 = tid * per < total ? tid * per : total, k1 = k0 + per < total ? k0 + per : total;
+  // x / y: column of k0 (column cj holds the cj scan positions cj(cj-1)/2 .. ; rows cj-1 down to 0)
+  int cj0 = 1, ci0 = 0;
+  if (kind < 2 && k0 < k1) {
+    cj0 = (int)((1.0 + sqrt(1.0 + 8.0 * (double)k0)) * 0.5);
+    while (cj0 * (cj0 - 1) / 2 > k0) cj0--;
+    while ((cj0 + 1) * cj0 / 2 <= k0) cj0++;
+    ci0 = cj0 - 1 - (k0 - cj0 * (cj0 - 1) / 2);
+  }
+  int mine = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int pos = 0;
+    if (pass == 1) {
+      __syncthreads();
+      for (int t = 0; t < tid; t++) pos += s_cnt[t];
+    }
+    int cj = cj0, ci = ci0, n = 0;
+    for (int k = k0; k < k1; k += 4) {   // four independent loads per round trip
+      float p[4];
+      int ri[4], rj[4];
+      int tj = cj, ti = ci;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        p[u] = 0.f; ri[u] = rj[u] = 0;
+        if (k + u < k1) {
+          p[u] = sparse_at(q, tj, ti, k + u, ri[u], rj[u]);
+          if (--ti < 0) { tj++; ti = tj - 1; }
+        }
+      }
+      cj = tj; ci = ti;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (k + u < k1 && p[u] > q.th) {
+          if (pass == 1 && pos + n < cap) { out[pos + n].i = ri[u]; out[pos + n].j = rj[u]; out[pos + n].p = p[u]; }
+          n++;
+        }
+      }
+    }
+    if (pass == 0) { mine = n; s_cnt[tid] = n; }
+  }
+  (void)mine;
+  if (tid == T - 1) {
+    int count = 0;
+    for (int t = 0; t < T; t++) count += s_cnt[t];
     int* cnt = reinterpret_cast<int*>(&s.counts[pair]);   // {n_x, n_y, n_z, overflow, n_v, n_w}
-    cnt[warp < 3 ? warp : warp + 1] = count;
-    if (overflow) atomicOr(&cnt[3], 1);
+    cnt[kind < 3 ? kind : kind + 1] = count;
+    if (count > cap) atomicOr(&cnt[3], 1);
   }
 }
+
 
 // gather the up sections of the dense buffer into the compact float buffer
 __global__ void gather_up_kernel(SparseDev s) {
@@ -574,7 +597,7 @@ cudaError_t launch_duplex(const BatchDev& b, int grid, cudaStream_t st) {
 }
 
 cudaError_t launch_sparse(const SparseDev& s, int n_pairs, bool with_ups, cudaStream_t st) {
-  sparse_kernel<<<n_pairs, 160, 0, st>>>(s);
+  sparse_kernel<<<dim3(n_pairs, 5), RP_SPARSE_THREADS, 0, st>>>(s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !with_ups) return e;
   gather_up_kernel<<<n_pairs, 256, 0, st>>>(s);
