@@ -251,6 +251,11 @@ typedef struct rp_timing {
   float ms_h2d, ms_d2h;/* 0 for rp_batch_run                                 */
   int kernel_launches; /* kernels launched by the call                       */
   double alg_flops;    /* dense algorithmic flops (SURVEY 8d F_pair summed)  */
+  /* the launch that carries most of those flops, timed by itself (events around it on its stream):
+   * 0 = band kernel, long class (<512,1>), 1 = band kernel, short class (<256,2>), 2 = general kernel */
+  int dominant_kind;
+  float ms_dominant;
+  double alg_flops_dominant;   /* F_mcc summed over the problems of that launch */
 } rp_timing;
 int rp_last_timing(const rp_ctx* ctx, rp_timing* t);
 

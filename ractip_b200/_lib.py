@@ -90,7 +90,8 @@ class RpIpOpts(C.Structure):
 
 class RpTiming(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-                ("kernel_launches", C.c_int), ("alg_flops", C.c_double)]
+                ("kernel_launches", C.c_int), ("alg_flops", C.c_double),
+                ("dominant_kind", C.c_int), ("ms_dominant", C.c_float), ("alg_flops_dominant", C.c_double)]
 
 
 # every symbol include/ractip_prob.h declares (tests check the .so exports all)

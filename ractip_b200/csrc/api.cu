@@ -46,6 +46,8 @@ struct rp_ctx {
   cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
+  cudaEvent_t ev_dom[2] = {};   // around the launch that carries most of the algorithmic flops (rp_timing::ms_dominant)
+  bool dom_timed = false;
   double* ws = nullptr;       // workspace slots (grow-only)
   size_t ws_bytes = 0;
   rp_timing timing = {};
@@ -107,6 +109,8 @@ struct rp_batch {
   int* d_done = nullptr;      // completion flags of the deferred problems (indexed by problem)
   int up_mode = 0;            // 0: pass fused with the wavefronts, 1: unstru_kernel after them, 2: jobs of their own inside the band kernel
   int up_grid = -1;
+  int dom_kind = -1;          // launch with the largest share of the algorithmic flops: 0 / 1 band class, 2 general
+  double dom_flops = 0;
   bool has_single = false;              // some pair has n2 == 0: its unused output sections are zero-filled once
   cudaStream_t last_stream = nullptr;   // stream the batch last ran on (rp_set_stream may have moved the context on)
   rp::SparsePair* d_spairs = nullptr;
@@ -397,6 +401,8 @@ int rp_create(rp_ctx** out, const rp_model* m, int device) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
+  for (auto& ev : ctx->ev_dom)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMalloc(&ctx->d_model, sizeof(rp::DevModel))) != cudaSuccess) return bail(RP_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMemcpy(ctx->d_model, host.data(), sizeof(rp::DevModel), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail(RP_ERR_CUDA, cudaGetErrorString(e));
@@ -429,6 +435,8 @@ int rp_destroy(rp_ctx* ctx) {
   if (ctx->d_model) cudaFree(ctx->d_model);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_dom)
     if (ev) cudaEventDestroy(ev);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -787,6 +795,26 @@ int rp_batch_run(rp_batch* b) {
     CU(cudaMemsetAsync(d_prof, 0, 64 * sizeof(long long), ctx->stream));
     d.prof = d_prof;
   }
+  if (b->dom_kind < 0) {   // which launch carries most of the algorithmic flops (timed by itself for the roofline)
+    double f[3] = {0, 0, 0};
+    int off = 0;
+    for (int k = 0; k < 3; k++) {
+      const int cnt = k < 2 ? b->n_band[k] : b->n_general;
+      for (int x = off; x < off + cnt; x++) {
+        if (b->order[x] & rp::RP_JOB_UNPAIRED) continue;   // (an unpaired-window job carries no credited flops)
+        const Problem& q = b->probs[b->order[x]];
+        if (q.kind != rp::KIND_DUPLEX) f[k] += rp_alg_flops_mcc(q.n);
+      }
+      off += cnt;
+    }
+    b->dom_kind = f[0] >= f[1] && f[0] >= f[2] ? 0 : (f[1] >= f[2] ? 1 : 2);
+    b->dom_flops = f[b->dom_kind];
+    if (b->dom_flops <= 0) b->dom_kind = 3;   // nothing to time
+  }
+  ctx->dom_timed = false;
+  ctx->timing.dominant_kind = b->dom_kind < 3 ? b->dom_kind : -1;
+  ctx->timing.alg_flops_dominant = b->dom_flops;
+  ctx->timing.ms_dominant = 0;
   cudaStream_t st = ctx->stream;
   b->last_stream = st;
   ctx->ws_stream = st;
@@ -809,7 +837,9 @@ int rp_batch_run(rp_batch* b) {
           CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
           ls = ctx->side_stream;
         }
+        if (b->dom_kind == k) CU(cudaEventRecord(ctx->ev_dom[0], ls));
         CU(rp::launch_band(db, b->band_grid[k], band_threads[k], band_smem[k], ls));
+        if (b->dom_kind == k) { CU(cudaEventRecord(ctx->ev_dom[1], ls)); ctx->dom_timed = true; }
         if (k == 0 && b->split_fetch) CU(cudaEventRecord(ctx->ev_main, st));   // the long class's outputs are final here
         if (ls != st) {                 // join before anything else of the batch runs
           CU(cudaEventRecord(ctx->ev_join, ls));
@@ -842,6 +872,7 @@ int rp_batch_run(rp_batch* b) {
     else if (b->n_mcc * 8 <= ctx->sm_count * (b->mcc_minb == 1 ? 5 : 4)) G = 8;   // up to 4-5 rounds of clusters (20 pairs of 400 x 300: 87 -> 56 ms; 40 pairs: 93 vs 106 ms)
     // a cluster shape the device (or its current partitioning) cannot schedule fails at launch, before
     // anything ran: fall back to the smaller cluster, then to one CTA per problem
+    if (b->dom_kind == 2) CU(cudaEventRecord(ctx->ev_dom[0], st));
     bool launched = false;
     for (; G && !launched; G = G == 16 ? 8 : 0) {
       const int ncl = std::max(1, std::min({b->n_mcc, grid, ctx->sm_count / G}));
@@ -849,6 +880,7 @@ int rp_batch_run(rp_batch* b) {
       else cudaGetLastError();
     }
     if (!launched) CU(rp::launch_mcc(d, grid, ctx->threads, b->mcc_minb, ctx->mcc_wide, st));
+    if (b->dom_kind == 2) { CU(cudaEventRecord(ctx->ev_dom[1], st)); ctx->dom_timed = true; }
     launches++;
   }
   if (b->n_duplex > 0) {
@@ -1014,6 +1046,10 @@ int rp_last_timing(const rp_ctx* cctx, rp_timing* t) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->timing.ms_total = ms;
+    if (ctx->dom_timed) {
+      CU(cudaEventElapsedTime(&ms, ctx->ev_dom[0], ctx->ev_dom[1]));
+      ctx->timing.ms_dominant = ms;
+    }
     if (ctx->timed_copies) {
       CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
       ctx->timing.ms_d2h = ms;
