@@ -187,6 +187,17 @@ __device__ __forceinline__ void outside_band_A_shfl(const Ctx& c, const Shared& 
   for (int e = 0; e < BAND; e++) pr[e] = ml[e] = 0.;
   long long tmark = (RP_PROF(c) && tid == 0) ? clock64() : 0;
   if (!(RP_DBG(c) & 2)) {
+    {  // the qb entries the ML part asks for below were written a whole pass ago: start them towards the L2 now
+      // (a prefetch holds no register and no scoreboard slot, unlike the loads themselves)
+      const int l = d0 - BAND + 2 + r, k0 = l - d0;
+      if (own && l <= n) {
+#pragma unroll
+        for (int e = 0; e < BAND; e++) {
+          const int k = k0 + e, d = d0 - e;
+          if (k > 2 && d > TURN) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.ptr(T_QB, d, k)));
+        }
+      }
+    }
     {  // PR, row k; t = j - (k+d0+TURN+3)
       const int k = 1 + r;
       const int tmax = n - k - d0 - (TURN + 3);   // decreases along the lanes: a lane past its tmax feeds zeros
