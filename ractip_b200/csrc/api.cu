@@ -615,9 +615,11 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
     const size_t slot = up.empty() ? 0 : rp::slot_doubles(maxn);
     int mode = 0;
     if (!up.empty() && (double)slot * sizeof(double) * up.size() <= 24e9) {
-      // (measured, MicA x ompA shuffles, fused / own launch: 125 pairs 5.15 / 5.90 ms, 500 pairs 19.5 / 19.8, 1000 pairs 39.0 / 38.1)
-      if ((int)up.size() >= 10 * ctx->sm_count && ctx->up_ctas_per_sm > 0) mode = 1;
-      else if (b->n_band[0] + b->n_band[1] >= 4 * ctx->sm_count) mode = 2;   // (jobs of their own / fused: 125 pairs 5.34 / 5.15 ms, 250 pairs 9.85 / 10.27, 500 pairs 19.2 / 19.6)
+      // (measured, MicA x ompA shuffles, kernel ms fused / own launch / jobs of their own: 125 pairs 5.09 / 5.13 / 5.29,
+      //  180 pairs 7.70 / 8.05 / 7.15, 250 pairs 10.40 / 9.89 / 9.83, 350 pairs 13.94 / 13.34 / 13.45, 500 pairs - / 18.3 / 19.1,
+      //  1000 pairs 39.0 / 36.2 / -)
+      if (2 * (int)up.size() >= 9 * ctx->sm_count && ctx->up_ctas_per_sm > 0) mode = 1;
+      else if (b->n_band[0] + b->n_band[1] >= 3 * ctx->sm_count) mode = 2;
       if (e) mode = std::atoi(e);
     }
     b->up_mode = mode;

@@ -176,12 +176,14 @@ __global__ void __launch_bounds__(T, MINB) mcc_band_kernel(BatchDev b) {
 }
 
 // unstru_kernel: the unpaired-window pass (pf_unstru, src/ractip.cpp:371-375) of the single-strand problems the
-// band kernel has finished, as a launch of its own.  The pass needs no shared-memory ring and is bound by the
-// latency of its table walks through L2, so it runs with small CTAs, several per SM (the band kernel's shape --
-// one 512-thread CTA per SM because of the ring -- keeps only 16 warps in flight).  Each problem's tables sit in
-// its private workspace (Problem::ws_off).
-constexpr int RP_UP_THREADS = 256;
-__global__ void __launch_bounds__(RP_UP_THREADS, 3) unstru_kernel(BatchDev b) {
+// band kernel has finished, as a launch of its own.  The pass needs no shared-memory ring and is bound by its
+// table walks, every table several times: ONE 768-thread CTA per SM (80 registers) keeps 24 warps in flight -- the
+// band kernel's shape allows 16 -- and 148 problems' tables (about 1 MB each) resident, which the 126 MB L2 nearly
+// holds; three 256-thread CTAs per SM have the same warps but three times the resident problems, and every re-read
+// of a table goes to DRAM (38.1 against 36.2 ms per 1000-pair step; 512 x 1: 36.9, 1024 x 1 at 64 registers: 36.4,
+// 256 x 2: 39.0, 128 x 6: 41.5).  Each problem's tables sit in its private workspace (Problem::ws_off).
+constexpr int RP_UP_THREADS = 768;
+__global__ void __launch_bounds__(RP_UP_THREADS, 1) unstru_kernel(BatchDev b) {
   __shared__ int s_next;
   __shared__ double s_gfull[(MAXLOOP + 1) * GROW_LD];
   __shared__ uint8_t s_seq[RP_SMEM_SEQ + 8];
