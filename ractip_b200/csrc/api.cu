@@ -597,11 +597,11 @@ int rp_batch_create(rp_ctx* ctx, const rp_pair* pairs, int n_pairs, const rp_opt
   }
   b->n_general = (int)b->order.size() - b->n_band[0] - b->n_band[1];
   // Unpaired-window passes of the band classes, three ways:
-  //   mode 1 (large batches, >= 10 problems per SM): a launch of their own after the wavefront kernels (unstru_kernel:
-  //           small CTAs, three per SM -- the pass needs no shared-memory ring);
-  //   mode 2 (batches with at least four problems per SM): JOBS of their own in the band kernel's queue, after all
-  //           wavefront jobs, each waiting for its problem's completion flag -- finer jobs shorten the tail when there are
-  //           few problems per SM (125 MicA x ompA pairs: the per-GPU share at 8 GPUs);
+  //   mode 1 (large batches, >= 4.5 single-strand problems per SM): a launch of their own after the wavefront kernels
+  //           (unstru_kernel: one 768-thread CTA per SM -- the pass needs no shared-memory ring, and the tables of 148
+  //           resident problems stay in the L2);
+  //   mode 2 (batches with at least three problems per SM): JOBS of their own in the band kernel's queue, after all
+  //           wavefront jobs, each waiting for its problem's completion flag -- finer jobs shorten the tail;
   //   mode 0 (a handful of problems, or no room for private workspaces): fused with the wavefronts.
   // Modes 1 and 2 keep a deferred problem's tables in a private workspace.  RP_DEFER_UP=0/1/2 forces a mode.
   {
