@@ -16,7 +16,10 @@
 //     sliding 8-wide register window: one shared load + one weight per 8 DFMA;
 //   * rows are stored "mod-8 transposed" (position p at (p&7)*LD8 + (p>>3)), so
 //     the 16 lanes of a half-warp, which own 16 consecutive groups, read 16
-//     consecutive doubles: no bank conflicts although every lane strides by 8;
+//     consecutive doubles although every lane strides by 8 (conflict-free for the
+//     window walk; measured over the whole kernel, ncu: 0.23 G conflicts on 1.81 G
+//     shared-load wavefronts, 13 %, from the two half-warps of a warp working on
+//     different rows and from the per-cell finish / small-loop reads);
 //   * the sum is DENSE (cells that cannot pair are computed and multiplied by
 //     a zero closing factor): no compaction lists, no divergence;
 //   * the 31 rows are dealt out as 16 balanced row pairs (q, 30-q) = 16 slices;
