@@ -137,3 +137,40 @@ def test_front_end_matches_pair_by_pair_solve(stage, bundled, model):
         j = solve_joint(model, a.seq, b.seq, p, default_ip_opts(), energies=True)
         assert (r.joint.r1, r.joint.r2) == (j.r1, j.r2)
         assert abs(r.joint.e3 - j.e3) < 1e-6
+
+
+@pytest.mark.gpu
+def test_command_line_zscore(tmp_path, bundled, capsys):
+    """--zscore: the shuffles of src/ractip.cpp:1636-1657 as ONE more GPU batch; the printed statistic is reproducible
+    and follows zscore_statistic over the per-shuffle energies."""
+    from ractip_b200 import (ProbabilityStage, default_ip_opts, default_opts, solve_joint, solve_ss, zscore_shuffles,
+                             zscore_statistic)
+    from ractip_b200.__main__ import main
+    seqs = bundled["sequences"]
+    f = tmp_path / "p.fa"
+    f.write_text(f">Tar\n{seqs['Tar']}\n>Tarstar\n{seqs['Tarstar']}\n")
+    args = ["--zscore", "12", "--num-shuffling", "6", "--seed", "3", str(f)]
+    assert main(args) == 0
+    out1 = capsys.readouterr().out.strip().split("\n")
+    assert main(args) == 0
+    assert capsys.readouterr().out.strip().split("\n") == out1
+    assert out1[-1].startswith("z-score: ") and len(out1) == 7
+    # the same numbers by hand
+    st = ProbabilityStage()
+    try:
+        s1, s2 = seqs["Tar"], seqs["Tarstar"]
+        p = st.solve_probabilities(s1, s2, default_opts())
+        j = solve_joint(st.model, s1, s2, p, default_ip_opts(), energies=True)
+        e1s = solve_ss(st.model, s1, p.bp1, default_ip_opts(), energy=True)[2]
+        e2s = solve_ss(st.model, s2, p.bp2, default_ip_opts(), energy=True)[2]
+        r1, r2 = zscore_shuffles(s1, s2, 6, 3, 12)
+        rows = []
+        for a, b, q in zip(r1, r2, st.run_dense(list(zip(r1, r2)), default_opts())):
+            jj = solve_joint(st.model, a, b, q, default_ip_opts(), energies=True)
+            rows.append((jj.e1 + jj.e2 + jj.e3,
+                         solve_ss(st.model, a, q.bp1, default_ip_opts(), energy=True)[2] +
+                         solve_ss(st.model, b, q.bp2, default_ip_opts(), energy=True)[2]))
+        z = zscore_statistic(j.e1 + j.e2 + j.e3, e1s + e2s, rows)
+    finally:
+        st.close()
+    assert out1[-1] == "z-score: " + format(z[0], ".6g") + ", " + format(z[1], ".6g")
